@@ -1,0 +1,249 @@
+"""Generate golden input/output vectors by running the UNMODIFIED reference modules on the CPU.
+
+Run in the build container only (``python tests/golden/make_golden.py``): it needs /root/reference,
+which does not exist on the GPU box.  The resulting ``tests/golden/*.npz`` files are committed and are
+what the tests read.  Recipe: SURVEY.md Appendix B — a test-only ``pytorch_lightning`` shim (the
+package is not installed), identity encoders, ``Tensor.cuda`` patched to identity because
+existing_algos/QMF.py:63,66 hard-codes ``.cuda()``.
+"""
+import argparse
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = os.environ.get("LF_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def install_shims():
+    pl = types.ModuleType("pytorch_lightning")
+
+    class LightningModule(nn.Module):
+        automatic_optimization = True
+
+        def log(self, *a, **k):
+            pass
+
+        def optimizers(self):
+            return self._opt
+
+        def lr_schedulers(self):
+            return []
+
+        def manual_backward(self, loss):
+            loss.backward()
+
+    pl.LightningModule = LightningModule
+    pl.seed_everything = lambda s, workers=False: torch.manual_seed(s)
+    pl.loggers = types.ModuleType("pytorch_lightning.loggers")
+    pl.loggers.WandbLogger = object
+    pl.callbacks = types.SimpleNamespace(LearningRateMonitor=object, ModelCheckpoint=object)
+    sys.modules.update({"pytorch_lightning": pl, "pytorch_lightning.loggers": pl.loggers})
+    if "sympy" not in sys.modules:
+        try:
+            import sympy  # noqa: F401  (stray import at cremad/joint_model_qmf.py:1)
+        except Exception:
+            sy = types.ModuleType("sympy")
+            sy.Idx = object
+            sys.modules["sympy"] = sy
+    sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self      # CPU run of QMF.py:63,66
+
+
+def lin_init(C, D, g):
+    bound = 1.0 / np.sqrt(D)
+    W = (torch.rand(C, D, generator=g) * 2 - 1) * bound
+    b = (torch.rand(C, generator=g) * 2 - 1) * bound
+    return W, b
+
+
+def set_heads(net, W1, b1, W2, b2):
+    C, D = W1.shape
+    net.x1_classifier = nn.Linear(D, C)
+    net.x2_classifier = nn.Linear(D, C)
+    with torch.no_grad():
+        net.x1_classifier.weight.copy_(W1); net.x1_classifier.bias.copy_(b1)
+        net.x2_classifier.weight.copy_(W2); net.x2_classifier.bias.copy_(b2)
+
+
+def accs(z1, z2, avg, y, off, zdf=None):
+    f = lambda z: float(torch.mean((torch.argmax(z, dim=1) == y).float()))
+    out = {"acc_x1_uncal": f(z1), "acc_x2_uncal": f(z2), "acc_x1_cal": f(z1 + off[0]),
+           "acc_x2_cal": f(z2 + off[1]), "acc_joint": f(avg)}
+    if zdf is not None:
+        out["acc_df"] = f(zdf)
+    return out
+
+
+def golden_qmf(name, B, D, C, N, steps, seed, idx_mode="replacement", dtype=torch.float32):
+    """cremad/joint_model_qmf.FusionNet (identity encoders) + utils/EMA.EMA for ``steps`` steps with
+    fresh features each step, fixed weights; records every step's outputs and the History arrays."""
+    import cremad.joint_model_qmf as mq
+    from utils.EMA import EMA
+    mq.resnet18 = lambda modality: nn.Identity()
+    g = torch.Generator().manual_seed(seed)
+    W1, b1 = lin_init(C, D, g)
+    W2, b2 = lin_init(C, D, g)
+    net = mq.FusionNet(argparse.Namespace(num_classes=C, num_samples=N), nn.CrossEntropyLoss())
+    set_heads(net, W1, b1, W2, b2)
+    net = net.to(dtype)
+    ema = EMA(torch.zeros(2, C, dtype=dtype))
+    rec = {"W1": W1.numpy(), "b1": b1.numpy(), "W2": W2.numpy(), "b2": b2.numpy(),
+           "meta": np.array([B, D, C, N, steps], dtype=np.int64)}
+    for s in range(steps):
+        f1 = torch.randn(B, D, generator=g); f2 = torch.randn(B, D, generator=g)
+        y = torch.randint(0, C, (B,), generator=g, dtype=torch.int64)
+        if idx_mode == "replacement":
+            idx = torch.randint(0, N, (B,), generator=g, dtype=torch.int64)
+        else:
+            idx = (torch.arange(B, dtype=torch.int64) + s * B) % N
+        a = f1.to(dtype).view(B, D, 1, 1).requires_grad_(True)
+        v = f2.to(dtype).view(B, D, 1, 1).requires_grad_(True)
+        net.zero_grad()
+        z1, z2, avg, loss, zdf = net(a, v, y, idx)
+        loss.backward()
+        ema.update(torch.mean(torch.stack([z1, z2]), dim=1))
+        off = ema.offset
+        r = {"f1": f1, "f2": f2, "y": y, "idx": idx, "z1": z1, "z2": z2, "avg": avg, "zdf": zdf,
+             "loss": loss, "dW1": net.x1_classifier.weight.grad, "db1": net.x1_classifier.bias.grad,
+             "dW2": net.x2_classifier.weight.grad, "db2": net.x2_classifier.bias.grad,
+             "df1": a.grad.view(B, D), "df2": v.grad.view(B, D), "ema_x": ema.x, "ema_off": off}
+        for k, t in r.items():
+            rec[f"s{s}_{k}"] = t.detach().to(torch.float64 if dtype == torch.float64 and t.is_floating_point()
+                                             else t.dtype).numpy().copy()
+        for k, val in accs(z1.detach(), z2.detach(), avg.detach(), y, off, zdf.detach()).items():
+            rec[f"s{s}_{k}"] = np.float64(val)
+        rec[f"s{s}_corr"] = np.stack([h.correctness for h in net.qmf.history]).copy()
+        rec[f"s{s}_confid"] = np.stack([h.confidence for h in net.qmf.history]).copy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print("wrote", name, "loss(last) =", float(loss.detach()))
+
+
+def golden_ogm(name, B, D, C, steps, seed, alpha, enrico=False):
+    """cremad/joint_model_ogm_ge.FusionNet (or enrico/joint_model.FusionNet) + EMA + existing_algos.OGM_GE.ogm_ge
+    with modulation='OGM' on a stub encoder holding one Dirac 1x1 conv, so the coefficients can be read
+    back as grad_after/grad_before."""
+    from existing_algos.OGM_GE import ogm_ge
+    from utils.EMA import EMA
+    g = torch.Generator().manual_seed(seed)
+    W1, b1 = lin_init(C, D, g)
+    W2, b2 = lin_init(C, D, g)
+    if enrico:
+        import torchvision
+        import enrico.joint_model as ej
+        orig = torchvision.models.resnet18
+        ej.tmodels.resnet18 = lambda pretrained=True: orig(weights=None)
+        net = ej.FusionNet(C, nn.CrossEntropyLoss())
+        for xm, (W, b) in zip((net.x1_model, net.x2_model), ((W1, b1), (W2, b2))):
+            xm.model = nn.Identity()
+            xm.classifier = nn.Linear(D, C)
+            with torch.no_grad():
+                xm.classifier.weight.copy_(W); xm.classifier.bias.copy_(b)
+        heads = [net.x1_model.classifier, net.x2_model.classifier]
+    else:
+        import cremad.joint_model_ogm_ge as mo
+
+        def stub(modality):
+            # ogm_ge indexes str(name).split('.')[1] (existing_algos/OGM_GE.py:47): the parameter
+            # name needs a dot, so the conv sits inside a Sequential ("0.weight")
+            conv = nn.Conv2d(D, D, 1, bias=False)
+            with torch.no_grad():
+                nn.init.dirac_(conv.weight)
+            return nn.Sequential(conv)
+        mo.resnet18 = stub
+        net = mo.FusionNet(C, nn.CrossEntropyLoss())
+        set_heads(net, W1, b1, W2, b2)
+        heads = [net.x1_classifier, net.x2_classifier]
+    ema = EMA(torch.zeros(2, C))
+    rec = {"W1": W1.numpy(), "b1": b1.numpy(), "W2": W2.numpy(), "b2": b2.numpy(),
+           "meta": np.array([B, D, C, 0, steps], dtype=np.int64), "alpha": np.float64(alpha)}
+    for s in range(steps):
+        # a label-aligned signal in one modality per step makes both coefficient branches occur
+        f1 = torch.randn(B, D, generator=g); f2 = torch.randn(B, D, generator=g)
+        y = torch.randint(0, C, (B,), generator=g, dtype=torch.int64)
+        if s % 2 == 0:
+            f1 = f1 + 0.3 * W1[y] * np.sqrt(D)      # modality 1 informative -> score1 > score2
+        else:
+            f2 = f2 + 0.3 * W2[y] * np.sqrt(D)      # modality 2 informative -> score2 > score1
+        a = f1.clone().view(B, D, 1, 1).requires_grad_(True)
+        v = f2.clone().view(B, D, 1, 1).requires_grad_(True)
+        net.zero_grad()
+        z1, z2, avg, loss = net(a, v, y)
+        loss.backward()
+        ema.update(torch.mean(torch.stack([z1, z2]), dim=1))
+        off = ema.offset
+        r = {"f1": f1, "f2": f2, "y": y, "z1": z1, "z2": z2, "avg": avg, "loss": loss,
+             "dW1": heads[0].weight.grad, "db1": heads[0].bias.grad,
+             "dW2": heads[1].weight.grad, "db2": heads[1].bias.grad,
+             "ema_x": ema.x, "ema_off": off}
+        if not enrico:
+            r["df1"] = a.grad.view(B, D); r["df2"] = v.grad.view(B, D)
+            g1 = net.x1_model[0].weight.grad.clone(); g2 = net.x2_model[0].weight.grad.clone()
+            ogm_ge(net, z1, z2, y, alpha=alpha, modulation="OGM")
+            k1 = (net.x1_model[0].weight.grad.flatten() @ g1.flatten()) / (g1.flatten() @ g1.flatten())
+            k2 = (net.x2_model[0].weight.grad.flatten() @ g2.flatten()) / (g2.flatten() @ g2.flatten())
+            rec[f"s{s}_coeff"] = np.array([float(k1), float(k2)])
+        for k, t in r.items():
+            rec[f"s{s}_{k}"] = t.detach().numpy().copy()
+        for k, val in accs(z1.detach(), z2.detach(), avg.detach(), y, off).items():
+            rec[f"s{s}_{k}"] = np.float64(val)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print("wrote", name, "loss(last) =", float(loss.detach()))
+
+
+def golden_modulate(name, seed):
+    """existing_algos.OGM_GE.ogm_ge on a tiny encoder with 4-D and non-4-D parameters: which tensors are
+    touched, the scale, and (mode 'noise'/'OGM_GE') the noise moments relative to std(g)+1e-8."""
+    from existing_algos.OGM_GE import ogm_ge
+    g = torch.Generator().manual_seed(seed)
+
+    class Enc(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8))
+            self.layer1 = nn.Sequential(nn.Conv2d(8, 16, 3, bias=False), nn.BatchNorm2d(16))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.x1_model = Enc(); self.x2_model = Enc()
+
+    net = Net()
+    grads = {}
+    for n, p in net.named_parameters():
+        p.grad = torch.randn(p.shape, generator=g) * 1e-3
+        grads[n] = p.grad.clone()
+    B, C = 48, 6
+    z1 = torch.randn(B, C, generator=g) * 2; z2 = torch.randn(B, C, generator=g)
+    y = torch.randint(0, C, (B,), generator=g)
+    ogm_ge(net, z1, z2, y, alpha=0.8, modulation="OGM")
+    rec = {"z1": z1.numpy(), "z2": z2.numpy(), "y": y.numpy(), "alpha": np.float64(0.8)}
+    for n, p in net.named_parameters():
+        rec["before/" + n] = grads[n].numpy()
+        rec["after_OGM/" + n] = p.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print("wrote", name)
+
+
+if __name__ == "__main__":
+    install_shims()
+    torch.manual_seed(5)
+    # K2: Crema-D QMF, B=64 D=512 C=6, sampling with replacement (duplicates), 4 steps of history
+    golden_qmf("qmf_cremad_b64", B=64, D=512, C=6, N=997, steps=3, seed=5)
+    # ragged / odd sizes, contiguous idx windows (Food101-style loader), C not a multiple of anything
+    golden_qmf("qmf_small_c11", B=37, D=64, C=11, N=101, steps=3, seed=7, idx_mode="contiguous")
+    # wide head, Food101 class count (smaller batch so the (B,B) reference stays small)
+    golden_qmf("qmf_food_c101", B=40, D=256, C=101, N=500, steps=2, seed=11)
+    golden_qmf("qmf_d768_c7", B=8, D=768, C=7, N=64, steps=2, seed=29)
+    # minimum legal batch for reg_loss
+    golden_qmf("qmf_b2", B=2, D=32, C=3, N=5, steps=3, seed=13)
+    # K3-shaped OGM-GE heads (small batch: the reference score loop is O(B^2 C))
+    golden_ogm("ogm_cremad_b48", B=48, D=512, C=6, steps=3, seed=5, alpha=0.8)
+    golden_ogm("ogm_wide_c309", B=40, D=128, C=309, steps=2, seed=17, alpha=0.8)
+    # K1: Enrico jlogits, B=32 D=512 C=20 (frozen encoders: no dfeat)
+    golden_ogm("jlogits_enrico_b32", B=32, D=512, C=20, steps=2, seed=19, alpha=0.1, enrico=True)
+    golden_modulate("ogm_modulate_small", seed=23)
