@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — fusion-step train samples/s on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload k4] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the fused late-fusion training step (heads -> fusion -> losses -> backward ->
+EMA / QMF History / OGM-GE coefficients [-> OGM-GE modulation]) over one batch of synthetic features.
+Workloads are the BASELINE.json configs; the default, k4, is the Food101 QMF shape
+named by the north-star target.  Scaling is weak: every GPU holds the config's batch, all statistics and
+gradients are global-batch quantities (all-reduce / all-gather inside the step).
+
+Rank 0 prints ONE JSON line (contract in the task description): `value` = device-resident throughput,
+`e2e` = same metric through the public Python API with pinned-host inputs copied H2D and the loss read
+back D2H every step, `roofline` = dominant kernel's algorithmic bytes / its CUDA-event time vs the
+measured HBM peak, `cpu_baseline` = the CPU oracle port timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+# name: (head mode, per-GPU batch, D, C, History length N, OGM alpha, need_dfeat, modulate encoder grads)
+WORKLOADS = {
+    "k1": dict(desc="Enrico joint_model late fusion, 512-d, 20 classes, batch 32 (frozen encoders)",
+               mode="jlogits", B=32, D=512, C=20, N=None, alpha=None, dfeat=False, modulate=False),
+    "k2": dict(desc="Crema-D joint_model_qmf, 512-d, 6 classes, batch 64",
+               mode="qmf", B=64, D=512, C=6, N=6698, alpha=None, dfeat=True, modulate=False),
+    "k3": dict(desc="Crema-D joint_model_ogm_ge, 512-d, 6 classes, batch 8192/GPU, OGM_GE modulation of 2x ResNet18 conv grads",
+               mode="jlogits", B=8192, D=512, C=6, N=None, alpha=0.8, dfeat=True, modulate=True),
+    "k4": dict(desc="Food101 joint_model_qmf, SigLIP 768-d, 101 classes, batch 32768/GPU",
+               mode="qmf", B=32768, D=768, C=101, N=65536, alpha=None, dfeat=True, modulate=False),
+    "k5": dict(desc="VGGSound-shape OGM-GE + EMA heads, 512-d, 309 classes, batch 131072/GPU",
+               mode="jlogits", B=131072, D=512, C=309, N=None, alpha=0.8, dfeat=True, modulate=False),
+}
+L2_BYTES = 126 * 1024 * 1024
+
+# ResNet18 conv weight shapes (audio 1-channel stem; the visual stem has 3 channels) — the 4-D tensors
+# existing_algos/OGM_GE.py:44 selects; 20 tensors, 11.16 M elements per encoder
+def resnet18_conv_shapes(in_ch):
+    s = [(64, in_ch, 7, 7)]
+    for cin, cout, down in ((64, 64, False), (64, 128, True), (128, 256, True), (256, 512, True)):
+        s += [(cout, cin, 3, 3), (cout, cout, 3, 3)]
+        if down:
+            s += [(cout, cin, 1, 1)]
+        s += [(cout, cout, 3, 3), (cout, cout, 3, 3)]
+    return s
+
+
+def step_alg_bytes_per_sample(w):
+    """SURVEY.md §8(d) algorithmic bytes per sample (fp32): read f, write df, write the returned logits,
+    label (+idx).  The QMF step is two-pass by construction (mid-step global dependency), so it adds one
+    more read of f (§8d: 'a two-pass design must report +M*D*4')."""
+    M, D, C = 2, w["D"], w["C"]
+    n_out = 4 if w["mode"] == "qmf" else 3
+    b = M * D * 4 + (M * D * 4 if w["dfeat"] else 0) + n_out * C * 4 + 8
+    if w["mode"] == "qmf":
+        b += 8 + M * D * 4
+    return b
+
+
+def kernel_alg_bytes(name, w, B):
+    """Algorithmic HBM bytes of ONE launch of kernel `name` (inputs read once + outputs written once)."""
+    D, C = w["D"], w["C"]
+    f = 4
+    table = {
+        "sgemm_logits": 2 * (B * D + C * D + C + B * C) * f,
+        "rows_forward_qmf": (2 * B * C + 2 * B * C + 2 * B + 4 * B) * f + 8 * B,
+        "rows_forward_jlogits": (2 * B * C + 2 * B * C) * f + 8 * B,
+        "rows_backward_qmf": (2 * B * C + 2 * B * C + 8 * B) * f + 8 * B,
+        "rows_calibrated": 2 * B * C * f + 8 * B,
+        "sgemm_dfeat": ((2 if w["mode"] == "qmf" else 1) * B * C + 2 * C * D + 2 * B * D) * f,
+        "sgemm_dweight": ((2 if w["mode"] == "qmf" else 1) * B * C + 2 * B * D) * f,
+        "modulate_stats": 11_160_000 * f,
+        "modulate_apply": 2 * 11_160_000 * f,
+    }
+    return table.get(name)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.25] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_batches(w, n_sets, device, seed):
+    g = torch.Generator().manual_seed(seed)
+    sets = []
+    for _ in range(n_sets):
+        B, D, C = w["B"], w["D"], w["C"]
+        s = {"f1": torch.randn(B, D, generator=g), "f2": torch.randn(B, D, generator=g),
+             "y": torch.randint(0, C, (B,), generator=g, dtype=torch.int64)}
+        if w["N"]:
+            s["idx"] = torch.randint(0, w["N"], (B,), generator=g, dtype=torch.int64) if w["B"] <= 8192 else \
+                (torch.arange(B, dtype=torch.int64) + int(torch.randint(0, w["N"], (1,), generator=g))) % w["N"]
+        sets.append(s)
+    return sets
+
+
+def head_params(w, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    bound = 1.0 / (w["D"] ** 0.5)
+    mk = lambda *s: (torch.rand(*s, generator=g) * 2 - 1) * bound
+    return [mk(w["C"], w["D"]), mk(w["C"], w["D"])], [mk(w["C"]), mk(w["C"])]
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, w, rank, world):
+    """Reference arm: the reference's CPU implementation of the path.  /root/reference is a pure-Python
+    package that does not exist on the GPU box, so this times the oracle port (oracle/late_fusion.py:
+    the same torch CPU ops as the reference's modules, closed-form reg_loss) on all host cores."""
+    if rank != 0:
+        return
+    from oracle import late_fusion as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    Bs = w["B"]
+    W, b = head_params(w)
+    sets = make_batches(dict(w, B=Bs), 2, "cpu", seed=7)
+    hist = O.HistoryState(w["N"]) if w["N"] else None
+    ema = torch.zeros(2, w["C"])
+
+    def one(i):
+        nonlocal ema
+        s = sets[i % len(sets)]
+        if w["mode"] == "qmf":
+            r = O.qmf_step([s["f1"], s["f2"]], W, b, s["y"], s["idx"], hist, ema_x=ema, feat_grad=w["dfeat"])
+        else:
+            r = O.jlogits_step([s["f1"], s["f2"]], W, b, s["y"], ema_x=ema, feat_grad=w["dfeat"])
+            if w["alpha"]:
+                O.ogm_coeffs(r["score1"], r["score2"], w["alpha"])
+        ema = r["ema_x"]
+        return float(r["loss"])
+
+    for i in range(max(1, min(args.warmup, 3))):
+        one(i)
+    steps = args.steps
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    val = Bs * steps / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": "fusion_step_train_samples_per_sec", "value": val, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(w, args, 1),
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} full-batch steps (B={Bs}) of the oracle port on {cores} host threads"},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w, args, world):
+    return {"workload": f"{args.workload}: {w['desc']}", "head": w["mode"], "batch_per_gpu": w["B"],
+            "global_batch": w["B"] * world, "feature_dim": w["D"], "classes": w["C"], "history_len": w["N"],
+            "precision": args.precision, "parallelism": f"dp{world}",
+            "l2": "inputs rotate over buffer sets totalling > 126 MB L2 (or a single set already larger)"}
+
+
+def cpu_baseline(w, budget_s=20.0):
+    from oracle import late_fusion as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    W, b = head_params(w)
+    s = make_batches(w, 1, "cpu", seed=7)[0]
+    hist = O.HistoryState(w["N"]) if w["N"] else None
+    ema = torch.zeros(2, w["C"])
+
+    def one():
+        if w["mode"] == "qmf":
+            return O.qmf_step([s["f1"], s["f2"]], W, b, s["y"], s["idx"], hist, ema_x=ema, feat_grad=w["dfeat"])
+        return O.jlogits_step([s["f1"], s["f2"]], W, b, s["y"], ema_x=ema, feat_grad=w["dfeat"])
+
+    one()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        one(); n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 200:
+            break
+    cores = torch.get_num_threads()
+    return {"value": w["B"] * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n} full-batch steps (B={w['B']}) of oracle/late_fusion.py (torch CPU fp32) in {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="k4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    w = WORKLOADS[args.workload]
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from multimodal_clinical_b200 import _lib
+    from multimodal_clinical_b200.step import LateFusionStep
+    lib = _lib.load()
+
+    eng = LateFusionStep(w["C"], mode=w["mode"], n_data=w["N"], device=dev, precision=args.precision)
+    W, b = head_params(w)
+    W = [x.to(dev) for x in W]; b = [x.to(dev) for x in b]
+    in_bytes = 2 * w["B"] * w["D"] * 4
+    n_sets = max(2, min(1024, -(-2 * L2_BYTES // in_bytes)))
+    host_sets = make_batches(w, n_sets, dev, seed=100 + rank)
+    dev_sets = [{k: v.to(dev) for k, v in s.items()} for s in host_sets]
+    enc_grads = None
+    if w["modulate"]:
+        enc_grads = [[torch.randn(s, device=dev) * 1e-3 for s in resnet18_conv_shapes(c)] for c in (1, 3)]
+
+    def one_step(s, i):
+        out = eng.step([s["f1"], s["f2"]], W, b, s["y"], idx=s.get("idx"), need_dfeat=w["dfeat"], ogm_alpha=w["alpha"])
+        if enc_grads is not None:
+            for m in range(2):
+                eng.modulate(enc_grads[m], which=m, modulation="OGM_GE", seed=5, offset=i * (1 << 24))
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (value)
+    for i in range(args.warmup):
+        one_step(dev_sets[i % n_sets], i)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    c0 = clocks.mark() if clocks else 0
+    l0 = lib.lf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one_step(dev_sets[i % n_sets], i)
+    e1.record()
+    barrier()
+    launches = lib.lf_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    c1 = clocks.mark() if clocks else 0
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clk = clocks.stop(c0, c1) if clocks else None
+    value = w["B"] * world * args.steps / (ms * 1e-3)
+
+    # ---------------- per-kernel CUDA-event timing of the same steps -> roofline of the dominant kernel
+    lib.lf_profile_enable(1)
+    for i in range(args.steps):
+        one_step(dev_sets[i % n_sets], i)
+    prof = _lib.profile_report()
+    lib.lf_profile_enable(0)
+
+    # ---------------- end-to-end through the public API with pinned host inputs (e2e)
+    pinned = [{k: v.pin_memory() for k, v in s.items()} for s in host_sets[:min(n_sets, 4)]]
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host_sets[0].items()}
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+
+    def e2e_step(i):
+        p = pinned[i % len(pinned)]
+        for k in stage:
+            stage[k].copy_(p[k], non_blocking=True)
+        out = one_step(stage, i)
+        loss_host.copy_(out.loss.view(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the user reads the loss every step
+        return float(loss_host[0])
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = w["B"] * world * args.steps / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        kern = {k: {"launches": c, "avg_us": tot / c * 1e3, "share": tot} for k, (c, tot) in prof.items()}
+        tot_ms = sum(v["share"] for v in kern.values()) or 1.0
+        for v in kern.values():
+            v["share"] = v["share"] / tot_ms
+        dom = max(kern, key=lambda k: kern[k]["share"]) if kern else None
+        roof = None
+        if dom:
+            ab = kernel_alg_bytes(dom, w, w["B"])
+            ach = ab / (kern[dom]["avg_us"] * 1e-6) / 1e9 if ab else None
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (ach / hbm_peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": ab, "avg_launch_us": kern[dom]["avg_us"], "share_of_step": kern[dom]["share"]}
+        step_bytes = step_alg_bytes_per_sample(w) * w["B"]
+        step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
+        line = {"metric": "fusion_step_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
+                "data": "synthetic", "config": workload_config(w, args, world),
+                "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
+                "step_roofline": {"alg_bytes_per_sample": step_alg_bytes_per_sample(w), "achieved": step_gbs,
+                                  "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak},
+                "kernels": {k: {"launches": v["launches"], "avg_us": round(v["avg_us"], 2), "share": round(v["share"], 4)}
+                            for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["share"])}}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(w)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

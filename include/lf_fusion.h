@@ -1,0 +1,189 @@
+/*
+ * lf_fusion.h — C ABI of the B200 (sm_100a) late-fusion training-step library.
+ *
+ * The reference (Nano1337/multimodal-clinical) has no FFI: its boundary for this path is the Python
+ * module API.  The entry points below are what a ctypes binding underneath that API
+ * needs; each cites the reference code it replaces (paths relative to the reference tree).
+ * All pointers are DEVICE pointers unless stated otherwise; all matrices are dense row-major fp32.
+ * `stream` is a cudaStream_t passed as void*.  Every call is asynchronous w.r.t. the host, returns
+ * 0 on success or a negative LF_ERR_* code, never throws, and keeps no hidden state between calls:
+ * outputs, state (History, EMA) and workspace are caller-owned.
+ */
+#ifndef LF_FUSION_H_
+#define LF_FUSION_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LF_ABI_VERSION 1
+
+/* error codes */
+#define LF_OK 0
+#define LF_ERR_BAD_ARG (-1)
+#define LF_ERR_WORKSPACE (-2)
+#define LF_ERR_CUDA (-3)
+#define LF_ERR_UNSUPPORTED (-4)
+
+/* head type: which loss the step assembles */
+#define LF_MODE_JLOGITS 0 /* avg=(z1+z2)/2, L=CE(avg): cremad/joint_model_ogm_ge.py:50-58, enrico/joint_model.py:78-86 */
+#define LF_MODE_QMF 1     /* L=CE(z_df)+CE(z1)+CE(z2)+L_reg: cremad/joint_model_qmf.py:57-75 */
+
+/* arithmetic of the three head GEMMs */
+#define LF_PREC_FP32 0 /* exact fp32 FMA; parity 1e-5 */
+#define LF_PREC_TF32 1 /* tcgen05 kind::tf32 tensor pipe (wide heads); parity 2e-2 like the reference's bf16-mixed */
+
+/* OGM-GE modulation (existing_algos/OGM_GE.py:48-54) */
+#define LF_MOD_OGM_GE 0 /* g <- k g + N(0, std(g)+1e-8) */
+#define LF_MOD_OGM 1    /* g <- k g */
+#define LF_MOD_NOISE 2  /* g <- g + N(0, std(g)+1e-8) */
+
+/*
+ * Packed per-step statistics, fp64, LF_STATS_HEADER + 2*C entries.  lf_heads_forward writes the LOCAL
+ * (this shard's) sums; with several GPUs the host all-reduces (sum) the buffer before the calls that
+ * consume it, which makes every mean a global-batch mean.
+ */
+#define LF_STAT_CE_JOINT 0  /* sum_b CE(avg_b) (JLOGITS) or sum_b CE(z_df_b) (QMF) */
+#define LF_STAT_CE_X1 1     /* sum_b CE(z1_b)      cremad/joint_model_qmf.py:64 */
+#define LF_STAT_CE_X2 2
+#define LF_STAT_SCORE_X1 3  /* sum_b softmax(z1)[b,y_b]   existing_algos/OGM_GE.py:21 */
+#define LF_STAT_SCORE_X2 4  /*                           existing_algos/OGM_GE.py:22 */
+#define LF_STAT_CNT_X1 5    /* #argmax(z1)==y      utils/BaseModel.py:78 */
+#define LF_STAT_CNT_X2 6    /*                     utils/BaseModel.py:79 */
+#define LF_STAT_CNT_JOINT 7 /* #argmax(avg)==y     utils/BaseModel.py:92 */
+#define LF_STAT_CNT_DF 8    /* #argmax(z_df)==y    utils/BaseModel.py:961 */
+#define LF_STAT_CNT_X1_CAL 9  /* #argmax(z1+off1)==y  utils/BaseModel.py:88 (written by lf_heads_backward) */
+#define LF_STAT_CNT_X2_CAL 10 /*                      utils/BaseModel.py:89 */
+#define LF_STAT_REG_SUM 11  /* sum of the two ranking-loss relu sums (written by lf_qmf_history_step) */
+#define LF_STATS_HEADER 16  /* [16, 16+C): sum_b z1[b,:]   [16+C, 16+2C): sum_b z2[b,:]  (utils/BaseModel.py:82-83) */
+
+typedef struct LfHeadsArgs {
+  int32_t batch;        /* B: samples in this shard */
+  int32_t batch_global; /* denominator of every batch mean (== batch on one GPU) */
+  int32_t dim;          /* D: feature width (multiple of 4) */
+  int32_t classes;      /* C */
+  int32_t mode;         /* LF_MODE_* */
+  int32_t precision;    /* LF_PREC_* */
+  int32_t need_dfeat;   /* 0: encoders frozen (enrico/joint_model.py:36-38), dfeat not produced */
+  int32_t reserved0;
+  const float* feat[2];   /* (B,D) pooled encoder features  cremad/joint_model_qmf.py:48-55 */
+  const float* weight[2]; /* (C,D) x{1,2}_classifier.weight cremad/joint_model_qmf.py:26,28 */
+  const float* bias[2];   /* (C)   x{1,2}_classifier.bias */
+  const int64_t* label;   /* (B) */
+  float* logits[2];       /* out (B,C) x1_logits, x2_logits */
+  float* avg_logits;      /* out (B,C) (x1+x2)/2            cremad/joint_model_qmf.py:73 */
+  float* logits_df;       /* out (B,C) QMF only             existing_algos/QMF.py:115-117 */
+  float* conf;            /* out (2,B) QMF only: log(sum(exp z))/10  existing_algos/QMF.py:113-114 */
+  float* dlogits[2];      /* scratch (B,C) each: dL/dz_m.  JLOGITS uses dlogits[0] only (dz1 == dz2) */
+  float* dfeat[2];        /* out (B,D) dL/df_m, or NULL when need_dfeat == 0 */
+  float* dweight[2];      /* out (C,D) LOCAL-shard dL/dW_m (host all-reduces across GPUs) */
+  float* dbias[2];        /* out (C) */
+  const float* qmf_g;     /* in  (2,B) dL_reg/dconf from lf_qmf_history_step (QMF backward only) */
+  const float* ema_offset;/* in  (2,C) offsets from lf_ema_update, for the calibrated counts */
+  double* stats;          /* in/out packed statistics, see LF_STAT_* */
+  void* workspace;        /* >= lf_workspace_bytes(batch, dim, classes) */
+  size_t workspace_bytes;
+} LfHeadsArgs;
+
+/* Bytes of caller-provided scratch the heads calls need. */
+size_t lf_workspace_bytes(int32_t batch, int32_t dim, int32_t classes);
+
+/*
+ * Forward half: logits of both heads (a1), mean fusion (a2) or QMF energy fusion (a3), per-sample CE
+ * terms, OGM-GE scores (a8), accuracy counts (a12) and the logit sums the EMA needs (a11), reduced into
+ * `stats`.  In JLOGITS mode dL/dz is final here and is left in dlogits[0].
+ * Replaces nn.Linear x2 + torch.stack/QMF.df + nn.CrossEntropyLoss x1..3 + the argmax/mean metrics.
+ */
+int lf_heads_forward(const LfHeadsArgs* args, void* stream);
+
+/*
+ * Backward half: dL/dz_m (QMF: needs stats with the global sums and qmf_g), dfeat = dz W, dW = dz^T f,
+ * db = sum dz, plus the calibrated-accuracy counts (z_m + ema_offset[m]).
+ * Replaces loss.backward() through the heads (autograd of the lines above).
+ */
+int lf_heads_backward(const LfHeadsArgs* args, void* stream);
+
+/* loss_out[0] = total loss of the step from (all-reduced) stats.  cremad/joint_model_qmf.py:70 */
+int lf_loss_finalize(const double* stats, int32_t mode, int32_t batch_global, float* loss_out, void* stream);
+
+/*
+ * EMA of the batch-mean logits and its offsets (utils/EMA.py:29-38; call site utils/BaseModel.py:82-85):
+ * x <- smoothing*mean_b(z_m) + (1-smoothing)*x ; offset = mean_m(x) - x.  ema_x, ema_offset: (2,C).
+ */
+int lf_ema_update(float* ema_x, float* ema_offset, const double* stats, int32_t classes,
+                  int32_t batch_global, float smoothing, void* stream);
+
+/*
+ * OGM-GE coefficients from the global score sums (existing_algos/OGM_GE.py:24-40).
+ * coeff_out[0] scales x1_model's conv grads, coeff_out[1] x2_model's.
+ */
+int lf_ogm_coeff(const double* stats, float alpha, float* coeff_out, void* stream);
+
+typedef struct LfQmfArgs {
+  int32_t batch_global;  /* Bg >= 2: length of idx / conf rows (the gathered global batch) */
+  int32_t n_data;        /* N: length of the History arrays (args.num_samples) */
+  const int64_t* idx;    /* (Bg) dataset indices of the batch, global batch order */
+  const float* conf;     /* (2,Bg) */
+  double* correctness;   /* in/out (2,N) History.correctness  existing_algos/QMF.py:13 */
+  double* confidence;    /* in/out (2,N) History.confidence   existing_algos/QMF.py:14 */
+  int64_t* last_writer;  /* in/out (N) scratch owned by the History, zero-initialised once */
+  int64_t step_base;     /* strictly increasing by >= Bg per call, starting at 1 */
+  double* stats;         /* in: global CE sums (LF_STAT_CE_X1/X2); out: LF_STAT_REG_SUM */
+  float* qmf_g;          /* out (2,Bg) dL_reg/dconf (already divided by Bg) */
+  float* target_out;     /* out (2,Bg) ranking targets in {-1,0,1}, or NULL */
+  int32_t g_begin;       /* [g_begin, g_begin+g_count) slice of the global batch whose qmf_g rows are */
+  int32_t g_count;       /* written at qmf_g[m*g_count + (j-g_begin)]; use 0,Bg for everything */
+  void* workspace;       /* >= lf_qmf_workspace_bytes(n_data) */
+  size_t workspace_bytes;
+} LfQmfArgs;
+
+size_t lf_qmf_workspace_bytes(int32_t n_data);
+
+/*
+ * QMF History update + ranking regulariser on the (global) batch:
+ *   History.correctness_update  existing_algos/QMF.py:20-29   (scalar batch-mean loss, alpha = 0.1)
+ *   History.get_target_margin   existing_algos/QMF.py:37-68   (global min/max over N)
+ *   QMF.reg_loss                existing_algos/QMF.py:119-141 (closed form, incl. the flattened roll)
+ */
+int lf_qmf_history_step(const LfQmfArgs* args, void* stream);
+
+typedef struct LfTensorList {
+  int32_t count;          /* number of gradient tensors (<= LF_MAX_TENSORS) */
+  int32_t reserved;
+  float* data[64];        /* device pointers of the 4-D .grad tensors of one encoder */
+  int64_t numel[64];
+} LfTensorList;
+#define LF_MAX_TENSORS 64
+
+size_t lf_modulate_workspace_bytes(void);
+
+/*
+ * OGM-GE add_factor over the 4-D gradients of one encoder (existing_algos/OGM_GE.py:42-54):
+ * sigma_t = unbiased std of tensor t (before scaling) + 1e-8; g <- coeff*g + sigma_t*xi (OGM_GE),
+ * coeff*g (OGM), g + sigma_t*xi (NOISE); xi ~ N(0,1) from Philox4x32-10 keyed by (seed, offset).
+ * coeff_dev points at ONE float on the device (lf_ogm_coeff output), so no host sync is needed.
+ */
+int lf_ogm_modulate(const LfTensorList* list, const float* coeff_dev, int32_t mode, uint64_t seed,
+                    uint64_t offset, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Evidence hooks for bench.py (no reference counterpart): number of kernels this library has launched
+ * since it was loaded, and optional CUDA-event timing of every launch (events recorded on the launch
+ * stream around each kernel).  lf_profile_report synchronises the device and writes one
+ * "name count total_ms" line per kernel name into buf, clearing the records.
+ */
+int64_t lf_launch_count(void);
+void lf_profile_enable(int32_t on);
+int32_t lf_profile_report(char* buf, int32_t buf_bytes);
+
+/* Last error message of the calling thread (host string). */
+const char* lf_last_error(void);
+int32_t lf_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LF_FUSION_H_ */

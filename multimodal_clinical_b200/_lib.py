@@ -1,0 +1,112 @@
+"""ctypes binding of the C-ABI library ``_lf_fusion.so`` (declared in ``include/lf_fusion.h``).
+
+There is deliberately NO fallback: if the shared object is missing or a call fails, an exception is
+raised.  The product path never routes through PyTorch eager ops or the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lf_fusion.so")
+
+LF_MODE_JLOGITS, LF_MODE_QMF = 0, 1
+LF_PREC_FP32, LF_PREC_TF32 = 0, 1
+LF_MOD_OGM_GE, LF_MOD_OGM, LF_MOD_NOISE = 0, 1, 2
+LF_STATS_HEADER = 16
+LF_MAX_TENSORS = 64
+STAT = dict(CE_JOINT=0, CE_X1=1, CE_X2=2, SCORE_X1=3, SCORE_X2=4, CNT_X1=5, CNT_X2=6, CNT_JOINT=7,
+            CNT_DF=8, CNT_X1_CAL=9, CNT_X2_CAL=10, REG_SUM=11)
+
+_f32p = C.c_void_p   # device pointers travel as plain integers
+_P2 = C.c_void_p * 2
+
+
+class LfHeadsArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("batch_global", C.c_int32), ("dim", C.c_int32), ("classes", C.c_int32),
+        ("mode", C.c_int32), ("precision", C.c_int32), ("need_dfeat", C.c_int32), ("reserved0", C.c_int32),
+        ("feat", _P2), ("weight", _P2), ("bias", _P2), ("label", C.c_void_p),
+        ("logits", _P2), ("avg_logits", C.c_void_p), ("logits_df", C.c_void_p), ("conf", C.c_void_p),
+        ("dlogits", _P2), ("dfeat", _P2), ("dweight", _P2), ("dbias", _P2),
+        ("qmf_g", C.c_void_p), ("ema_offset", C.c_void_p), ("stats", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class LfQmfArgs(C.Structure):
+    _fields_ = [
+        ("batch_global", C.c_int32), ("n_data", C.c_int32),
+        ("idx", C.c_void_p), ("conf", C.c_void_p), ("correctness", C.c_void_p), ("confidence", C.c_void_p),
+        ("last_writer", C.c_void_p), ("step_base", C.c_int64), ("stats", C.c_void_p), ("qmf_g", C.c_void_p),
+        ("target_out", C.c_void_p), ("g_begin", C.c_int32), ("g_count", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class LfTensorList(C.Structure):
+    _fields_ = [("count", C.c_int32), ("reserved", C.c_int32),
+                ("data", C.c_void_p * LF_MAX_TENSORS), ("numel", C.c_int64 * LF_MAX_TENSORS)]
+
+
+# name -> (restype, argtypes); also the list the "exports every declared symbol" test walks
+SIGNATURES = {
+    "lf_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "lf_heads_forward": (C.c_int, [C.POINTER(LfHeadsArgs), C.c_void_p]),
+    "lf_heads_backward": (C.c_int, [C.POINTER(LfHeadsArgs), C.c_void_p]),
+    "lf_loss_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "lf_ema_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "lf_ogm_coeff": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "lf_qmf_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "lf_qmf_history_step": (C.c_int, [C.POINTER(LfQmfArgs), C.c_void_p]),
+    "lf_modulate_workspace_bytes": (C.c_size_t, []),
+    "lf_ogm_modulate": (C.c_int, [C.POINTER(LfTensorList), C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64,
+                                  C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lf_launch_count": (C.c_int64, []),
+    "lf_profile_enable": (None, [C.c_int32]),
+    "lf_profile_report": (C.c_int32, [C.c_char_p, C.c_int32]),
+    "lf_last_error": (C.c_char_p, []),
+    "lf_abi_version": (C.c_int32, []),
+}
+
+_lib = None
+
+
+class LfError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LfError(f"{LIB_PATH} is missing: build it with `python -m multimodal_clinical_b200.build` "
+                      "(or __graft_entry__.build()). There is no CPU/eager fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().lf_last_error()
+        raise LfError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def profile_report() -> dict:
+    """{kernel name: (launches, total_ms)} for everything timed since the last report."""
+    lib = load()
+    buf = C.create_string_buffer(1 << 16)
+    lib.lf_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out

@@ -1,0 +1,233 @@
+// extern "C" entry points of the late-fusion step library (include/lf_fusion.h): argument checking,
+// workspace carving and kernel sequencing.  No torch types, no global state beyond a thread-local
+// error string.
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "lf_common.cuh"
+#include "lf_gemm.cuh"
+#include "lf_rows.cuh"
+
+namespace lf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return LF_ERR_CUDA;
+  }
+  return LF_OK;
+}
+
+// ---- launch accounting + optional per-kernel event timing -------------------------------------
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static thread_local cudaEvent_t g_pending = nullptr;
+
+void prof_begin(const char*, cudaStream_t s) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  cudaEventCreate(&g_pending);
+  cudaEventRecord(g_pending, s);
+}
+void prof_end(const char* name, cudaStream_t s) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on.load(std::memory_order_relaxed) || !g_pending) return;
+  ProfRec r; r.name = name; r.e0 = g_pending; g_pending = nullptr;
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e1, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+}
+
+int dw_splits(int B, int D, int C) {
+  // enough CTAs to fill the machine: tiles(C,D) * splits >= ~2 waves, each split >= 256 samples
+  const int tiles = div_up(C, C <= 16 ? 16 : 64) * div_up(D, 64);
+  int s = div_up(2 * 148, tiles);
+  const int by_rows = div_up(B, 256);
+  if (s > by_rows) s = by_rows;
+  if (s > kMaxSplits) s = kMaxSplits;
+  if (s < 1) s = 1;
+  return s;
+}
+
+HeadsWorkspace carve_heads_workspace(void* base, int B, int D, int C) {
+  HeadsWorkspace w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes, 256); return r; };
+  w.row_partials = (float*)take((size_t)kMaxRowBlocks * stat_len(C) * sizeof(float));
+  w.dw_partials = (float*)take((size_t)2 * kMaxSplits * C * D * sizeof(float));
+  w.db_partials = (float*)take((size_t)2 * kMaxSplits * C * sizeof(float));
+  w.total = off + (size_t)B * 4 * sizeof(float) + 256;  // + rowstat
+  return w;
+}
+
+static float* rowstat_ptr(void* base, int B, int D, int C) {
+  HeadsWorkspace w = carve_heads_workspace(base, B, D, C);
+  return (float*)((char*)base + (w.total - (size_t)B * 4 * sizeof(float) - 256));
+}
+
+static int check_heads(const LfHeadsArgs* a, bool backward) {
+  if (!a) { set_error("null LfHeadsArgs"); return LF_ERR_BAD_ARG; }
+  if (a->batch < 1 || a->batch_global < a->batch || a->dim < 4 || a->dim % 4 || a->classes < 1) {
+    set_error("bad sizes: batch=%d batch_global=%d dim=%d (multiple of 4) classes=%d", a->batch,
+              a->batch_global, a->dim, a->classes);
+    return LF_ERR_BAD_ARG;
+  }
+  if (a->mode != LF_MODE_JLOGITS && a->mode != LF_MODE_QMF) { set_error("bad mode %d", a->mode); return LF_ERR_BAD_ARG; }
+  if (a->precision != LF_PREC_FP32 && a->precision != LF_PREC_TF32) { set_error("bad precision %d", a->precision); return LF_ERR_BAD_ARG; }
+  for (int m = 0; m < 2; ++m)
+    if (!a->feat[m] || !a->weight[m] || !a->bias[m] || !a->logits[m] || !a->dweight[m] || !a->dbias[m]) {
+      set_error("null per-modality pointer (modality %d)", m);
+      return LF_ERR_BAD_ARG;
+    }
+  if (!a->label || !a->avg_logits || !a->dlogits[0] || !a->stats || !a->workspace) { set_error("null pointer argument"); return LF_ERR_BAD_ARG; }
+  if (a->mode == LF_MODE_QMF && (!a->logits_df || !a->conf || !a->dlogits[1])) { set_error("QMF mode needs logits_df, conf, dlogits[1]"); return LF_ERR_BAD_ARG; }
+  if (a->need_dfeat && (!a->dfeat[0] || !a->dfeat[1])) { set_error("need_dfeat set but dfeat is null"); return LF_ERR_BAD_ARG; }
+  if (backward && !a->ema_offset) { set_error("backward needs ema_offset"); return LF_ERR_BAD_ARG; }
+  if (backward && a->mode == LF_MODE_QMF && !a->qmf_g) { set_error("QMF backward needs qmf_g"); return LF_ERR_BAD_ARG; }
+  if (a->workspace_bytes < lf_workspace_bytes(a->batch, a->dim, a->classes)) {
+    set_error("workspace too small: %zu < %zu", a->workspace_bytes, lf_workspace_bytes(a->batch, a->dim, a->classes));
+    return LF_ERR_WORKSPACE;
+  }
+  return LF_OK;
+}
+
+static RowsArgs rows_args(const LfHeadsArgs* a, const HeadsWorkspace& w) {
+  RowsArgs r;
+  r.z[0] = a->logits[0]; r.z[1] = a->logits[1];
+  r.avg = a->avg_logits; r.zdf = a->logits_df; r.conf = a->conf;
+  r.rowstat = rowstat_ptr(a->workspace, a->batch, a->dim, a->classes);
+  r.dz[0] = a->dlogits[0]; r.dz[1] = a->dlogits[1];
+  r.label = a->label; r.qmf_g = a->qmf_g; r.ema_off = a->ema_offset;
+  r.partials = w.row_partials; r.stats = a->stats;
+  r.B = a->batch; r.B_global = a->batch_global; r.C = a->classes;
+  return r;
+}
+
+}  // namespace lf
+
+using namespace lf;
+
+extern "C" const char* lf_last_error(void) { return g_err; }
+extern "C" int32_t lf_abi_version(void) { return LF_ABI_VERSION; }
+extern "C" int64_t lf_launch_count(void) { return g_launches.load(); }
+extern "C" void lf_profile_enable(int32_t on) { g_prof_on.store(on ? 1 : 0); }
+
+// Synchronises the device, then writes "name count total_ms\n" lines for every kernel timed since the
+// last report and clears the records.  Returns the number of bytes written (excluding the NUL).
+extern "C" int32_t lf_profile_report(char* buf, int32_t buf_bytes) {
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<long long, double>> agg;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+        auto& a = agg[r.name];
+        a.first += 1; a.second += ms;
+      }
+      cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+  }
+  std::string out;
+  char line[256];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (!buf || buf_bytes <= 0) return 0;
+  const size_t n = out.size() < (size_t)buf_bytes - 1 ? out.size() : (size_t)buf_bytes - 1;
+  memcpy(buf, out.data(), n);
+  buf[n] = 0;
+  return (int32_t)n;
+}
+
+extern "C" size_t lf_workspace_bytes(int32_t batch, int32_t dim, int32_t classes) {
+  if (batch < 1 || dim < 1 || classes < 1) return 0;
+  return carve_heads_workspace(nullptr, batch, dim, classes).total;
+}
+
+extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
+  int rc = check_heads(a, false);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  HeadsWorkspace w = carve_heads_workspace(a->workspace, a->batch, a->dim, a->classes);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  for (int m = 0; m < 2; ++m) { g.A[m] = a->feat[m]; g.B[m] = a->weight[m]; g.bias[m] = a->bias[m]; g.C[m] = a->logits[m]; }
+  g.M = a->batch; g.N = a->classes; g.K = a->dim;
+  g.lda = a->dim; g.ldb = a->dim; g.ldc = a->classes;
+  rc = gemm_logits(g, 2, s);
+  if (rc) return rc;
+  return rows_forward(rows_args(a, w), a->mode, s);
+}
+
+extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
+  int rc = check_heads(a, true);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  HeadsWorkspace w = carve_heads_workspace(a->workspace, a->batch, a->dim, a->classes);
+  rc = rows_backward(rows_args(a, w), a->mode, s);
+  if (rc) return rc;
+  const float* dz[2] = {a->dlogits[0], a->mode == LF_MODE_QMF ? a->dlogits[1] : a->dlogits[0]};
+  GemmArgs g;
+  if (a->need_dfeat) {
+    memset(&g, 0, sizeof(g));
+    for (int m = 0; m < 2; ++m) { g.A[m] = dz[m]; g.B[m] = a->weight[m]; g.bias[m] = nullptr; g.C[m] = a->dfeat[m]; }
+    g.M = a->batch; g.N = a->dim; g.K = a->classes;
+    g.lda = a->classes; g.ldb = a->dim; g.ldc = a->dim;
+    rc = gemm_dfeat(g, 2, s);
+    if (rc) return rc;
+  }
+  // dW_m = dZ_m^T F_m : split-K over the batch, partials reduced in fixed order
+  const int splits = dw_splits(a->batch, a->dim, a->classes);
+  const size_t cd = (size_t)a->classes * a->dim;
+  memset(&g, 0, sizeof(g));
+  for (int m = 0; m < 2; ++m) { g.A[m] = dz[m]; g.B[m] = a->feat[m]; g.bias[m] = nullptr; g.C[m] = w.dw_partials + (size_t)m * kMaxSplits * cd; }
+  g.M = a->classes; g.N = a->dim; g.K = a->batch;
+  g.lda = a->classes; g.ldb = a->dim; g.ldc = a->dim;
+  g.splits = splits; g.k_chunk = div_up(a->batch, splits); g.split_stride = cd;
+  rc = gemm_dweight(g, 2, s);
+  if (rc) return rc;
+  for (int m = 0; m < 2; ++m) {
+    rc = reduce_splits(w.dw_partials + (size_t)m * kMaxSplits * cd, a->dweight[m], splits, cd, s);
+    if (rc) return rc;
+  }
+  // db_m = column sums of dZ_m
+  rc = colsum(dz, a->batch, a->classes, w.db_partials, a->dbias, s);
+  return rc;
+}
+
+extern "C" int lf_loss_finalize(const double* stats, int32_t mode, int32_t batch_global, float* loss_out, void* stream) {
+  if (!stats || !loss_out || batch_global < 1) { set_error("lf_loss_finalize: bad argument"); return LF_ERR_BAD_ARG; }
+  return loss_finalize(stats, mode, batch_global, loss_out, (cudaStream_t)stream);
+}
+
+extern "C" int lf_ema_update(float* ema_x, float* ema_offset, const double* stats, int32_t classes,
+                             int32_t batch_global, float smoothing, void* stream) {
+  if (!ema_x || !ema_offset || !stats || classes < 1 || batch_global < 1) { set_error("lf_ema_update: bad argument"); return LF_ERR_BAD_ARG; }
+  return ema_update(ema_x, ema_offset, stats, classes, batch_global, smoothing, (cudaStream_t)stream);
+}
+
+extern "C" int lf_ogm_coeff(const double* stats, float alpha, float* coeff_out, void* stream) {
+  if (!stats || !coeff_out) { set_error("lf_ogm_coeff: bad argument"); return LF_ERR_BAD_ARG; }
+  return ogm_coeff(stats, alpha, coeff_out, (cudaStream_t)stream);
+}

@@ -1,0 +1,81 @@
+// Shared device/host helpers for the late-fusion step kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/lf_fusion.h"
+
+namespace lf {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+// launch accounting (lf_launch_count) and optional per-kernel CUDA-event timing (lf_profile_*)
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end(const char* name, cudaStream_t s);
+#define LF_LAUNCH(name, stream, ...)      \
+  do {                                    \
+    ::lf::prof_begin(name, stream);       \
+    __VA_ARGS__;                          \
+    ::lf::prof_end(name, stream);         \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+// argmax with torch semantics: first index among equal maxima.
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(kFull, v, o);
+    int oi = __shfl_xor_sync(kFull, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// relu that lets NaN through (torch.clamp_min semantics; fmaxf would swallow it)
+__device__ __forceinline__ float relu_nan(float x) { return (x > 0.f || x != x) ? x : 0.f; }
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- workspace carving (shared by lf_api.cu and tests of lf_workspace_bytes) -------------------
+struct HeadsWorkspace {
+  float* row_partials;   // [kMaxRowBlocks][stat_len]   per-block partial statistics
+  float* dw_partials;    // [2][splits][C][D]
+  float* db_partials;    // [2][splits][C]
+  size_t total;
+};
+constexpr int kMaxRowBlocks = 592;   // 4 CTAs per SM on 148 SMs
+constexpr int kMaxSplits = 64;
+
+inline int stat_len(int C) { return LF_STATS_HEADER + 2 * C; }
+int dw_splits(int B, int D, int C);
+HeadsWorkspace carve_heads_workspace(void* base, int B, int D, int C);
+
+}  // namespace lf

@@ -1,0 +1,297 @@
+// Per-sample ("row") math of the late-fusion step on logits already in HBM:
+// softmax / log-sum-exp statistics, cross-entropy terms, QMF energy confidence and fused logits,
+// OGM-GE scores, accuracy counts, EMA logit sums, and dL/dlogits.   One warp per sample, lanes
+// strided over classes (coalesced for any C), online log-sum-exp, warp-shuffle reductions,
+// deterministic two-stage reduction of the batch statistics.
+//
+// Reference arithmetic restated here (paths relative to the reference tree):
+//   avg = (z1+z2)/2, CE(avg)                cremad/joint_model_ogm_ge.py:54-56
+//   energy/conf/z_df                        existing_algos/QMF.py:113-117
+//   CE(z_m), CE(z_df)                       cremad/joint_model_qmf.py:64,68
+//   scores                                  existing_algos/OGM_GE.py:21-22
+//   argmax accuracies                       utils/BaseModel.py:78-92, 961
+//   dL/dz (analytic)
+#include "lf_common.cuh"
+#include "lf_rows.cuh"
+
+namespace lf {
+
+struct Lse {  // online log-sum-exp accumulator
+  float m, s;
+  __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
+  __device__ __forceinline__ void add(float v) {
+    if (v > m) { s = s * __expf(m - v) + 1.f; m = v; }
+    else s += __expf(v - m);
+  }
+  // warp-combine; result (same in all lanes) = log sum exp over everything added by the warp
+  __device__ __forceinline__ float finish() {
+    const float M = warp_max(m);
+    const float part = (m == -INFINITY) ? 0.f : s * __expf(m - M);
+    return M + logf(warp_sum(part));
+  }
+};
+
+// NOTE on intrinsics: __expf/__logf are the fast SFU forms (abs err ~2 ulp in the ranges that occur
+// here); the fp32 parity budget is 1e-5 relative and tests/test_parity_gpu.py checks it holds.
+// The QMF energy deliberately uses the NON-stabilised sum of exp like the reference (QMF.py:113).
+
+template <int MODE>
+__global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
+  extern __shared__ float smem[];
+  const int C = a.C, B = a.B;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int nwarp = blockDim.x / 32;
+  float* colsum = smem + (size_t)warp * 2 * C;  // [2][C] owned by this warp
+  for (int c = lane; c < 2 * C; c += 32) colsum[c] = 0.f;
+  __syncwarp();
+
+  float st[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) st[i] = 0.f;
+
+  const float dz_scale = 0.5f / (float)a.B_global;
+
+  for (int b = blockIdx.x * nwarp + warp; b < B; b += gridDim.x * nwarp) {
+    const float* __restrict__ z1 = a.z[0] + (size_t)b * C;
+    const float* __restrict__ z2 = a.z[1] + (size_t)b * C;
+    const int y = (int)a.label[b];
+    Lse l1, l2, la;
+    l1.init(); l2.init(); la.init();
+    float e1 = 0.f, e2 = 0.f;                       // plain sum exp (QMF energy)
+    float m1 = -INFINITY, m2 = -INFINITY, ma = -INFINITY;
+    int i1 = 0x7fffffff, i2 = 0x7fffffff, ia = 0x7fffffff;
+    float zy1 = 0.f, zy2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v1 = z1[c], v2 = z2[c];
+      const float av = (v1 + v2) / 2.f;
+      a.avg[(size_t)b * C + c] = av;
+      l1.add(v1); l2.add(v2); la.add(av);
+      if (MODE == LF_MODE_QMF) { e1 += expf(v1); e2 += expf(v2); }
+      if (v1 > m1) { m1 = v1; i1 = c; }
+      if (v2 > m2) { m2 = v2; i2 = c; }
+      if (av > ma) { ma = av; ia = c; }
+      if (c == y) { zy1 = v1; zy2 = v2; }
+      colsum[c] += v1;
+      colsum[C + c] += v2;
+    }
+    const float lse1 = l1.finish(), lse2 = l2.finish(), lsea = la.finish();
+    warp_argmax(m1, i1); warp_argmax(m2, i2); warp_argmax(ma, ia);
+    zy1 = __shfl_sync(kFull, zy1, y & 31);
+    zy2 = __shfl_sync(kFull, zy2, y & 31);
+
+    float ce_joint, lse_joint;
+    int cnt_df = 0;
+    if (MODE == LF_MODE_QMF) {
+      const float c1 = logf(warp_sum(e1)) / 10.f;
+      const float c2 = logf(warp_sum(e2)) / 10.f;
+      Lse ld; ld.init();
+      float md = -INFINITY; int idf = 0x7fffffff; float zyd = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float vd = z1[c] * c1 + z2[c] * c2;
+        a.zdf[(size_t)b * C + c] = vd;
+        ld.add(vd);
+        if (vd > md) { md = vd; idf = c; }
+        if (c == y) zyd = vd;
+      }
+      lse_joint = ld.finish();
+      warp_argmax(md, idf);
+      zyd = __shfl_sync(kFull, zyd, y & 31);
+      ce_joint = lse_joint - zyd;
+      cnt_df = (idf == y);
+      if (lane == 0) {
+        a.conf[b] = c1;
+        a.conf[B + b] = c2;
+        a.rowstat[(size_t)b * 4 + 0] = lse1;
+        a.rowstat[(size_t)b * 4 + 1] = lse2;
+        a.rowstat[(size_t)b * 4 + 2] = lse_joint;
+      }
+    } else {
+      lse_joint = lsea;
+      ce_joint = lsea - 0.5f * (zy1 + zy2);
+      // dL/dz1 = dL/dz2 = (softmax(avg) - onehot) / (2 Bg)
+      for (int c = lane; c < C; c += 32) {
+        const float av = (z1[c] + z2[c]) / 2.f;
+        const float p = __expf(av - lsea);
+        a.dz[0][(size_t)b * C + c] = (p - (c == y ? 1.f : 0.f)) * dz_scale;
+      }
+    }
+    if (lane == 0) {
+      st[LF_STAT_CE_JOINT] += ce_joint;
+      st[LF_STAT_CE_X1] += lse1 - zy1;
+      st[LF_STAT_CE_X2] += lse2 - zy2;
+      st[LF_STAT_SCORE_X1] += __expf(zy1 - lse1);
+      st[LF_STAT_SCORE_X2] += __expf(zy2 - lse2);
+      st[LF_STAT_CNT_X1] += (i1 == y);
+      st[LF_STAT_CNT_X2] += (i2 == y);
+      st[LF_STAT_CNT_JOINT] += (ia == y);
+      st[LF_STAT_CNT_DF] += cnt_df;
+    }
+  }
+
+  // ---- block reduction in fixed order -> one partial row per block
+  __shared__ float sst[8][9];
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sst[warp][i] = st[i];
+  __syncthreads();
+  float* out = a.partials + (size_t)blockIdx.x * stat_len_dev(C);
+  if (threadIdx.x < LF_STATS_HEADER) {
+    float s = 0.f;
+    if (threadIdx.x < 9)
+      for (int w = 0; w < nwarp; ++w) s += sst[w][threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nwarp; ++w) s += smem[(size_t)w * 2 * C + c];
+    out[LF_STATS_HEADER + c] = s;
+  }
+}
+
+// stats[i] = sum over blocks (fp64, fixed order).  Entries [lo, hi) plus, when with_cols, the 2C tail.
+__global__ void finalize_stats_kernel(const float* __restrict__ partials, int nblocks, int len, int lo,
+                                      int hi, int with_cols, double* __restrict__ stats) {
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const bool header = i < LF_STATS_HEADER;
+    if (header && (i < lo || i >= hi)) continue;
+    if (!header && !with_cols) continue;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += (double)partials[(size_t)b * len + i];
+    stats[i] = s;
+  }
+}
+
+// Backward rows: QMF dL/dz_m and, for both modes, the calibrated counts
+// argmax(z_m + offset_m) == y (utils/BaseModel.py:84-89).
+template <int MODE>
+__global__ void __launch_bounds__(256) rows_backward_kernel(RowsArgs a) {
+  const int C = a.C, B = a.B;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int nwarp = blockDim.x / 32;
+  const float invB = 1.f / (float)a.B_global;
+  float cal1 = 0.f, cal2 = 0.f;
+  for (int b = blockIdx.x * nwarp + warp; b < B; b += gridDim.x * nwarp) {
+    const float* __restrict__ z1 = a.z[0] + (size_t)b * C;
+    const float* __restrict__ z2 = a.z[1] + (size_t)b * C;
+    const int y = (int)a.label[b];
+    float c1 = 0.f, c2 = 0.f, lse1 = 0.f, lse2 = 0.f, lsed = 0.f, g1 = 0.f, g2 = 0.f;
+    if (MODE == LF_MODE_QMF) {
+      c1 = a.conf[b]; c2 = a.conf[B + b];
+      lse1 = a.rowstat[(size_t)b * 4 + 0];
+      lse2 = a.rowstat[(size_t)b * 4 + 1];
+      lsed = a.rowstat[(size_t)b * 4 + 2];
+      g1 = a.qmf_g[b] / 10.f;
+      g2 = a.qmf_g[B + b] / 10.f;
+    }
+    float m1 = -INFINITY, m2 = -INFINITY;
+    int i1 = 0x7fffffff, i2 = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+      const float v1 = z1[c], v2 = z2[c];
+      const float w1 = v1 + a.ema_off[c], w2 = v2 + a.ema_off[C + c];
+      if (w1 > m1) { m1 = w1; i1 = c; }
+      if (w2 > m2) { m2 = w2; i2 = c; }
+      if (MODE == LF_MODE_QMF) {
+        const float oh = (c == y) ? 1.f : 0.f;
+        const float p1 = __expf(v1 - lse1), p2 = __expf(v2 - lse2);
+        const float pd = __expf((v1 * c1 + v2 * c2) - lsed) - oh;
+        a.dz[0][(size_t)b * C + c] = ((p1 - oh) + c1 * pd) * invB + g1 * p1;
+        a.dz[1][(size_t)b * C + c] = ((p2 - oh) + c2 * pd) * invB + g2 * p2;
+      }
+    }
+    warp_argmax(m1, i1); warp_argmax(m2, i2);
+    cal1 += (i1 == y); cal2 += (i2 == y);
+  }
+  __shared__ float s1[8], s2[8];
+  if (lane == 0) { s1[warp] = cal1; s2[warp] = cal2; }
+  __syncthreads();
+  if (threadIdx.x < LF_STATS_HEADER) {
+    float s = 0.f;
+    if (threadIdx.x == LF_STAT_CNT_X1_CAL) for (int w = 0; w < nwarp; ++w) s += s1[w];
+    if (threadIdx.x == LF_STAT_CNT_X2_CAL) for (int w = 0; w < nwarp; ++w) s += s2[w];
+    a.partials[(size_t)blockIdx.x * stat_len_dev(C) + threadIdx.x] = s;
+  }
+}
+
+static int row_blocks(int B) {
+  int nb = div_up(B, 8);
+  return nb < kMaxRowBlocks ? (nb < 1 ? 1 : nb) : kMaxRowBlocks;
+}
+
+int rows_forward(const RowsArgs& a, int mode, cudaStream_t s) {
+  const int nb = row_blocks(a.B);
+  const size_t sm = (size_t)8 * 2 * a.C * sizeof(float);
+  if (sm > 200 * 1024) { set_error("classes=%d too wide for rows_forward shared memory", a.C); return LF_ERR_UNSUPPORTED; }
+  if (mode == LF_MODE_QMF) {
+    if (sm > 48 * 1024) cudaFuncSetAttribute(rows_forward_kernel<LF_MODE_QMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    LF_LAUNCH("rows_forward_qmf", s, (rows_forward_kernel<LF_MODE_QMF><<<nb, 256, sm, s>>>(a)));
+  } else {
+    if (sm > 48 * 1024) cudaFuncSetAttribute(rows_forward_kernel<LF_MODE_JLOGITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    LF_LAUNCH("rows_forward_jlogits", s, (rows_forward_kernel<LF_MODE_JLOGITS><<<nb, 256, sm, s>>>(a)));
+  }
+  int rc = check_launch("rows_forward_kernel");
+  if (rc) return rc;
+  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<1, 256, 0, s>>>(a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats)));
+  return check_launch("finalize_stats_kernel");
+}
+
+int rows_backward(const RowsArgs& a, int mode, cudaStream_t s) {
+  const int nb = row_blocks(a.B);
+  if (mode == LF_MODE_QMF) LF_LAUNCH("rows_backward_qmf", s, (rows_backward_kernel<LF_MODE_QMF><<<nb, 256, 0, s>>>(a)));
+  else LF_LAUNCH("rows_calibrated", s, (rows_backward_kernel<LF_MODE_JLOGITS><<<nb, 256, 0, s>>>(a)));
+  int rc = check_launch("rows_backward_kernel");
+  if (rc) return rc;
+  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<1, 32, 0, s>>>(a.partials, nb, stat_len(a.C), LF_STAT_CNT_X1_CAL,
+                                         LF_STAT_CNT_X2_CAL + 1, 0, a.stats)));
+  return check_launch("finalize_stats_kernel(cal)");
+}
+
+// ---- tiny scalar kernels ---------------------------------------------------------------------
+__global__ void loss_finalize_kernel(const double* __restrict__ stats, int mode, int Bg, float* out) {
+  const double inv = 1.0 / (double)Bg;
+  // each term is a separate fp32 mean in the reference; summed in fp32 (cremad/joint_model_qmf.py:70)
+  float loss = (float)(stats[LF_STAT_CE_JOINT] * inv);
+  if (mode == LF_MODE_QMF) {
+    const float uni = (float)(stats[LF_STAT_CE_X1] * inv) + (float)(stats[LF_STAT_CE_X2] * inv);
+    loss = loss + uni + (float)(stats[LF_STAT_REG_SUM] * inv);
+  }
+  out[0] = loss;
+}
+
+__global__ void ema_update_kernel(float* __restrict__ x, float* __restrict__ off, const double* __restrict__ stats,
+                                  int C, int Bg, float beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean1 = (float)(stats[LF_STATS_HEADER + c] / (double)Bg);
+  const float mean2 = (float)(stats[LF_STATS_HEADER + C + c] / (double)Bg);
+  const float x1 = mean1 * beta + x[c] * (1.0f - beta);        // utils/EMA.py:33
+  const float x2 = mean2 * beta + x[C + c] * (1.0f - beta);
+  x[c] = x1; x[C + c] = x2;
+  const float mu = (x1 + x2) / 2.f;                             // utils/EMA.py:38
+  off[c] = mu - x1;
+  off[C + c] = mu - x2;
+}
+
+__global__ void ogm_coeff_kernel(const double* __restrict__ stats, float alpha, float* __restrict__ coeff) {
+  const float s1 = (float)stats[LF_STAT_SCORE_X1], s2 = (float)stats[LF_STAT_SCORE_X2];
+  const float r1 = s1 / s2;                 // existing_algos/OGM_GE.py:24
+  const float r2 = 1.f / r1;                // :25
+  float k1 = 1.f, k2 = 1.f;
+  if (r1 > 1.f) k1 = 1.f - tanhf(alpha * fmaxf(r1, 0.f));   // :35-37
+  else k2 = 1.f - tanhf(alpha * fmaxf(r2, 0.f));            // :38-40
+  coeff[0] = k1; coeff[1] = k2;
+}
+
+int loss_finalize(const double* stats, int mode, int Bg, float* out, cudaStream_t s) {
+  LF_LAUNCH("loss_finalize", s, (loss_finalize_kernel<<<1, 1, 0, s>>>(stats, mode, Bg, out)));
+  return check_launch("loss_finalize_kernel");
+}
+int ema_update(float* x, float* off, const double* stats, int C, int Bg, float beta, cudaStream_t s) {
+  LF_LAUNCH("ema_update", s, (ema_update_kernel<<<div_up(C, 128), 128, 0, s>>>(x, off, stats, C, Bg, beta)));
+  return check_launch("ema_update_kernel");
+}
+int ogm_coeff(const double* stats, float alpha, float* coeff, cudaStream_t s) {
+  LF_LAUNCH("ogm_coeff", s, (ogm_coeff_kernel<<<1, 1, 0, s>>>(stats, alpha, coeff)));
+  return check_launch("ogm_coeff_kernel");
+}
+
+}  // namespace lf

@@ -1,0 +1,31 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/lf_fusion.h"
+
+namespace lf {
+
+struct RowsArgs {
+  const float* z[2];     // (B,C) logits
+  float* avg;            // (B,C)
+  float* zdf;            // (B,C) QMF
+  float* conf;           // (2,B) QMF
+  float* rowstat;        // (B,4): lse1, lse2, lse_joint, - (QMF forward -> backward)
+  float* dz[2];          // (B,C)
+  const int64_t* label;  // (B)
+  const float* qmf_g;    // (2,B)
+  const float* ema_off;  // (2,C)
+  float* partials;       // [blocks][stat_len]
+  double* stats;
+  int B, B_global, C;
+};
+
+__host__ __device__ inline int stat_len_dev(int C) { return LF_STATS_HEADER + 2 * C; }
+
+int rows_forward(const RowsArgs& a, int mode, cudaStream_t s);
+int rows_backward(const RowsArgs& a, int mode, cudaStream_t s);
+int loss_finalize(const double* stats, int mode, int Bg, float* out, cudaStream_t s);
+int ema_update(float* x, float* off, const double* stats, int C, int Bg, float beta, cudaStream_t s);
+int ogm_coeff(const double* stats, float alpha, float* coeff, cudaStream_t s);
+
+}  // namespace lf

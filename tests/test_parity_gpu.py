@@ -1,0 +1,222 @@
+"""GPU parity: the CUDA path (through the C-ABI via LateFusionStep) against the golden vectors produced by
+the unmodified reference, and against the CPU oracle on seeded inputs.  Tolerances are BASELINE.json's:
+1e-5 relative (fp32 path), 2e-2 (tensor-pipe path)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import late_fusion as O
+from tests.util import load_golden, assert_close, relerr, t, TOL_FP32, TOL_TENSOR
+
+pytestmark = pytest.mark.gpu
+
+QMF_CASES = ["qmf_cremad_b64", "qmf_small_c11", "qmf_food_c101", "qmf_d768_c7", "qmf_b2"]
+OGM_CASES = ["ogm_cremad_b48", "ogm_wide_c309", "jlogits_enrico_b32"]
+
+
+def _step(**kw):
+    from multimodal_clinical_b200.step import LateFusionStep
+    return LateFusionStep(device="cuda:0", **kw)
+
+
+def cu(x):
+    return t(x).cuda()
+
+
+@pytest.mark.parametrize("name", QMF_CASES)
+def test_qmf_cuda_matches_reference_golden(name):
+    g = load_golden(name)
+    B, D, C, N, steps = [int(v) for v in g["meta"]]
+    eng = _step(num_classes=C, mode="qmf", n_data=N)
+    W = [cu(g["W1"]), cu(g["W2"])]
+    b = [cu(g["b1"]), cu(g["b2"])]
+    for s in range(steps):
+        p = f"s{s}_"
+        out = eng.step([cu(g[p + "f1"]), cu(g[p + "f2"])], W, b, cu(g[p + "y"]), idx=cu(g[p + "idx"]))
+        torch.cuda.synchronize()
+        assert_close(out.logits[0], g[p + "z1"], TOL_FP32, "z1")
+        assert_close(out.logits[1], g[p + "z2"], TOL_FP32, "z2")
+        assert_close(out.avg_logits, g[p + "avg"], TOL_FP32, "avg")
+        assert_close(out.logits_df, g[p + "zdf"], TOL_FP32, "zdf")
+        assert_close(out.loss, g[p + "loss"], TOL_FP32, f"loss step {s}")
+        for m in range(2):
+            assert_close(out.dweight[m], g[p + f"dW{m+1}"], TOL_FP32, f"dW{m+1} step {s}")
+            assert_close(out.dbias[m], g[p + f"db{m+1}"], TOL_FP32, f"db{m+1} step {s}")
+            assert_close(out.dfeat[m], g[p + f"df{m+1}"], TOL_FP32, f"df{m+1} step {s}")
+        assert_close(eng.ema_x, g[p + "ema_x"], TOL_FP32, "ema_x")
+        assert_close(eng.ema_offset, g[p + "ema_off"], 1e-4, "ema_off")
+        assert_close(eng.correctness, g[p + "corr"], 1e-7, "history.correctness")
+        assert_close(eng.confidence, g[p + "confid"], 1e-6, "history.confidence")
+        acc = out.accuracies()
+        for k, gk in (("x1_acc_uncal", "acc_x1_uncal"), ("x2_acc_uncal", "acc_x2_uncal"), ("x1_acc_cal", "acc_x1_cal"),
+                      ("x2_acc_cal", "acc_x2_cal"), ("joint_acc", "acc_joint"), ("df_acc", "acc_df")):
+            assert abs(acc[k] - float(g[p + gk])) < 1e-6, (k, acc[k], float(g[p + gk]))
+
+
+@pytest.mark.parametrize("name", OGM_CASES)
+def test_jlogits_cuda_matches_reference_golden(name):
+    g = load_golden(name)
+    B, D, C, _, steps = [int(v) for v in g["meta"]]
+    alpha = float(g["alpha"])
+    eng = _step(num_classes=C, mode="jlogits")
+    W = [cu(g["W1"]), cu(g["W2"])]
+    b = [cu(g["b1"]), cu(g["b2"])]
+    for s in range(steps):
+        p = f"s{s}_"
+        has_df = (p + "df1") in g
+        out = eng.step([cu(g[p + "f1"]), cu(g[p + "f2"])], W, b, cu(g[p + "y"]), need_dfeat=has_df, ogm_alpha=alpha)
+        torch.cuda.synchronize()
+        assert_close(out.logits[0], g[p + "z1"], TOL_FP32, "z1")
+        assert_close(out.logits[1], g[p + "z2"], TOL_FP32, "z2")
+        assert_close(out.avg_logits, g[p + "avg"], TOL_FP32, "avg")
+        assert_close(out.loss, g[p + "loss"], TOL_FP32, "loss")
+        for m in range(2):
+            assert_close(out.dweight[m], g[p + f"dW{m+1}"], TOL_FP32, f"dW{m+1}")
+            assert_close(out.dbias[m], g[p + f"db{m+1}"], TOL_FP32, f"db{m+1}")
+            if has_df:
+                assert_close(out.dfeat[m], g[p + f"df{m+1}"], TOL_FP32, f"df{m+1}")
+        assert_close(eng.ema_x, g[p + "ema_x"], TOL_FP32, "ema_x")
+        acc = out.accuracies()
+        for k, gk in (("x1_acc_uncal", "acc_x1_uncal"), ("x2_acc_uncal", "acc_x2_uncal"), ("x1_acc_cal", "acc_x1_cal"),
+                      ("x2_acc_cal", "acc_x2_cal"), ("joint_acc", "acc_joint")):
+            assert abs(acc[k] - float(g[p + gk])) < 1e-6, k
+        if (p + "coeff") in g:
+            assert_close(eng.coeff, g[p + "coeff"], 2e-5, "OGM-GE coefficients")
+
+
+@pytest.mark.parametrize("B,D,C,N", [(257, 512, 6, 1000), (1000, 768, 101, 5000), (130, 128, 309, 300),
+                                     (33, 36, 1, 50), (4096, 512, 6, 6698)])
+def test_qmf_cuda_matches_oracle_seeded(B, D, C, N):
+    """Seeded random inputs, three steps of History evolution, checked against the CPU oracle in fp64
+    (the oracle's own fp32 summation noise would otherwise eat the 1e-5 budget at large B)."""
+    inp = O.make_inputs(B, D, C, seed=B + C, n_data=N)
+    eng = _step(num_classes=C, mode="qmf", n_data=N)
+    hist = O.HistoryState(N)
+    ema = torch.zeros(2, C, dtype=torch.float64)
+    W = [inp["W1"], inp["W2"]]; b = [inp["b1"], inp["b2"]]
+    for s in range(3):
+        step_in = O.make_inputs(B, D, C, seed=100 * s + B, n_data=N)
+        f = [step_in["f1"], step_in["f2"]]
+        ref = O.qmf_step(f, W, b, step_in["y"], step_in["idx"], hist, ema_x=ema, dtype=torch.float64)
+        ema = ref["ema_x"]
+        out = eng.step([x.cuda() for x in f], [x.cuda() for x in W], [x.cuda() for x in b], step_in["y"].cuda(),
+                       idx=step_in["idx"].cuda())
+        torch.cuda.synchronize()
+        assert_close(out.loss, ref["loss"], TOL_FP32, "loss")
+        assert_close(out.logits_df, ref["logits_df"], TOL_FP32, "zdf")
+        for m in range(2):
+            assert_close(out.logits[m], ref["logits"][m], TOL_FP32, "logits")
+            assert_close(out.dweight[m], ref["dW"][m], TOL_FP32, "dW")
+            assert_close(out.dbias[m], ref["db"][m], TOL_FP32, "db")
+            assert_close(out.dfeat[m], ref["dfeat"][m], TOL_FP32, "dfeat")
+        assert_close(eng.correctness, hist.correctness, 1e-6, "correctness")
+        assert_close(eng.ema_x, ref["ema_x"], TOL_FP32, "ema")
+
+
+@pytest.mark.parametrize("B,D,C", [(8192, 512, 6), (513, 512, 20), (2048, 768, 101), (777, 512, 309), (5, 8, 2)])
+def test_jlogits_cuda_matches_oracle_seeded(B, D, C):
+    inp = O.make_inputs(B, D, C, seed=B + C)
+    eng = _step(num_classes=C, mode="jlogits")
+    ref = O.jlogits_step([inp["f1"], inp["f2"]], [inp["W1"], inp["W2"]], [inp["b1"], inp["b2"]], inp["y"],
+                         ema_x=torch.zeros(2, C, dtype=torch.float64), dtype=torch.float64)
+    out = eng.step([inp["f1"].cuda(), inp["f2"].cuda()], [inp["W1"].cuda(), inp["W2"].cuda()],
+                   [inp["b1"].cuda(), inp["b2"].cuda()], inp["y"].cuda(), ogm_alpha=0.8)
+    torch.cuda.synchronize()
+    assert_close(out.loss, ref["loss"], TOL_FP32, "loss")
+    for m in range(2):
+        assert_close(out.logits[m], ref["logits"][m], TOL_FP32, "logits")
+        assert_close(out.dweight[m], ref["dW"][m], TOL_FP32, "dW")
+        assert_close(out.dbias[m], ref["db"][m], TOL_FP32, "db")
+        assert_close(out.dfeat[m], ref["dfeat"][m], TOL_FP32, "dfeat")
+    k = O.ogm_coeffs(ref["score1"], ref["score2"], 0.8)
+    assert_close(eng.coeff, np.array(k), 2e-5, "coeff")
+    acc = out.accuracies()
+    assert abs(acc["joint_acc"] - ref["acc_joint"]) < 2.0 / B
+    assert abs(acc["x1_acc_cal"] - ref["acc_x1_cal"]) < 2.0 / B
+
+
+def test_step_is_deterministic_run_to_run():
+    inp = O.make_inputs(3000, 512, 6, seed=3, n_data=4000)
+    outs = []
+    for _ in range(2):
+        eng = _step(num_classes=6, mode="qmf", n_data=4000)
+        o = eng.step([inp["f1"].cuda(), inp["f2"].cuda()], [inp["W1"].cuda(), inp["W2"].cuda()],
+                     [inp["b1"].cuda(), inp["b2"].cuda()], inp["y"].cuda(), idx=inp["idx"].cuda())
+        torch.cuda.synchronize()
+        outs.append([o.loss.clone(), o.dweight[0].clone(), o.dfeat[1].clone(), eng.correctness.clone()])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b), "fused step must be bit-reproducible (reference runs deterministic=True)"
+
+
+def test_qmf_batch_of_one_is_rejected():
+    """The reference raises for B == 1; the C-ABI returns LF_ERR_BAD_ARG."""
+    from multimodal_clinical_b200._lib import LfError
+    eng = _step(num_classes=3, mode="qmf", n_data=10)
+    inp = O.make_inputs(1, 16, 3, seed=1, n_data=10)
+    with pytest.raises(LfError):
+        eng.step([inp["f1"].cuda(), inp["f2"].cuda()], [inp["W1"].cuda(), inp["W2"].cuda()],
+                 [inp["b1"].cuda(), inp["b2"].cuda()], inp["y"].cuda(), idx=inp["idx"].cuda())
+
+
+def test_qmf_degenerate_history_gives_nan_loss():
+    """All N indices covered by one batch on step 1 -> max == min -> NaN margins."""
+    N = 16
+    inp = O.make_inputs(N, 32, 4, seed=2)
+    eng = _step(num_classes=4, mode="qmf", n_data=N)
+    out = eng.step([inp["f1"].cuda(), inp["f2"].cuda()], [inp["W1"].cuda(), inp["W2"].cuda()],
+                   [inp["b1"].cuda(), inp["b2"].cuda()], inp["y"].cuda(), idx=torch.arange(N).cuda())
+    assert torch.isnan(out.loss).item()
+
+
+@pytest.mark.parametrize("mode", ["OGM", "OGM_GE", "noise"])
+def test_modulate_scale_and_noise_moments(mode):
+    """existing_algos/OGM_GE.py:42-54: exact scale when noise is off; with noise on, the residual
+    (g' - k g)/sigma must look N(0,1) (mean, std, kurtosis) and non-4-D grads stay untouched."""
+    torch.manual_seed(0)
+    eng = _step(num_classes=6, mode="jlogits")
+    eng.coeff.copy_(torch.tensor([0.3096, 1.0]))
+    shapes = [(64, 3, 7, 7), (64, 64, 3, 3), (128, 64, 3, 3), (512, 512, 3, 3), (7, 5, 3, 1)]
+    grads = [torch.randn(s, device="cuda") * (1e-3 * (i + 1)) + 1e-4 for i, s in enumerate(shapes)]
+    bn = torch.randn(64, device="cuda")
+    before = [g.clone() for g in grads]
+    bn0 = bn.clone()
+    eng.modulate(grads + [bn], which=0, modulation=mode, seed=1234, offset=0)
+    torch.cuda.synchronize()
+    assert torch.equal(bn, bn0)
+    k = 1.0 if mode == "noise" else 0.3096
+    for g, g0 in zip(grads, before):
+        if mode == "OGM":
+            assert torch.equal(g, g0 * torch.tensor(k, device="cuda")) or relerr(g, g0 * k) < 1e-7
+            continue
+        sigma = g0.std().item() + 1e-8
+        z = ((g - g0 * k) / sigma).double().flatten()
+        n = z.numel()
+        tol = 6.0 / np.sqrt(n)
+        assert abs(z.mean().item()) < tol, "noise mean"
+        assert abs(z.std().item() - 1.0) < tol + 2e-3, "noise std vs std(g)+1e-8"
+        if n > 10000:
+            assert abs((z ** 4).mean().item() - 3.0) < 0.15, "noise kurtosis"
+    if mode != "OGM":
+        # Philox stream is addressable: same (seed, offset) -> same draws; different offset -> different
+        g2 = [b.clone() for b in before]
+        eng.modulate(g2, which=0, modulation=mode, seed=1234, offset=0)
+        assert all(torch.equal(a, b) for a, b in zip(grads, g2))
+        g3 = [b.clone() for b in before]
+        eng.modulate(g3, which=0, modulation=mode, seed=1234, offset=7)
+        assert not torch.equal(grads[1], g3[1])
+
+
+def test_modulate_matches_reference_golden():
+    g = load_golden("ogm_modulate_small")
+    eng = _step(num_classes=6, mode="jlogits")
+    z1, z2, y = t(g["z1"]), t(g["z2"]), t(g["y"])
+    s1, s2 = O.ogm_scores(z1, z2, y)
+    k = O.ogm_coeffs(float(s1), float(s2), float(g["alpha"]))
+    eng.coeff.copy_(torch.tensor(k))
+    names = sorted(n[len("before/"):] for n in g if n.startswith("before/"))
+    for which, enc in enumerate(("x1_model", "x2_model")):
+        sel = [n for n in names if n.startswith(enc)]
+        grads = [cu(g["before/" + n]).clone() for n in sel]
+        eng.modulate(grads, which=which, modulation="OGM", seed=0, offset=0)
+        for n, gr in zip(sel, grads):
+            assert_close(gr, g["after_OGM/" + n], 1e-6, n)
