@@ -1,0 +1,60 @@
+"""Collective plumbing of the batch-sharded late-fusion step (one process per GPU, torch.distributed).
+
+The reference defines no multi-GPU semantics; here the global result is DEFINED as the
+single-GPU reference applied to the concatenation of all ranks' shards in rank order.  That needs:
+  * all-reduce(sum) of the packed statistics (score sums for OGM-GE, CE sums for the QMF History, logit
+    sums for the EMA, accuracy counts) before anything derived from a batch mean,
+  * all-gather of (idx, conf) for QMF, because the History scatter, the global min/max and the
+    flattened-roll neighbour (which crosses shard and modality boundaries) need the whole batch,
+  * all-reduce(sum) of the head gradients.
+Works on any backend (NCCL on the GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world(pg=None) -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(pg), dist.get_world_size(pg)
+    return 0, 1
+
+
+def shard_range(rank: int, batch_local: int) -> Tuple[int, int]:
+    """[begin, begin+count) of this rank's samples in the global batch order."""
+    return rank * batch_local, batch_local
+
+
+def allreduce_sum_(t: torch.Tensor, pg=None) -> torch.Tensor:
+    if world(pg)[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg)
+    return t
+
+
+def gather_batch(idx_local: torch.Tensor, conf_local: torch.Tensor, pg=None
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """idx (B,) int64 and conf (2,B) of every rank -> idx (Bg,), conf (2,Bg) in global batch order."""
+    rank, ws = world(pg)
+    if ws == 1:
+        return idx_local, conf_local
+    B = idx_local.numel()
+    idx_g = torch.empty(ws * B, dtype=idx_local.dtype, device=idx_local.device)
+    dist.all_gather_into_tensor(idx_g, idx_local.contiguous(), group=pg)
+    cg = torch.empty(ws, 2, B, dtype=conf_local.dtype, device=conf_local.device)
+    dist.all_gather_into_tensor(cg, conf_local.contiguous(), group=pg)
+    return idx_g, cg.permute(1, 0, 2).reshape(2, ws * B).contiguous()
+
+
+def pack_grad_exchange(grad_flat: torch.Tensor, n_head: int, stats: torch.Tensor, cal_lo: int, cal_hi: int,
+                       pg=None) -> None:
+    """ONE all-reduce for [dW1|db1|dW2|db2|calibrated counts]: the two fp64 counts ride in the tail of the
+    fp32 gradient buffer (exact: counts < 2^24)."""
+    if world(pg)[1] == 1:
+        return
+    grad_flat[n_head:n_head + (cal_hi - cal_lo)] = stats[cal_lo:cal_hi].to(grad_flat.dtype)
+    dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=pg)
+    stats[cal_lo:cal_hi] = grad_flat[n_head:n_head + (cal_hi - cal_lo)].to(stats.dtype)

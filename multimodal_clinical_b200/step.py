@@ -18,7 +18,7 @@ from typing import List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, parallel
 from ._lib import (LF_MODE_JLOGITS, LF_MODE_QMF, LF_PREC_FP32, LF_PREC_TF32, LF_STATS_HEADER, STAT,
                    LfHeadsArgs, LfQmfArgs, LfTensorList, check)
 
@@ -87,8 +87,7 @@ class LateFusionStep:
         self.precision = {"fp32": LF_PREC_FP32, "tf32": LF_PREC_TF32}[precision]
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.rank, self.world = parallel.world(process_group)
         self.smoothing = float(ema_smoothing)
         dev = self.device
         self.ema_x = torch.zeros(2, self.C, device=dev)          # EMA.x      (utils/EMA.py:25)
@@ -174,8 +173,7 @@ class LateFusionStep:
         st = _stream()
 
         check(lib.lf_heads_forward(C.byref(a), st), "lf_heads_forward")
-        if self.world > 1:
-            dist.all_reduce(self.stats, group=self.pg)            # score sums, CE sums, logit sums, counts
+        parallel.allreduce_sum_(self.stats, self.pg)              # score sums, CE sums, logit sums, counts
         if update_ema:
             check(lib.lf_ema_update(_ptr(self.ema_x), _ptr(self.ema_offset), _ptr(self.stats), Cn, Bg,
                                     self.smoothing, st), "lf_ema_update")
@@ -186,30 +184,20 @@ class LateFusionStep:
             if idx is None:
                 raise ValueError("QMF step needs the dataset indices of the batch (idx)")
             idx = idx.to(device=self.device, dtype=torch.int64).contiguous().view(-1)
-            conf_l = bufs["conf"]
-            if self.world > 1:
-                idx_g = torch.empty(Bg, dtype=torch.int64, device=self.device)
-                dist.all_gather_into_tensor(idx_g, idx, group=self.pg)
-                cg = torch.empty(self.world, 2, B, device=self.device)
-                dist.all_gather_into_tensor(cg, conf_l, group=self.pg)
-                conf_g = cg.permute(1, 0, 2).reshape(2, Bg).contiguous()
-            else:
-                idx_g, conf_g = idx, conf_l
+            idx_g, conf_g = parallel.gather_batch(idx, bufs["conf"], self.pg)
             q = LfQmfArgs()
             q.batch_global, q.n_data = Bg, self.n_data
             q.idx, q.conf = _ptr(idx_g), _ptr(conf_g)
             q.correctness, q.confidence = _ptr(self.correctness), _ptr(self.confidence)
             q.last_writer, q.step_base = _ptr(self.last_writer), self.step_base
             q.stats, q.qmf_g, q.target_out = _ptr(self.stats), _ptr(bufs["qmf_g"]), None
-            q.g_begin, q.g_count = self.rank * B, B
+            q.g_begin, q.g_count = parallel.shard_range(self.rank, B)
             q.workspace, q.workspace_bytes = _ptr(self.qmf_ws), self.qmf_ws.numel()
             check(lib.lf_qmf_history_step(C.byref(q), st), "lf_qmf_history_step")
             self.step_base += Bg
         check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
-        if self.world > 1:
-            gf[2 * (n + Cn):] = self.stats[STAT["CNT_X1_CAL"]:STAT["CNT_X2_CAL"] + 1].float()
-            dist.all_reduce(gf, group=self.pg)                    # head gradients + calibrated counts
-            self.stats[STAT["CNT_X1_CAL"]:STAT["CNT_X2_CAL"] + 1] = gf[2 * (n + Cn):].double()
+        # head gradients + calibrated counts: one all-reduce
+        parallel.pack_grad_exchange(gf, 2 * (n + Cn), self.stats, STAT["CNT_X1_CAL"], STAT["CNT_X2_CAL"] + 1, self.pg)
         check(lib.lf_loss_finalize(_ptr(self.stats), self.mode, Bg, _ptr(self.loss), st), "lf_loss_finalize")
 
         return StepOutput(

@@ -1,0 +1,115 @@
+"""CPU-side checks of the C-ABI boundary: the library builds and loads, exports every symbol the header
+declares (and nothing the ctypes table does not know), the POD structs agree in size with the C side,
+argument validation fails loudly, and nothing in the product package reaches for the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lf_fusion.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from multimodal_clinical_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from multimodal_clinical_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/lf_fusion.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.lf_abi_version() == 1
+
+
+def test_struct_layout_matches_c(tmp_path):
+    """sizeof/offsetof computed by gcc from the header must equal the ctypes mirror."""
+    from multimodal_clinical_b200 import _lib
+    prog = tmp_path / "layout.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lf_fusion.h"\nint main(){'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(LfHeadsArgs), offsetof(LfHeadsArgs, feat),'
+                    'offsetof(LfHeadsArgs, stats), sizeof(LfQmfArgs), offsetof(LfQmfArgs, step_base),'
+                    'offsetof(LfQmfArgs, workspace), sizeof(LfTensorList)); return 0;}')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(_lib.LfHeadsArgs), _lib.LfHeadsArgs.feat.offset, _lib.LfHeadsArgs.stats.offset,
+            C.sizeof(_lib.LfQmfArgs), _lib.LfQmfArgs.step_base.offset, _lib.LfQmfArgs.workspace.offset,
+            C.sizeof(_lib.LfTensorList)]
+    assert got == want
+
+
+def test_workspace_sizes_are_monotone(lib):
+    a = lib.lf_workspace_bytes(64, 512, 6)
+    b = lib.lf_workspace_bytes(8192, 512, 6)
+    c = lib.lf_workspace_bytes(8192, 768, 101)
+    assert 0 < a <= b < c
+    assert lib.lf_workspace_bytes(0, 512, 6) == 0
+    assert lib.lf_qmf_workspace_bytes(1000) > 0 and lib.lf_modulate_workspace_bytes() >= 2 * 8 * 64
+
+
+def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
+    from multimodal_clinical_b200 import _lib
+    a = _lib.LfHeadsArgs()
+    assert lib.lf_heads_forward(C.byref(a), None) == -1            # LF_ERR_BAD_ARG
+    assert b"bad sizes" in lib.lf_last_error()
+    a.batch, a.batch_global, a.dim, a.classes = 8, 8, 30, 4          # dim not a multiple of 4
+    assert lib.lf_heads_forward(C.byref(a), None) == -1
+    q = _lib.LfQmfArgs()
+    assert lib.lf_qmf_history_step(C.byref(q), None) == -1
+    tl = _lib.LfTensorList()
+    tl.count = 65
+    assert lib.lf_ogm_modulate(C.byref(tl), None, 0, 0, 0, None, 0, None) == -1
+    tl.count = 0                                                      # no 4-D grads (Food101 MLPs): no-op, OK
+    assert lib.lf_ogm_modulate(C.byref(tl), None, 2, 0, 0, None, 0, None) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from multimodal_clinical_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.LfError, match="no CPU/eager fallback"):
+        _lib.load()
+
+
+def test_step_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from multimodal_clinical_b200 import _lib
+    from multimodal_clinical_b200.step import LateFusionStep
+    with pytest.raises(_lib.LfError):
+        LateFusionStep(6, mode="jlogits")
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "multimodal_clinical_b200")
+    bad = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "/root/reference" in txt:
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad
+
+
+def test_sass_is_sm100a():
+    so = os.path.join(ROOT, "multimodal_clinical_b200", "_lf_fusion.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
