@@ -44,9 +44,9 @@ def gather_batch(idx_local: torch.Tensor, conf_local: torch.Tensor, pg=None
     B = idx_local.numel()
     idx_g = torch.empty(ws * B, dtype=idx_local.dtype, device=idx_local.device)
     dist.all_gather_into_tensor(idx_g, idx_local.contiguous(), group=pg)
-    cg = torch.empty(ws, 2, B, dtype=conf_local.dtype, device=conf_local.device)
-    dist.all_gather_into_tensor(cg, conf_local.contiguous(), group=pg)
-    return idx_g, cg.permute(1, 0, 2).reshape(2, ws * B).contiguous()
+    cg = torch.empty(ws * 2, B, dtype=conf_local.dtype, device=conf_local.device)   # rank-major concat on dim 0
+    dist.all_gather_into_tensor(cg, conf_local.contiguous().view(2, B), group=pg)
+    return idx_g, cg.view(ws, 2, B).permute(1, 0, 2).reshape(2, ws * B).contiguous()
 
 
 def pack_grad_exchange(grad_flat: torch.Tensor, n_head: int, stats: torch.Tensor, cal_lo: int, cal_hi: int,
