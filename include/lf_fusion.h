@@ -179,6 +179,18 @@ int64_t lf_launch_count(void);
 void lf_profile_enable(int32_t on);
 int32_t lf_profile_report(char* buf, int32_t buf_bytes);
 
+/*
+ * Test hook (no reference counterpart): ONE tensor-pipe (tcgen05 kind::tf32 + TMA) GEMM,
+ * out(M,N) = A*B (+bias), so the kernel behind LF_PREC_TF32 can be checked in isolation.
+ *   a_mn_major = 0: A is (M,K) row-major, pitch lda.   1: A is stored (K,M) row-major (A = stored^T)
+ *   b_mn_major = 0: B is stored (N,K) row-major, pitch ldb (out = A*stored^T).   1: B is (K,N) row-major
+ * block_n: N tile (multiple of 16; 32 if b_mn_major), splits: split-K factor writing partial outputs
+ * split_stride elements apart.
+ */
+int lf_debug_tc_gemm(const float* A, const float* B, const float* bias, float* out, int32_t M, int32_t N,
+                     int32_t K, int32_t lda, int32_t ldb, int32_t ld_out, int32_t a_mn_major,
+                     int32_t b_mn_major, int32_t block_n, int32_t splits, int64_t split_stride, void* stream);
+
 /* Last error message of the calling thread (host string). */
 const char* lf_last_error(void);
 int32_t lf_abi_version(void);

@@ -1,0 +1,45 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lf {
+
+// Device-side parameters of tc_gemm_kernel.
+struct TcGemmParams {
+  int M, N, K;             // true problem sizes (ragged edges are zero-filled by TMA / masked on store)
+  int block_n;             // N tile: multiple of 16 (32 when B is MN-major), <= 256
+  int splits;              // split-K factor (gridDim.z = batch * splits)
+  int k_per_split;         // multiple of 32
+  int stages;              // smem ring depth
+  int tmem_cols;           // power of two >= block_n
+  int a_mn_major, b_mn_major;
+  int vec_store;           // 128-bit epilogue stores are legal
+  float* out[2];
+  const float* bias[2];
+  long long ld_out;        // output row pitch (elements)
+  long long split_stride;  // elements between split partials
+};
+
+// Host-side description of one (batched x2) GEMM:  out[b] (M x N) = A[b] * B[b] (+ bias[b]).
+//   a_mn_major = 0: A is (M x K) row-major with pitch lda (K contiguous)
+//   a_mn_major = 1: A is stored (K x M) row-major with pitch lda (M contiguous), i.e. A = stored^T
+//   b_mn_major = 0: B is stored (N x K) row-major with pitch ldb (K contiguous), i.e. out = A * stored^T
+//   b_mn_major = 1: B is (K x N) row-major with pitch ldb (N contiguous)
+struct TcGemmDesc {
+  int nbatch;
+  const float* A[2];
+  const float* B[2];
+  const float* bias[2];
+  float* out[2];
+  int M, N, K;
+  long long lda, ldb, ld_out;
+  int a_mn_major, b_mn_major;
+  int block_n;
+  int splits;
+  long long split_stride;
+  const char* name;
+};
+
+int tc_gemm(const TcGemmDesc& d, cudaStream_t s);
+
+}  // namespace lf

@@ -1,0 +1,59 @@
+"""The tcgen05/TMA TF32 GEMM kernel in isolation (through the C-ABI test hook lf_debug_tc_gemm), in the
+three operand orientations the wide-head path uses, against an fp64 matmul.  Tolerance: TF32 class (2e-2
+norm-wise is the contract; these shapes come out near 1e-3)."""
+import pytest
+import torch
+
+from tests.util import relerr, TOL_TENSOR
+
+pytestmark = pytest.mark.gpu
+
+
+def run(A, B, bias, M, N, K, a_mn, b_mn, block_n, splits=1):
+    from multimodal_clinical_b200 import _lib
+    lib = _lib.load()
+    out = torch.full((splits, M, N), float("nan"), device="cuda")
+    rc = lib.lf_debug_tc_gemm(A.data_ptr(), B.data_ptr(), bias.data_ptr() if bias is not None else None,
+                              out.data_ptr(), M, N, K, A.stride(0), B.stride(0), N, a_mn, b_mn, block_n, splits,
+                              M * N, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "lf_debug_tc_gemm")
+    torch.cuda.synchronize()
+    return out.sum(0)
+
+
+# (M, N, K, block_n): logits-like  Z = F W^T + b   (A K-major, B K-major)
+@pytest.mark.parametrize("M,N,K,bn", [(128, 16, 32, 16), (256, 112, 768, 112), (1000, 101, 768, 112),
+                                      (300, 309, 512, 160), (128, 64, 40, 64), (4096, 101, 768, 112)])
+def test_tc_gemm_logits_orientation(M, N, K, bn):
+    torch.manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda")
+    W = torch.randn(N, K, device="cuda") / K ** 0.5
+    bias = torch.randn(N, device="cuda")
+    got = run(A, W, bias, M, N, K, 0, 0, bn)
+    ref = A.double() @ W.double().T + bias.double()
+    assert relerr(got, ref) < 5e-3, relerr(got, ref)
+
+
+# dfeat-like  dF = dZ W  (A K-major with padded pitch, B MN-major)
+@pytest.mark.parametrize("M,N,K,bn", [(128, 32, 8, 32), (256, 768, 101, 256), (777, 512, 309, 256), (130, 96, 6, 32)])
+def test_tc_gemm_dfeat_orientation(M, N, K, bn):
+    torch.manual_seed(M + K)
+    ldz = (K + 3) // 4 * 4
+    dZ = torch.randn(M, ldz, device="cuda")
+    W = torch.randn(K, N, device="cuda")
+    got = run(dZ[:, :K], W, None, M, N, K, 0, 1, bn)
+    ref = dZ[:, :K].double() @ W.double()
+    assert relerr(got, ref) < 5e-3, relerr(got, ref)
+
+
+# dweight-like  dW = dZ^T F  (both MN-major, split-K)
+@pytest.mark.parametrize("M,N,K,bn,splits", [(32, 32, 32, 32, 1), (101, 768, 2048, 256, 1), (101, 768, 5000, 256, 7),
+                                             (309, 512, 1111, 256, 3), (6, 512, 700, 256, 2)])
+def test_tc_gemm_dweight_orientation(M, N, K, bn, splits):
+    torch.manual_seed(M + K)
+    ldz = (M + 3) // 4 * 4
+    dZ = torch.randn(K, ldz, device="cuda")
+    F = torch.randn(K, N, device="cuda")
+    got = run(dZ[:, :M], F, None, M, N, K, 1, 1, bn, splits)
+    ref = dZ[:, :M].double().T @ F.double()
+    assert relerr(got, ref) < 5e-3, relerr(got, ref)
