@@ -68,7 +68,7 @@ typedef struct LfHeadsArgs {
   int32_t mode;         /* LF_MODE_* */
   int32_t precision;    /* LF_PREC_* */
   int32_t need_dfeat;   /* 0: encoders frozen (enrico/joint_model.py:36-38), dfeat not produced */
-  int32_t reserved0;
+  int32_t ld_dlogits;   /* row pitch (elements) of dlogits; 0 = classes.  LF_PREC_TF32 needs a multiple of 4 (TMA) */
   const float* feat[2];   /* (B,D) pooled encoder features  cremad/joint_model_qmf.py:48-55 */
   const float* weight[2]; /* (C,D) x{1,2}_classifier.weight cremad/joint_model_qmf.py:26,28 */
   const float* bias[2];   /* (C)   x{1,2}_classifier.bias */

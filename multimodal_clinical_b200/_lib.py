@@ -26,7 +26,7 @@ _P2 = C.c_void_p * 2
 class LfHeadsArgs(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("batch_global", C.c_int32), ("dim", C.c_int32), ("classes", C.c_int32),
-        ("mode", C.c_int32), ("precision", C.c_int32), ("need_dfeat", C.c_int32), ("reserved0", C.c_int32),
+        ("mode", C.c_int32), ("precision", C.c_int32), ("need_dfeat", C.c_int32), ("ld_dlogits", C.c_int32),
         ("feat", _P2), ("weight", _P2), ("bias", _P2), ("label", C.c_void_p),
         ("logits", _P2), ("avg_logits", C.c_void_p), ("logits_df", C.c_void_p), ("conf", C.c_void_p),
         ("dlogits", _P2), ("dfeat", _P2), ("dweight", _P2), ("dbias", _P2),

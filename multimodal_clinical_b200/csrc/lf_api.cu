@@ -11,6 +11,7 @@
 #include "lf_common.cuh"
 #include "lf_gemm.cuh"
 #include "lf_rows.cuh"
+#include "lf_tc.cuh"
 
 namespace lf {
 
@@ -83,6 +84,14 @@ static float* rowstat_ptr(void* base, int B, int D, int C) {
   return (float*)((char*)base + (w.total - (size_t)B * 4 * sizeof(float) - 256));
 }
 
+// The tensor pipe only pays for wide heads (C = 6/20 is HBM-bound on FMA).
+static bool use_tensor_pipe(const LfHeadsArgs* a) { return a->precision == LF_PREC_TF32 && a->classes >= 32; }
+
+static int tc_block_n(int n) {            // N tile: <= 256, multiple of 16, balanced over the tiles
+  const int tiles = div_up(n, 256);
+  return div_up(div_up(n, tiles), 16) * 16;
+}
+
 static int check_heads(const LfHeadsArgs* a, bool backward) {
   if (!a) { set_error("null LfHeadsArgs"); return LF_ERR_BAD_ARG; }
   if (a->batch < 1 || a->batch_global < a->batch || a->dim < 4 || a->dim % 4 || a->classes < 1) {
@@ -102,6 +111,11 @@ static int check_heads(const LfHeadsArgs* a, bool backward) {
   if (a->need_dfeat && (!a->dfeat[0] || !a->dfeat[1])) { set_error("need_dfeat set but dfeat is null"); return LF_ERR_BAD_ARG; }
   if (backward && !a->ema_offset) { set_error("backward needs ema_offset"); return LF_ERR_BAD_ARG; }
   if (backward && a->mode == LF_MODE_QMF && !a->qmf_g) { set_error("QMF backward needs qmf_g"); return LF_ERR_BAD_ARG; }
+  if (a->ld_dlogits != 0 && a->ld_dlogits < a->classes) { set_error("ld_dlogits %d < classes %d", a->ld_dlogits, a->classes); return LF_ERR_BAD_ARG; }
+  if (use_tensor_pipe(a) && (a->ld_dlogits % 4 != 0 || a->ld_dlogits == 0)) {
+    set_error("LF_PREC_TF32 needs ld_dlogits to be a non-zero multiple of 4 (TMA row pitch), got %d", a->ld_dlogits);
+    return LF_ERR_BAD_ARG;
+  }
   if (a->workspace_bytes < lf_workspace_bytes(a->batch, a->dim, a->classes)) {
     set_error("workspace too small: %zu < %zu", a->workspace_bytes, lf_workspace_bytes(a->batch, a->dim, a->classes));
     return LF_ERR_WORKSPACE;
@@ -118,6 +132,7 @@ static RowsArgs rows_args(const LfHeadsArgs* a, const HeadsWorkspace& w) {
   r.label = a->label; r.qmf_g = a->qmf_g; r.ema_off = a->ema_offset;
   r.partials = w.row_partials; r.stats = a->stats;
   r.B = a->batch; r.B_global = a->batch_global; r.C = a->classes;
+  r.ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
   return r;
 }
 
@@ -175,7 +190,18 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
   for (int m = 0; m < 2; ++m) { g.A[m] = a->feat[m]; g.B[m] = a->weight[m]; g.bias[m] = a->bias[m]; g.C[m] = a->logits[m]; }
   g.M = a->batch; g.N = a->classes; g.K = a->dim;
   g.lda = a->dim; g.ldb = a->dim; g.ldc = a->classes;
-  rc = gemm_logits(g, 2, s);
+  if (use_tensor_pipe(a)) {
+    TcGemmDesc d;
+    d.nbatch = 2;
+    for (int m = 0; m < 2; ++m) { d.A[m] = a->feat[m]; d.B[m] = a->weight[m]; d.bias[m] = a->bias[m]; d.out[m] = a->logits[m]; }
+    d.M = a->batch; d.N = a->classes; d.K = a->dim;
+    d.lda = a->dim; d.ldb = a->dim; d.ld_out = a->classes;
+    d.a_mn_major = 0; d.b_mn_major = 0; d.block_n = tc_block_n(a->classes);
+    d.splits = 1; d.split_stride = 0; d.name = "tc_logits";
+    rc = tc_gemm(d, s);
+  } else {
+    rc = gemm_logits(g, 2, s);
+  }
   if (rc) return rc;
   return rows_forward(rows_args(a, w), a->mode, s);
 }
@@ -188,31 +214,62 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   rc = rows_backward(rows_args(a, w), a->mode, s);
   if (rc) return rc;
   const float* dz[2] = {a->dlogits[0], a->mode == LF_MODE_QMF ? a->dlogits[1] : a->dlogits[0]};
+  const int ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
+  const bool tc = use_tensor_pipe(a);
   GemmArgs g;
   if (a->need_dfeat) {
     memset(&g, 0, sizeof(g));
     for (int m = 0; m < 2; ++m) { g.A[m] = dz[m]; g.B[m] = a->weight[m]; g.bias[m] = nullptr; g.C[m] = a->dfeat[m]; }
     g.M = a->batch; g.N = a->dim; g.K = a->classes;
-    g.lda = a->classes; g.ldb = a->dim; g.ldc = a->dim;
-    rc = gemm_dfeat(g, 2, s);
+    g.lda = ldz; g.ldb = a->dim; g.ldc = a->dim;
+    if (tc) {
+      TcGemmDesc d;
+      d.nbatch = 2;
+      for (int m = 0; m < 2; ++m) { d.A[m] = dz[m]; d.B[m] = a->weight[m]; d.bias[m] = nullptr; d.out[m] = a->dfeat[m]; }
+      d.M = a->batch; d.N = a->dim; d.K = a->classes;
+      d.lda = ldz; d.ldb = a->dim; d.ld_out = a->dim;
+      d.a_mn_major = 0; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 32) * 32;
+      d.splits = 1; d.split_stride = 0; d.name = "tc_dfeat";
+      rc = tc_gemm(d, s);
+    } else {
+      rc = gemm_dfeat(g, 2, s);
+    }
     if (rc) return rc;
   }
   // dW_m = dZ_m^T F_m : split-K over the batch, partials reduced in fixed order
-  const int splits = dw_splits(a->batch, a->dim, a->classes);
+  int splits = dw_splits(a->batch, a->dim, a->classes);
   const size_t cd = (size_t)a->classes * a->dim;
   memset(&g, 0, sizeof(g));
   for (int m = 0; m < 2; ++m) { g.A[m] = dz[m]; g.B[m] = a->feat[m]; g.bias[m] = nullptr; g.C[m] = w.dw_partials + (size_t)m * kMaxSplits * cd; }
   g.M = a->classes; g.N = a->dim; g.K = a->batch;
-  g.lda = a->classes; g.ldb = a->dim; g.ldc = a->dim;
-  g.splits = splits; g.k_chunk = div_up(a->batch, splits); g.split_stride = cd;
-  rc = gemm_dweight(g, 2, s);
+  g.lda = ldz; g.ldb = a->dim; g.ldc = a->dim;
+  if (tc) {
+    TcGemmDesc d;
+    d.nbatch = 2;
+    for (int m = 0; m < 2; ++m) { d.A[m] = dz[m]; d.B[m] = a->feat[m]; d.bias[m] = nullptr; d.out[m] = w.dw_partials + (size_t)m * kMaxSplits * cd; }
+    d.M = a->classes; d.N = a->dim; d.K = a->batch;
+    d.lda = ldz; d.ldb = a->dim; d.ld_out = a->dim;
+    d.a_mn_major = 1; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 32) * 32;
+    // split-K so that (C tiles x D tiles x 2 modalities x splits) covers the 148 SMs about once or twice
+    const int tiles = div_up(a->classes, 128) * div_up(a->dim, d.block_n) * 2;
+    splits = div_up(148, tiles);
+    const int by_rows = div_up(a->batch, 128);
+    if (splits > by_rows) splits = by_rows;
+    if (splits > kMaxSplits) splits = kMaxSplits;
+    if (splits < 1) splits = 1;
+    d.splits = splits; d.split_stride = (long long)cd; d.name = "tc_dweight";
+    rc = tc_gemm(d, s);
+  } else {
+    g.splits = splits; g.k_chunk = div_up(a->batch, splits); g.split_stride = cd;
+    rc = gemm_dweight(g, 2, s);
+  }
   if (rc) return rc;
   for (int m = 0; m < 2; ++m) {
     rc = reduce_splits(w.dw_partials + (size_t)m * kMaxSplits * cd, a->dweight[m], splits, cd, s);
     if (rc) return rc;
   }
   // db_m = column sums of dZ_m
-  rc = colsum(dz, a->batch, a->classes, w.db_partials, a->dbias, s);
+  rc = colsum(dz, a->batch, a->classes, ldz, w.db_partials, a->dbias, s);
   return rc;
 }
 

@@ -128,7 +128,7 @@ int reduce_splits(const float* part, float* out, int splits, size_t n, cudaStrea
 }
 
 // db_m[c] = sum_b dZ_m[b][c]: column sums, two-stage and fixed-order like dW
-__global__ void __launch_bounds__(256) colsum_kernel(const float* dz0, const float* dz1, int B, int C, int rows_per_split,
+__global__ void __launch_bounds__(256) colsum_kernel(const float* dz0, const float* dz1, int B, int C, int ldz, int rows_per_split,
                                                      float* __restrict__ part, int max_splits) {
   const int m = blockIdx.z, split = blockIdx.y;
   const float* __restrict__ dz = m == 0 ? dz0 : dz1;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* dz0, const flo
   const int b0 = split * rows_per_split, b1 = min(B, b0 + rows_per_split);
   float s = 0.f;
   if (c < C)
-    for (int b = b0 + ty; b < b1; b += 8) s += dz[(size_t)b * C + c];
+    for (int b = b0 + ty; b < b1; b += 8) s += dz[(size_t)b * ldz + c];
   __shared__ float sm[8][33];
   sm[ty][tx] = s;
   __syncthreads();
@@ -149,11 +149,11 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* dz0, const flo
   }
 }
 
-int colsum(const float* const dz[2], int B, int C, float* part, float* const out[2], cudaStream_t s) {
+int colsum(const float* const dz[2], int B, int C, int ldz, float* part, float* const out[2], cudaStream_t s) {
   int splits = div_up(B, 256);
   if (splits > kMaxSplits) splits = kMaxSplits;
   const int rows = div_up(B, splits);
-  LF_LAUNCH("colsum", s, (colsum_kernel<<<dim3(div_up(C, 32), splits, 2), 256, 0, s>>>(dz[0], dz[1], B, C, rows, part, kMaxSplits)));
+  LF_LAUNCH("colsum", s, (colsum_kernel<<<dim3(div_up(C, 32), splits, 2), 256, 0, s>>>(dz[0], dz[1], B, C, ldz, rows, part, kMaxSplits)));
   int rc = check_launch("colsum_kernel");
   if (rc) return rc;
   for (int m = 0; m < 2; ++m) {

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
       for (int c = lane; c < C; c += 32) {
         const float av = (z1[c] + z2[c]) / 2.f;
         const float p = __expf(av - lsea);
-        a.dz[0][(size_t)b * C + c] = (p - (c == y ? 1.f : 0.f)) * dz_scale;
+        a.dz[0][(size_t)b * a.ldz + c] = (p - (c == y ? 1.f : 0.f)) * dz_scale;
       }
     }
     if (lane == 0) {
@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(256) rows_backward_kernel(RowsArgs a) {
         const float oh = (c == y) ? 1.f : 0.f;
         const float p1 = __expf(v1 - lse1), p2 = __expf(v2 - lse2);
         const float pd = __expf((v1 * c1 + v2 * c2) - lsed) - oh;
-        a.dz[0][(size_t)b * C + c] = ((p1 - oh) + c1 * pd) * invB + g1 * p1;
-        a.dz[1][(size_t)b * C + c] = ((p2 - oh) + c2 * pd) * invB + g2 * p2;
+        a.dz[0][(size_t)b * a.ldz + c] = ((p1 - oh) + c1 * pd) * invB + g1 * p1;
+        a.dz[1][(size_t)b * a.ldz + c] = ((p2 - oh) + c2 * pd) * invB + g2 * p2;
       }
     }
     warp_argmax(m1, i1); warp_argmax(m2, i2);

@@ -18,6 +18,7 @@ struct RowsArgs {
   float* partials;       // [blocks][stat_len]
   double* stats;
   int B, B_global, C;
+  int ldz;               // row pitch of dz
 };
 
 __host__ __device__ inline int stat_len_dev(int C) { return LF_STATS_HEADER + 2 * C; }

@@ -124,7 +124,8 @@ class LateFusionStep:
             b["avg"] = torch.empty(B, Cn, device=dev)
             b["zdf"] = torch.empty(B, Cn, device=dev) if qmf else None
             b["conf"] = torch.empty(2, B, device=dev) if qmf else None
-            b["dz"] = torch.empty(2 if qmf else 1, B, Cn, device=dev)
+            b["ldz"] = (Cn + 3) // 4 * 4            # dL/dlogits rows padded to 16 B (TMA row pitch, 128-bit access)
+            b["dz"] = torch.zeros(2 if qmf else 1, B, b["ldz"], device=dev)
             b["dfeat"] = torch.empty(2, B, D, device=dev) if need_dfeat else None
             # one flat buffer [dW1 | db1 | dW2 | db2 | cal1 cal2] so the gradient exchange is ONE all-reduce
             n = Cn * D
@@ -158,6 +159,7 @@ class LateFusionStep:
         a = LfHeadsArgs()
         a.batch, a.batch_global, a.dim, a.classes = B, Bg, D, Cn
         a.mode, a.precision, a.need_dfeat = self.mode, self.precision, int(need_dfeat)
+        a.ld_dlogits = bufs["ldz"]
         for m in range(2):
             a.feat[m] = _ptr(f[m]); a.weight[m] = _ptr(W[m]); a.bias[m] = _ptr(bb[m])
             a.logits[m] = _ptr(bufs["logits"][m])

@@ -137,6 +137,81 @@ def test_jlogits_cuda_matches_oracle_seeded(B, D, C):
     assert abs(acc["x1_acc_cal"] - ref["acc_x1_cal"]) < 2.0 / B
 
 
+@pytest.mark.parametrize("B,D,C,N", [(1000, 768, 101, 5000), (4096, 768, 101, 65536), (700, 512, 309, 900)])
+def test_qmf_tensor_pipe_matches_oracle(B, D, C, N):
+    """LF_PREC_TF32 (tcgen05 kind::tf32 GEMMs) against the fp64 oracle at the reduced-precision tolerance
+    BASELINE.json states for the reference's bf16-mixed mode (2e-2)."""
+    inp = O.make_inputs(B, D, C, seed=B + C, n_data=N)
+    eng = _step(num_classes=C, mode="qmf", n_data=N, precision="tf32")
+    hist = O.HistoryState(N)
+    ema = torch.zeros(2, C, dtype=torch.float64)
+    W = [inp["W1"], inp["W2"]]; b = [inp["b1"], inp["b2"]]
+    for s in range(2):
+        step_in = O.make_inputs(B, D, C, seed=100 * s + B, n_data=N)
+        f = [step_in["f1"], step_in["f2"]]
+        ref = O.qmf_step(f, W, b, step_in["y"], step_in["idx"], hist, ema_x=ema, dtype=torch.float64)
+        ema = ref["ema_x"]
+        out = eng.step([x.cuda() for x in f], [x.cuda() for x in W], [x.cuda() for x in b], step_in["y"].cuda(),
+                       idx=step_in["idx"].cuda())
+        torch.cuda.synchronize()
+        assert_close(out.loss, ref["loss"], TOL_TENSOR, "loss")
+        assert_close(out.logits_df, ref["logits_df"], TOL_TENSOR, "zdf")
+        for m in range(2):
+            assert_close(out.logits[m], ref["logits"][m], TOL_TENSOR, "logits")
+            assert_close(out.dweight[m], ref["dW"][m], TOL_TENSOR, "dW")
+            assert_close(out.dbias[m], ref["db"][m], TOL_TENSOR, "db")
+            assert_close(out.dfeat[m], ref["dfeat"][m], TOL_TENSOR, "dfeat")
+        assert_close(eng.ema_x, ref["ema_x"], TOL_TENSOR, "ema")
+
+
+@pytest.mark.parametrize("B,D,C", [(2048, 768, 101), (777, 512, 309), (4096, 512, 309)])
+def test_jlogits_tensor_pipe_matches_oracle(B, D, C):
+    inp = O.make_inputs(B, D, C, seed=B + C)
+    eng = _step(num_classes=C, mode="jlogits", precision="tf32")
+    ref = O.jlogits_step([inp["f1"], inp["f2"]], [inp["W1"], inp["W2"]], [inp["b1"], inp["b2"]], inp["y"],
+                         ema_x=torch.zeros(2, C, dtype=torch.float64), dtype=torch.float64)
+    out = eng.step([inp["f1"].cuda(), inp["f2"].cuda()], [inp["W1"].cuda(), inp["W2"].cuda()],
+                   [inp["b1"].cuda(), inp["b2"].cuda()], inp["y"].cuda(), ogm_alpha=0.8)
+    torch.cuda.synchronize()
+    assert_close(out.loss, ref["loss"], TOL_TENSOR, "loss")
+    for m in range(2):
+        assert_close(out.logits[m], ref["logits"][m], TOL_TENSOR, "logits")
+        assert_close(out.dweight[m], ref["dW"][m], TOL_TENSOR, "dW")
+        assert_close(out.dbias[m], ref["db"][m], TOL_TENSOR, "db")
+        assert_close(out.dfeat[m], ref["dfeat"][m], TOL_TENSOR, "dfeat")
+    k = O.ogm_coeffs(ref["score1"], ref["score2"], 0.8)
+    assert_close(eng.coeff, np.array(k), 1e-2, "coeff")
+
+
+def test_tensor_pipe_matches_reference_golden_wide():
+    """Golden vectors from the unmodified reference (C = 101 QMF, C = 309 jlogits) through LF_PREC_TF32."""
+    g = load_golden("qmf_food_c101")
+    B, D, C, N, steps = [int(v) for v in g["meta"]]
+    eng = _step(num_classes=C, mode="qmf", n_data=N, precision="tf32")
+    for s in range(steps):
+        p = f"s{s}_"
+        out = eng.step([cu(g[p + "f1"]), cu(g[p + "f2"])], [cu(g["W1"]), cu(g["W2"])], [cu(g["b1"]), cu(g["b2"])],
+                       cu(g[p + "y"]), idx=cu(g[p + "idx"]))
+        torch.cuda.synchronize()
+        assert_close(out.loss, g[p + "loss"], TOL_TENSOR, "loss")
+        for m in range(2):
+            assert_close(out.logits[m], g[p + f"z{m+1}"], TOL_TENSOR, "z")
+            assert_close(out.dweight[m], g[p + f"dW{m+1}"], TOL_TENSOR, "dW")
+            assert_close(out.dfeat[m], g[p + f"df{m+1}"], TOL_TENSOR, "df")
+    g = load_golden("ogm_wide_c309")
+    B, D, C, _, steps = [int(v) for v in g["meta"]]
+    eng = _step(num_classes=C, mode="jlogits", precision="tf32")
+    for s in range(steps):
+        p = f"s{s}_"
+        out = eng.step([cu(g[p + "f1"]), cu(g[p + "f2"])], [cu(g["W1"]), cu(g["W2"])], [cu(g["b1"]), cu(g["b2"])],
+                       cu(g[p + "y"]))
+        torch.cuda.synchronize()
+        assert_close(out.loss, g[p + "loss"], TOL_TENSOR, "loss")
+        for m in range(2):
+            assert_close(out.dweight[m], g[p + f"dW{m+1}"], TOL_TENSOR, "dW")
+            assert_close(out.dfeat[m], g[p + f"df{m+1}"], TOL_TENSOR, "df")
+
+
 def test_step_is_deterministic_run_to_run():
     inp = O.make_inputs(3000, 512, 6, seed=3, n_data=4000)
     outs = []
