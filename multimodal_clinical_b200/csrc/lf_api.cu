@@ -14,6 +14,10 @@
 #include "lf_tc.cuh"
 
 namespace lf {
+int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* rowstat, cudaStream_t s);  // lf_tc_fwd.cu
+}
+
+namespace lf {
 
 static thread_local char g_err[512] = "";
 
@@ -72,7 +76,8 @@ HeadsWorkspace carve_heads_workspace(void* base, int B, int D, int C) {
   char* p = (char*)base;
   size_t off = 0;
   auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes, 256); return r; };
-  w.row_partials = (float*)take((size_t)kMaxRowBlocks * stat_len(C) * sizeof(float));
+  const int part_rows = div_up(B, 128) > kMaxRowBlocks ? div_up(B, 128) : kMaxRowBlocks;   // fused forward: one row per 128 samples
+  w.row_partials = (float*)take((size_t)part_rows * stat_len(C) * sizeof(float));
   w.dw_partials = (float*)take((size_t)2 * kMaxSplits * C * D * sizeof(float));
   w.db_partials = (float*)take((size_t)2 * kMaxSplits * C * sizeof(float));
   w.total = off + (size_t)B * 4 * sizeof(float) + 256;  // + rowstat
@@ -190,6 +195,10 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
   for (int m = 0; m < 2; ++m) { g.A[m] = a->feat[m]; g.B[m] = a->weight[m]; g.bias[m] = a->bias[m]; g.C[m] = a->logits[m]; }
   g.M = a->batch; g.N = a->classes; g.K = a->dim;
   g.lda = a->dim; g.ldb = a->dim; g.ldc = a->classes;
+  if (use_tensor_pipe(a) && a->classes <= 256) {
+    // logits GEMMs + all per-sample forward math in one kernel (lf_tc_fwd.cu)
+    return tc_heads_forward(a, w.row_partials, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), s);
+  }
   if (use_tensor_pipe(a)) {
     TcGemmDesc d;
     d.nbatch = 2;
@@ -252,7 +261,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     d.a_mn_major = 1; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 32) * 32;
     // split-K so that (C tiles x D tiles x 2 modalities x splits) covers the 148 SMs about once or twice
     const int tiles = div_up(a->classes, 128) * div_up(a->dim, d.block_n) * 2;
-    splits = div_up(148, tiles);
+    splits = 148 / tiles;                    // floor: one full wave, no second-wave tail
     const int by_rows = div_up(a->batch, 128);
     if (splits > by_rows) splits = by_rows;
     if (splits > kMaxSplits) splits = kMaxSplits;

@@ -149,16 +149,25 @@ __global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
 }
 
 // stats[i] = sum over blocks (fp64, fixed order).  Entries [lo, hi) plus, when with_cols, the 2C tail.
-__global__ void finalize_stats_kernel(const float* __restrict__ partials, int nblocks, int len, int lo,
-                                      int hi, int with_cols, double* __restrict__ stats) {
-  for (int i = threadIdx.x; i < len; i += blockDim.x) {
-    const bool header = i < LF_STATS_HEADER;
-    if (header && (i < lo || i >= hi)) continue;
-    if (!header && !with_cols) continue;
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += (double)partials[(size_t)b * len + i];
-    stats[i] = s;
-  }
+// One CTA per 32 statistics: 32 columns x 8 row groups, coalesced 128-byte reads, fixed summation order.
+__global__ void __launch_bounds__(256) finalize_stats_kernel(const float* __restrict__ partials, int nblocks, int len, int lo,
+                                                             int hi, int with_cols, double* __restrict__ stats) {
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int i = blockIdx.x * 32 + tx;
+  double s = 0.0;
+  if (i < len)
+    for (int b = ty; b < nblocks; b += 8) s += (double)partials[(size_t)b * len + i];
+  __shared__ double sm[8][33];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || i >= len) return;
+  const bool header = i < LF_STATS_HEADER;
+  if (header && (i < lo || i >= hi)) return;
+  if (!header && !with_cols) return;
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += sm[w][tx];
+  stats[i] = t;
 }
 
 // Backward rows: QMF dL/dz_m and, for both modes, the calibrated counts
@@ -230,8 +239,12 @@ int rows_forward(const RowsArgs& a, int mode, cudaStream_t s) {
   }
   int rc = check_launch("rows_forward_kernel");
   if (rc) return rc;
-  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<1, 256, 0, s>>>(a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats)));
+  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(a.C), 32), 256, 0, s>>>(a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats)));
   return check_launch("finalize_stats_kernel");
+}
+
+void finalize_forward_stats(const float* partials, int nblocks, int C, double* stats, cudaStream_t s) {
+  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(C), 32), 256, 0, s>>>(partials, nblocks, stat_len(C), 0, LF_STATS_HEADER, 1, stats)));
 }
 
 int rows_backward(const RowsArgs& a, int mode, cudaStream_t s) {
@@ -240,7 +253,7 @@ int rows_backward(const RowsArgs& a, int mode, cudaStream_t s) {
   else LF_LAUNCH("rows_calibrated", s, (rows_backward_kernel<LF_MODE_JLOGITS><<<nb, 256, 0, s>>>(a)));
   int rc = check_launch("rows_backward_kernel");
   if (rc) return rc;
-  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<1, 32, 0, s>>>(a.partials, nb, stat_len(a.C), LF_STAT_CNT_X1_CAL,
+  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<1, 256, 0, s>>>(a.partials, nb, stat_len(a.C), LF_STAT_CNT_X1_CAL,
                                          LF_STAT_CNT_X2_CAL + 1, 0, a.stats)));
   return check_launch("finalize_stats_kernel(cal)");
 }

@@ -4,16 +4,19 @@
 
 namespace lf {
 
-// Device-side parameters of tc_gemm_kernel.
+// Device-side parameters of the persistent tc_gemm_kernel.
 struct TcGemmParams {
-  int M, N, K;             // true problem sizes (ragged edges are zero-filled by TMA / masked on store)
-  int block_n;             // N tile: multiple of 16 (32 when B is MN-major), <= 256
-  int splits;              // split-K factor (gridDim.z = batch * splits)
+  int M, N, K;             // true problem sizes (ragged edges are zero-filled by TMA / clipped on store)
+  int block_n;             // N tile: multiple of 16 (32 when B is MN-major or the TMA-store epilogue is used), <= 256
+  int nbatch;              // 1 or 2 (the two modalities)
+  int splits;              // split-K factor
   int k_per_split;         // multiple of 32
   int stages;              // smem ring depth
-  int tmem_cols;           // power of two >= block_n
+  int acc_cols;            // TMEM columns of one accumulator buffer (power of two >= block_n)
+  int tmem_cols;           // 2 * acc_cols (double-buffered)
   int a_mn_major, b_mn_major;
-  int vec_store;           // 128-bit epilogue stores are legal
+  int tma_store;           // epilogue writes through cp.async.bulk.tensor (needs a 16-byte output pitch)
+  int m_tiles, n_tiles, total_items;
   float* out[2];
   const float* bias[2];
   long long ld_out;        // output row pitch (elements)
