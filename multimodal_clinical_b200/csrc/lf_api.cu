@@ -14,7 +14,7 @@
 #include "lf_tc.cuh"
 
 namespace lf {
-int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* rowstat, cudaStream_t s);  // lf_tc_fwd.cu
+int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* dbpart, float* rowstat, cudaStream_t s);  // lf_tc_fwd.cu
 }
 
 namespace lf {
@@ -79,7 +79,8 @@ HeadsWorkspace carve_heads_workspace(void* base, int B, int D, int C) {
   const int part_rows = div_up(B, 128) > kMaxRowBlocks ? div_up(B, 128) : kMaxRowBlocks;   // fused forward: one row per 128 samples
   w.row_partials = (float*)take((size_t)part_rows * stat_len(C) * sizeof(float));
   w.dw_partials = (float*)take((size_t)2 * kMaxSplits * C * D * sizeof(float));
-  w.db_partials = (float*)take((size_t)2 * kMaxSplits * C * sizeof(float));
+  w.db_partials = (float*)take((size_t)part_rows * 2 * C * sizeof(float));
+  w.cal_partials = (float*)take((size_t)kMaxRowBlocks * 2 * sizeof(float));
   w.total = off + (size_t)B * 4 * sizeof(float) + 256;  // + rowstat
   return w;
 }
@@ -136,6 +137,7 @@ static RowsArgs rows_args(const LfHeadsArgs* a, const HeadsWorkspace& w) {
   r.dz[0] = a->dlogits[0]; r.dz[1] = a->dlogits[1];
   r.label = a->label; r.qmf_g = a->qmf_g; r.ema_off = a->ema_offset;
   r.partials = w.row_partials; r.stats = a->stats;
+  r.dbpart = w.db_partials; r.calpart = w.cal_partials;
   r.B = a->batch; r.B_global = a->batch_global; r.C = a->classes;
   r.ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
   return r;
@@ -197,7 +199,7 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
   g.lda = a->dim; g.ldb = a->dim; g.ldc = a->classes;
   if (use_tensor_pipe(a) && a->classes <= 256) {
     // logits GEMMs + all per-sample forward math in one kernel (lf_tc_fwd.cu)
-    return tc_heads_forward(a, w.row_partials, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), s);
+    return tc_heads_forward(a, w.row_partials, w.db_partials, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), s);
   }
   if (use_tensor_pipe(a)) {
     TcGemmDesc d;
@@ -273,13 +275,13 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     rc = gemm_dweight(g, 2, s);
   }
   if (rc) return rc;
-  for (int m = 0; m < 2; ++m) {
-    rc = reduce_splits(w.dw_partials + (size_t)m * kMaxSplits * cd, a->dweight[m], splits, cd, s);
-    if (rc) return rc;
-  }
-  // db_m = column sums of dZ_m
-  rc = colsum(dz, a->batch, a->classes, ldz, w.db_partials, a->dbias, s);
-  return rc;
+  rc = reduce_splits2(w.dw_partials, a->dweight[0], a->dweight[1], splits, kMaxSplits, cd, s);
+  if (rc) return rc;
+  // db_m (column sums of dZ_m, accumulated by the kernel that produced dZ) and the calibrated counts
+  const bool fused_fwd = tc && a->classes <= 256;
+  const int nb_db = (a->mode == LF_MODE_JLOGITS && fused_fwd) ? div_up(a->batch, 128) : row_blocks(a->batch);
+  return finalize_db_cal(w.db_partials, nb_db, a->classes, w.cal_partials, row_blocks(a->batch), a->dbias[0], a->dbias[1],
+                         a->stats, s);
 }
 
 extern "C" int lf_loss_finalize(const double* stats, int32_t mode, int32_t batch_global, float* loss_out, void* stream) {

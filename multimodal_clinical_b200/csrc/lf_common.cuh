@@ -68,7 +68,8 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct HeadsWorkspace {
   float* row_partials;   // [kMaxRowBlocks][stat_len]   per-block partial statistics
   float* dw_partials;    // [2][splits][C][D]
-  float* db_partials;    // [2][splits][C]
+  float* db_partials;    // [part_rows][2][C]  column sums of dz per producing CTA
+  float* cal_partials;   // [kMaxRowBlocks][2]
   size_t total;
 };
 constexpr int kMaxRowBlocks = 592;   // 4 CTAs per SM on 148 SMs

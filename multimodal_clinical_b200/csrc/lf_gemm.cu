@@ -122,6 +122,22 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __re
   out[i] = s;
 }
 
+// both modalities in one launch: blockIdx.y = modality, partials [m][max_splits][n]
+__global__ void reduce_splits2_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1,
+                                      int splits, int max_splits, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = part + (size_t)blockIdx.y * max_splits * n;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += p[(size_t)k * n + i];
+  (blockIdx.y == 0 ? out0 : out1)[i] = s;
+}
+
+int reduce_splits2(const float* part, float* out0, float* out1, int splits, int max_splits, size_t n, cudaStream_t s) {
+  LF_LAUNCH("reduce_dweight", s, (reduce_splits2_kernel<<<dim3(div_up((long long)n, 256), 2), 256, 0, s>>>(part, out0, out1, splits, max_splits, n)));
+  return check_launch("reduce_splits2_kernel");
+}
+
 int reduce_splits(const float* part, float* out, int splits, size_t n, cudaStream_t s) {
   LF_LAUNCH("reduce_splits", s, (reduce_splits_kernel<<<div_up((long long)n, 256), 256, 0, s>>>(part, out, splits, n)));
   return check_launch("reduce_splits_kernel");

@@ -23,6 +23,7 @@ int gemm_logits(GemmArgs g, int nbatch, cudaStream_t s);
 int gemm_dfeat(GemmArgs g, int nbatch, cudaStream_t s);
 int gemm_dweight(GemmArgs g, int nbatch, cudaStream_t s);
 int colsum(const float* const dz[2], int B, int C, int ldz, float* part, float* const out[2], cudaStream_t s);
+int reduce_splits2(const float* part, float* out0, float* out1, int splits, int max_splits, size_t n, cudaStream_t s);
 int reduce_splits(const float* part, float* out, int splits, size_t n, cudaStream_t s);
 
 }  // namespace lf

@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
   const int C = a.C, B = a.B;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int nwarp = blockDim.x / 32;
-  float* colsum = smem + (size_t)warp * 2 * C;  // [2][C] owned by this warp
-  for (int c = lane; c < 2 * C; c += 32) colsum[c] = 0.f;
+  float* colsum = smem + (size_t)warp * 3 * C;  // [z1 | z2 | dz][C] owned by this warp
+  for (int c = lane; c < 3 * C; c += 32) colsum[c] = 0.f;
   __syncwarp();
 
   float st[9];
@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
       for (int c = lane; c < C; c += 32) {
         const float av = (z1[c] + z2[c]) / 2.f;
         const float p = __expf(av - lsea);
-        a.dz[0][(size_t)b * a.ldz + c] = (p - (c == y ? 1.f : 0.f)) * dz_scale;
+        const float d = (p - (c == y ? 1.f : 0.f)) * dz_scale;
+        a.dz[0][(size_t)b * a.ldz + c] = d;
+        colsum[2 * C + c] += d;
       }
     }
     if (lane == 0) {
@@ -143,21 +145,35 @@ __global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
   }
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
     float s = 0.f;
-    for (int w = 0; w < nwarp; ++w) s += smem[(size_t)w * 2 * C + c];
+    for (int w = 0; w < nwarp; ++w) s += smem[(size_t)w * 3 * C + c];
     out[LF_STATS_HEADER + c] = s;
   }
+  if (MODE == LF_MODE_JLOGITS)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < nwarp; ++w) s += smem[(size_t)w * 3 * C + 2 * C + c];
+      a.dbpart[(size_t)blockIdx.x * 2 * C + c] = s;          // dz1 == dz2 -> db1 == db2
+      a.dbpart[(size_t)blockIdx.x * 2 * C + C + c] = s;
+    }
 }
 
 // stats[i] = sum over blocks (fp64, fixed order).  Entries [lo, hi) plus, when with_cols, the 2C tail.
 // One CTA per 32 statistics: 32 columns x 8 row groups, coalesced 128-byte reads, fixed summation order.
-__global__ void __launch_bounds__(256) finalize_stats_kernel(const float* __restrict__ partials, int nblocks, int len, int lo,
-                                                             int hi, int with_cols, double* __restrict__ stats) {
-  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+__global__ void __launch_bounds__(1024) finalize_stats_kernel(const float* __restrict__ partials, int nblocks, int len, int lo,
+                                                              int hi, int with_cols, double* __restrict__ stats) {
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;      // 32 columns x 32 row groups
   const int i = blockIdx.x * 32 + tx;
   double s = 0.0;
-  if (i < len)
-    for (int b = ty; b < nblocks; b += 8) s += (double)partials[(size_t)b * len + i];
-  __shared__ double sm[8][33];
+  if (i < len) {
+    int b = ty;
+    for (; b + 96 < nblocks; b += 128) {                          // four independent loads in flight
+      const float v0 = partials[(size_t)b * len + i], v1 = partials[(size_t)(b + 32) * len + i];
+      const float v2 = partials[(size_t)(b + 64) * len + i], v3 = partials[(size_t)(b + 96) * len + i];
+      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    }
+    for (; b < nblocks; b += 32) s += (double)partials[(size_t)b * len + i];
+  }
+  __shared__ double sm[32][33];
   sm[ty][tx] = s;
   __syncthreads();
   if (ty != 0 || i >= len) return;
@@ -166,7 +182,7 @@ __global__ void __launch_bounds__(256) finalize_stats_kernel(const float* __rest
   if (!header && !with_cols) return;
   double t = 0.0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) t += sm[w][tx];
+  for (int w = 0; w < 32; ++w) t += sm[w][tx];
   stats[i] = t;
 }
 
@@ -174,9 +190,15 @@ __global__ void __launch_bounds__(256) finalize_stats_kernel(const float* __rest
 // argmax(z_m + offset_m) == y (utils/BaseModel.py:84-89).
 template <int MODE>
 __global__ void __launch_bounds__(256) rows_backward_kernel(RowsArgs a) {
+  extern __shared__ float smem[];
   const int C = a.C, B = a.B;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int nwarp = blockDim.x / 32;
+  float* dsum = smem + (size_t)warp * 2 * C;     // [2][C] column sums of dz owned by this warp (QMF)
+  if (MODE == LF_MODE_QMF) {
+    for (int c = lane; c < 2 * C; c += 32) dsum[c] = 0.f;
+    __syncwarp();
+  }
   const float invB = 1.f / (float)a.B_global;
   float cal1 = 0.f, cal2 = 0.f;
   for (int b = blockIdx.x * nwarp + warp; b < B; b += gridDim.x * nwarp) {
@@ -203,8 +225,12 @@ __global__ void __launch_bounds__(256) rows_backward_kernel(RowsArgs a) {
         const float oh = (c == y) ? 1.f : 0.f;
         const float p1 = __expf(v1 - lse1), p2 = __expf(v2 - lse2);
         const float pd = __expf((v1 * c1 + v2 * c2) - lsed) - oh;
-        a.dz[0][(size_t)b * a.ldz + c] = ((p1 - oh) + c1 * pd) * invB + g1 * p1;
-        a.dz[1][(size_t)b * a.ldz + c] = ((p2 - oh) + c2 * pd) * invB + g2 * p2;
+        const float d1 = ((p1 - oh) + c1 * pd) * invB + g1 * p1;
+        const float d2 = ((p2 - oh) + c2 * pd) * invB + g2 * p2;
+        a.dz[0][(size_t)b * a.ldz + c] = d1;
+        a.dz[1][(size_t)b * a.ldz + c] = d2;
+        dsum[c] += d1;
+        dsum[C + c] += d2;
       }
     }
     warp_argmax(m1, i1); warp_argmax(m2, i2);
@@ -213,22 +239,66 @@ __global__ void __launch_bounds__(256) rows_backward_kernel(RowsArgs a) {
   __shared__ float s1[8], s2[8];
   if (lane == 0) { s1[warp] = cal1; s2[warp] = cal2; }
   __syncthreads();
-  if (threadIdx.x < LF_STATS_HEADER) {
+  if (threadIdx.x < 2) {
     float s = 0.f;
-    if (threadIdx.x == LF_STAT_CNT_X1_CAL) for (int w = 0; w < nwarp; ++w) s += s1[w];
-    if (threadIdx.x == LF_STAT_CNT_X2_CAL) for (int w = 0; w < nwarp; ++w) s += s2[w];
-    a.partials[(size_t)blockIdx.x * stat_len_dev(C) + threadIdx.x] = s;
+    for (int w = 0; w < nwarp; ++w) s += threadIdx.x == 0 ? s1[w] : s2[w];
+    a.calpart[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
   }
+  if (MODE == LF_MODE_QMF)
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < nwarp; ++w) s += smem[(size_t)w * 2 * C + c];
+      a.dbpart[(size_t)blockIdx.x * 2 * C + c] = s;
+    }
 }
 
-static int row_blocks(int B) {
+// dbias / calibrated counts: 32 columns x 8 row groups per CTA, fixed summation order
+__global__ void __launch_bounds__(1024) finalize_db_cal_kernel(const float* __restrict__ dbpart, int nb_db, int C,
+                                                               const float* __restrict__ calpart, int nb_cal,
+                                                               float* __restrict__ db0, float* __restrict__ db1,
+                                                               double* __restrict__ stats) {
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;      // 32 columns x 32 row groups
+  const int i = blockIdx.x * 32 + tx;             // [0, 2C): db columns; [2C, 2C+2): calibrated counts
+  const bool is_db = i < 2 * C;
+  const float* __restrict__ src = is_db ? dbpart + i : calpart + (i - 2 * C);
+  const size_t pitch = is_db ? (size_t)2 * C : 2;
+  const int nb = is_db ? nb_db : nb_cal;
+  double s = 0.0;
+  if (i < 2 * C + 2) {
+    int b = ty;
+    for (; b + 96 < nb; b += 128) {
+      const float v0 = src[(size_t)b * pitch], v1 = src[(size_t)(b + 32) * pitch];
+      const float v2 = src[(size_t)(b + 64) * pitch], v3 = src[(size_t)(b + 96) * pitch];
+      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    }
+    for (; b < nb; b += 32) s += (double)src[(size_t)b * pitch];
+  }
+  __shared__ double sm[32][33];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || i >= 2 * C + 2) return;
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < 32; ++w) t += sm[w][tx];
+  if (i < C) db0[i] = (float)t;
+  else if (i < 2 * C) db1[i - C] = (float)t;
+  else stats[LF_STAT_CNT_X1_CAL + (i - 2 * C)] = t;
+}
+
+int finalize_db_cal(const float* dbpart, int nb_db, int C, const float* calpart, int nb_cal, float* db0, float* db1,
+                    double* stats, cudaStream_t s) {
+  LF_LAUNCH("finalize_db_cal", s, (finalize_db_cal_kernel<<<div_up(2 * C + 2, 32), 1024, 0, s>>>(dbpart, nb_db, C, calpart, nb_cal, db0, db1, stats)));
+  return check_launch("finalize_db_cal");
+}
+
+int row_blocks(int B) {
   int nb = div_up(B, 8);
   return nb < kMaxRowBlocks ? (nb < 1 ? 1 : nb) : kMaxRowBlocks;
 }
 
 int rows_forward(const RowsArgs& a, int mode, cudaStream_t s) {
   const int nb = row_blocks(a.B);
-  const size_t sm = (size_t)8 * 2 * a.C * sizeof(float);
+  const size_t sm = (size_t)8 * 3 * a.C * sizeof(float);
   if (sm > 200 * 1024) { set_error("classes=%d too wide for rows_forward shared memory", a.C); return LF_ERR_UNSUPPORTED; }
   if (mode == LF_MODE_QMF) {
     if (sm > 48 * 1024) cudaFuncSetAttribute(rows_forward_kernel<LF_MODE_QMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -239,23 +309,24 @@ int rows_forward(const RowsArgs& a, int mode, cudaStream_t s) {
   }
   int rc = check_launch("rows_forward_kernel");
   if (rc) return rc;
-  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(a.C), 32), 256, 0, s>>>(a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats)));
+  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(a.C), 32), 1024, 0, s>>>(a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats)));
   return check_launch("finalize_stats_kernel");
 }
 
 void finalize_forward_stats(const float* partials, int nblocks, int C, double* stats, cudaStream_t s) {
-  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(C), 32), 256, 0, s>>>(partials, nblocks, stat_len(C), 0, LF_STATS_HEADER, 1, stats)));
+  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(C), 32), 1024, 0, s>>>(partials, nblocks, stat_len(C), 0, LF_STATS_HEADER, 1, stats)));
 }
 
 int rows_backward(const RowsArgs& a, int mode, cudaStream_t s) {
   const int nb = row_blocks(a.B);
-  if (mode == LF_MODE_QMF) LF_LAUNCH("rows_backward_qmf", s, (rows_backward_kernel<LF_MODE_QMF><<<nb, 256, 0, s>>>(a)));
-  else LF_LAUNCH("rows_calibrated", s, (rows_backward_kernel<LF_MODE_JLOGITS><<<nb, 256, 0, s>>>(a)));
-  int rc = check_launch("rows_backward_kernel");
-  if (rc) return rc;
-  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<1, 256, 0, s>>>(a.partials, nb, stat_len(a.C), LF_STAT_CNT_X1_CAL,
-                                         LF_STAT_CNT_X2_CAL + 1, 0, a.stats)));
-  return check_launch("finalize_stats_kernel(cal)");
+  const size_t sm = (size_t)8 * 2 * a.C * sizeof(float);
+  if (mode == LF_MODE_QMF) {
+    if (sm > 48 * 1024) cudaFuncSetAttribute(rows_backward_kernel<LF_MODE_QMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    LF_LAUNCH("rows_backward_qmf", s, (rows_backward_kernel<LF_MODE_QMF><<<nb, 256, sm, s>>>(a)));
+  } else {
+    LF_LAUNCH("rows_calibrated", s, (rows_backward_kernel<LF_MODE_JLOGITS><<<nb, 256, 0, s>>>(a)));
+  }
+  return check_launch("rows_backward_kernel");
 }
 
 // ---- tiny scalar kernels ---------------------------------------------------------------------

@@ -16,6 +16,8 @@ struct RowsArgs {
   const float* qmf_g;    // (2,B)
   const float* ema_off;  // (2,C)
   float* partials;       // [blocks][stat_len]
+  float* dbpart;         // [blocks][2][C] column sums of dz (written by whichever kernel produces dz)
+  float* calpart;        // [blocks][2] calibrated-accuracy counts
   double* stats;
   int B, B_global, C;
   int ldz;               // row pitch of dz
@@ -25,6 +27,10 @@ __host__ __device__ inline int stat_len_dev(int C) { return LF_STATS_HEADER + 2 
 
 int rows_forward(const RowsArgs& a, int mode, cudaStream_t s);
 int rows_backward(const RowsArgs& a, int mode, cudaStream_t s);
+int row_blocks(int B);
+// dbias[m][c] = sum over blocks of dbpart; stats[CNT_X*_CAL] = sum over blocks of calpart
+int finalize_db_cal(const float* dbpart, int nb_db, int C, const float* calpart, int nb_cal, float* db0, float* db1,
+                    double* stats, cudaStream_t s);
 int loss_finalize(const double* stats, int mode, int Bg, float* out, cudaStream_t s);
 int ema_update(float* x, float* off, const double* stats, int C, int Bg, float beta, cudaStream_t s);
 int ogm_coeff(const double* stats, float alpha, float* coeff, cudaStream_t s);

@@ -37,6 +37,7 @@ struct TcFwdParams {
   float* rowstat;
   float* dz;
   float* partials;
+  float* dbpart;     // [gridDim.x][2][C]  (JLOGITS: column sums of dz)
   int dbg;
 };
 
@@ -68,6 +69,7 @@ tc_heads_forward_kernel(const __grid_constant__ CUtensorMap mapF0, const __grid_
   float* s_colsum = s_bias + 2 * p.block_n;             // [4 warps][2][block_n]
   float* s_stat = s_colsum + 8 * p.block_n;             // [4 warps][16]
   float* s_rows = s_stat + 64;                          // [4 warps][2][32] per-row scalars for the transposed loop
+  float* s_dzsum = s_rows + 256;                        // [4 warps][block_n] column sums of dz (JLOGITS)
   float* s_tile = (float*)smem;                         // [4 warps][2][32][33], aliases the drained stages 0..1
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -133,7 +135,9 @@ tc_heads_forward_kernel(const __grid_constant__ CUtensorMap mapF0, const __grid_
     float* tile = s_tile + q * (2 * 32 * 33);
     float* tile2 = tile + 32 * 33;
     float* colsum = s_colsum + ew * 2 * p.block_n;
+    float* dzsum = s_dzsum + ew * p.block_n;
     for (int c = lane; c < 2 * p.block_n; c += 32) colsum[c] = 0.f;
+    for (int c = lane; c < p.block_n; c += 32) dzsum[c] = 0.f;
     const int row0 = m0 + q * 32;
     const int b = row0 + lane;
     const bool live = b < p.B;
@@ -258,7 +262,7 @@ tc_heads_forward_kernel(const __grid_constant__ CUtensorMap mapF0, const __grid_
       __syncwarp();
       const int col = c0 + lane;
       const bool col_ok = col < C;
-      float cs1 = 0.f, cs2 = 0.f;
+      float cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
       float* o0 = p.z[0] + (size_t)row0 * C + col;
       float* o1 = p.z[1] + (size_t)row0 * C + col;
       float* o2 = p.avg + (size_t)row0 * C + col;
@@ -273,6 +277,7 @@ tc_heads_forward_kernel(const __grid_constant__ CUtensorMap mapF0, const __grid_
         float fourth;
         if (p.mode == LF_MODE_QMF) fourth = a1 * ra + a2 * rb;
         else fourth = (exp2f((av - ra) * kLog2e) - (col == __float_as_int(rb) ? 1.f : 0.f)) * dz_scale;
+        cs3 += fourth;
         if (col_ok) {
           o0[(size_t)r * C] = a1;
           o1[(size_t)r * C] = a2;
@@ -280,7 +285,7 @@ tc_heads_forward_kernel(const __grid_constant__ CUtensorMap mapF0, const __grid_
           o3[(size_t)r * ld3] = fourth;
         }
       }
-      if (col_ok) { colsum[col] += cs1; colsum[p.block_n + col] += cs2; }
+      if (col_ok) { colsum[col] += cs1; colsum[p.block_n + col] += cs2; dzsum[col] += cs3; }
     }
 
     // ---- per-sample scalars and the CTA's partial statistics
@@ -327,6 +332,12 @@ tc_heads_forward_kernel(const __grid_constant__ CUtensorMap mapF0, const __grid_
       out[LF_STATS_HEADER + i] = (s_colsum[o] + s_colsum[2 * p.block_n + o]) +
                                  (s_colsum[4 * p.block_n + o] + s_colsum[6 * p.block_n + o]);
     }
+    if (p.mode == LF_MODE_JLOGITS)
+      for (int c = et; c < C; c += 128) {
+        const float d = (s_dzsum[c] + s_dzsum[p.block_n + c]) + (s_dzsum[2 * p.block_n + c] + s_dzsum[3 * p.block_n + c]);
+        p.dbpart[(size_t)blockIdx.x * 2 * C + c] = d;            // dz1 == dz2 -> db1 == db2
+        p.dbpart[(size_t)blockIdx.x * 2 * C + C + c] = d;
+      }
   }
   __syncthreads();
   if (warp == 1) {
@@ -338,7 +349,7 @@ tc_heads_forward_kernel(const __grid_constant__ CUtensorMap mapF0, const __grid_
 void finalize_forward_stats(const float* partials, int nblocks, int C, double* stats, cudaStream_t s);  // lf_rows.cu
 
 // Fused forward for 32 <= C <= 256, LF_PREC_TF32.  Returns LF_ERR_UNSUPPORTED when the shape does not fit.
-int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* rowstat, cudaStream_t s) {
+int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* dbpart, float* rowstat, cudaStream_t s) {
   const int C = a->classes;
   if (C > 256) return LF_ERR_UNSUPPORTED;
   TcFwdParams p;
@@ -349,7 +360,7 @@ int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* rowstat, cuda
   p.ldz = a->ld_dlogits > 0 ? a->ld_dlogits : C;
   for (int m = 0; m < 2; ++m) { p.bias[m] = a->bias[m]; p.z[m] = a->logits[m]; }
   p.label = a->label; p.avg = a->avg_logits; p.zdf = a->logits_df; p.conf = a->conf;
-  p.rowstat = rowstat; p.dz = a->dlogits[0]; p.partials = partials;
+  p.rowstat = rowstat; p.dz = a->dlogits[0]; p.partials = partials; p.dbpart = dbpart;
   CUtensorMap mF[2], mW[2];
   for (int m = 0; m < 2; ++m) {
     int rc = make_map(&mF[m], a->feat[m], a->dim, a->batch, a->dim, TC_BLOCK_K, TC_BLOCK_M, false);
@@ -358,7 +369,7 @@ int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* rowstat, cuda
     if (rc) return rc;
   }
   const uint32_t stage_bytes = TC_BLOCK_M * TC_BLOCK_K * 4 + p.block_n * TC_BLOCK_K * 4;
-  const size_t tail = 256 + (size_t)(2 + 8) * p.block_n * 4 + 4 * 16 * 4 + 4 * 64 * 4;
+  const size_t tail = 256 + (size_t)(2 + 8 + 4) * p.block_n * 4 + 4 * 16 * 4 + 4 * 64 * 4;
   // two CTAs per SM when TMEM allows it (2 x tmem_cols <= 512): one CTA's epilogue hides behind the
   // other's loads, and 256-CTA grids stop paying a second-wave tail
   const size_t cap = ((p.tmem_cols <= 256 && !getenv("LF_FWD_ONECTA")) ? 112 : 224) * 1024;
