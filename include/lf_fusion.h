@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 1
+#define LF_ABI_VERSION 2
 
 /* error codes */
 #define LF_OK 0
@@ -138,7 +138,16 @@ typedef struct LfQmfArgs {
   int32_t g_count;       /* written at qmf_g[m*g_count + (j-g_begin)]; use 0,Bg for everything */
   void* workspace;       /* >= lf_qmf_workspace_bytes(n_data) */
   size_t workspace_bytes;
+  int32_t flags;         /* LF_QMF_* bits: which parts run (the fused step passes LF_QMF_ALL) */
+  int32_t reserved;
+  const float* loss_uni[2]; /* optional device scalars: batch-mean CE of modality m handed to
+                               History.correctness_update (QMF.py:20-29); NULL = stats[CE_Xm]/Bg */
 } LfQmfArgs;
+
+#define LF_QMF_UPDATE_X1 1 /* history[0].correctness_update   cremad/joint_model_qmf.py:65 */
+#define LF_QMF_UPDATE_X2 2 /* history[1].correctness_update */
+#define LF_QMF_REG 4       /* reg_loss + dL_reg/dconf         existing_algos/QMF.py:119-141 */
+#define LF_QMF_ALL 7
 
 size_t lf_qmf_workspace_bytes(int32_t n_data);
 
@@ -190,6 +199,20 @@ int32_t lf_profile_report(char* buf, int32_t buf_bytes);
 int lf_debug_tc_gemm(const float* A, const float* B, const float* bias, float* out, int32_t M, int32_t N,
                      int32_t K, int32_t lda, int32_t ldb, int32_t ld_out, int32_t a_mn_major,
                      int32_t b_mn_major, int32_t block_n, int32_t splits, int64_t split_stride, void* stream);
+
+/*
+ * Stand-alone pieces of the reference's algorithm API, for callers that use existing_algos/ directly
+ * instead of the fused step.
+ *   lf_qmf_df      QMF.df (existing_algos/QMF.py:109-117): conf_m = log(sum(exp z_m))/10 (non-stabilised,
+ *                  like the reference), z_df = sum_m z_m * conf_m.   z1,z2,zdf: (B,C); conf: (2,B).
+ *   lf_ogm_scores  the two score sums of ogm_ge (existing_algos/OGM_GE.py:21-22) written to
+ *                  stats[LF_STAT_SCORE_X1/X2]; deterministic two-stage reduction.
+ *                  workspace >= lf_ogm_scores_workspace_bytes(), zero-initialised ONCE by the caller.
+ */
+int lf_qmf_df(const float* z1, const float* z2, int32_t batch, int32_t classes, float* zdf, float* conf, void* stream);
+size_t lf_ogm_scores_workspace_bytes(void);
+int lf_ogm_scores(const float* z1, const float* z2, const int64_t* label, int32_t batch, int32_t classes,
+                  double* stats, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Last error message of the calling thread (host string). */
 const char* lf_last_error(void);

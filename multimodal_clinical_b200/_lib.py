@@ -42,7 +42,11 @@ class LfQmfArgs(C.Structure):
         ("last_writer", C.c_void_p), ("step_base", C.c_int64), ("stats", C.c_void_p), ("qmf_g", C.c_void_p),
         ("target_out", C.c_void_p), ("g_begin", C.c_int32), ("g_count", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("flags", C.c_int32), ("reserved", C.c_int32), ("loss_uni", _P2),
     ]
+
+
+LF_QMF_UPDATE_X1, LF_QMF_UPDATE_X2, LF_QMF_REG, LF_QMF_ALL = 1, 2, 4, 7
 
 
 class LfTensorList(C.Structure):
@@ -63,6 +67,10 @@ SIGNATURES = {
     "lf_modulate_workspace_bytes": (C.c_size_t, []),
     "lf_ogm_modulate": (C.c_int, [C.POINTER(LfTensorList), C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64,
                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lf_qmf_df": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lf_ogm_scores_workspace_bytes": (C.c_size_t, []),
+    "lf_ogm_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_size_t, C.c_void_p]),
     "lf_launch_count": (C.c_int64, []),
     "lf_profile_enable": (None, [C.c_int32]),
     "lf_profile_report": (C.c_int32, [C.c_char_p, C.c_int32]),

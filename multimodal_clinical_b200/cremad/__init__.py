@@ -1,0 +1,12 @@
+def get_model(args):
+    """Model factory keyed on args.model_type (cremad/__init__.py of the reference).  The types on the
+    fused path are implemented; the others name reference models outside it."""
+    if args.model_type == "jlogits":
+        from .joint_model import MultimodalCremadModel
+    elif args.model_type == "ogm_ge":
+        from .joint_model_ogm_ge import MultimodalCremadModel
+    elif args.model_type == "qmf":
+        from .joint_model_qmf import MultimodalCremadModel
+    else:
+        raise NotImplementedError("Model type not implemented")
+    return MultimodalCremadModel(args)

@@ -34,20 +34,25 @@ __global__ void qmf_mark_kernel(const int64_t* __restrict__ idx, int Bg, int N, 
 __global__ void qmf_update_kernel(const int64_t* __restrict__ idx, const float* __restrict__ conf, int Bg,
                                   int N, long long base, const long long* __restrict__ last_writer,
                                   const double* __restrict__ stats, double* __restrict__ corr,
-                                  double* __restrict__ confid) {
+                                  double* __restrict__ confid, int flags, const float* __restrict__ loss0,
+                                  const float* __restrict__ loss1) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Bg) return;
   const int64_t i = idx[j];
   if ((unsigned long long)i >= (unsigned long long)N) return;   // out-of-range index: ignored (numpy would raise)
   if (last_writer[i] != base + j) return;
   // batch-mean unimodal CE as the fp32 scalar the reference hands to numpy (cremad/joint_model_qmf.py:64-65)
-  const double l0 = (double)(float)(stats[LF_STAT_CE_X1] / (double)Bg);
-  const double l1 = (double)(float)(stats[LF_STAT_CE_X2] / (double)Bg);
   const double keep = 1.0 - 0.1, alpha = 0.1;           // QMF.py:17,26
-  corr[i] = keep * corr[i] + alpha * l0;
-  corr[(size_t)N + i] = keep * corr[(size_t)N + i] + alpha * l1;
-  confid[i] = (double)conf[j];
-  confid[(size_t)N + i] = (double)conf[Bg + j];
+  if (flags & LF_QMF_UPDATE_X1) {
+    const double l0 = loss0 ? (double)loss0[0] : (double)(float)(stats[LF_STAT_CE_X1] / (double)Bg);
+    corr[i] = keep * corr[i] + alpha * l0;
+    confid[i] = (double)conf[j];
+  }
+  if (flags & LF_QMF_UPDATE_X2) {
+    const double l1 = loss1 ? (double)loss1[0] : (double)(float)(stats[LF_STAT_CE_X2] / (double)Bg);
+    corr[(size_t)N + i] = keep * corr[(size_t)N + i] + alpha * l1;
+    confid[(size_t)N + i] = (double)conf[Bg + j];
+  }
 }
 
 __global__ void qmf_minmax_kernel(const double* __restrict__ corr, int N, double* __restrict__ out) {
@@ -190,7 +195,9 @@ extern "C" size_t lf_qmf_workspace_bytes(int32_t) {
 
 extern "C" int lf_qmf_history_step(const LfQmfArgs* a, void* stream) {
   if (!a || !a->idx || !a->conf || !a->correctness || !a->confidence || !a->last_writer || !a->stats ||
-      !a->qmf_g || !a->workspace) { set_error("lf_qmf_history_step: null argument"); return LF_ERR_BAD_ARG; }
+      !a->workspace) { set_error("lf_qmf_history_step: null argument"); return LF_ERR_BAD_ARG; }
+  if ((a->flags & ~LF_QMF_ALL) || a->flags == 0) { set_error("lf_qmf_history_step: bad flags %d", a->flags); return LF_ERR_BAD_ARG; }
+  if ((a->flags & LF_QMF_REG) && !a->qmf_g) { set_error("lf_qmf_history_step: LF_QMF_REG needs qmf_g"); return LF_ERR_BAD_ARG; }
   if (a->batch_global < 2) {
     // the reference raises for B == 1 (len() of a 0-d array)
     set_error("lf_qmf_history_step: batch_global must be >= 2 (reference raises for a batch of one)");
@@ -205,9 +212,13 @@ extern "C" int lf_qmf_history_step(const LfQmfArgs* a, void* stream) {
   ws.regpart = (float*)((char*)a->workspace + align_up(sizeof(double) * 2 * kMinMaxBlocks * 2, 256));
   const int Bg = a->batch_global, N = a->n_data;
   const int nb = div_up(Bg, 256);
-  LF_LAUNCH("qmf_mark", s, (qmf_mark_kernel<<<nb, 256, 0, s>>>(a->idx, Bg, N, (long long)a->step_base, (long long*)a->last_writer)));
-  LF_LAUNCH("qmf_update", s, (qmf_update_kernel<<<nb, 256, 0, s>>>(a->idx, a->conf, Bg, N, (long long)a->step_base,
-                                      (const long long*)a->last_writer, a->stats, a->correctness, a->confidence)));
+  if (a->flags & (LF_QMF_UPDATE_X1 | LF_QMF_UPDATE_X2)) {
+    LF_LAUNCH("qmf_mark", s, (qmf_mark_kernel<<<nb, 256, 0, s>>>(a->idx, Bg, N, (long long)a->step_base, (long long*)a->last_writer)));
+    LF_LAUNCH("qmf_update", s, (qmf_update_kernel<<<nb, 256, 0, s>>>(a->idx, a->conf, Bg, N, (long long)a->step_base,
+                                        (const long long*)a->last_writer, a->stats, a->correctness, a->confidence,
+                                        a->flags, a->loss_uni[0], a->loss_uni[1])));
+  }
+  if (!(a->flags & LF_QMF_REG)) return check_launch("lf_qmf_history_step");
   LF_LAUNCH("qmf_minmax", s, (qmf_minmax_kernel<<<dim3(kMinMaxBlocks, 2), 256, 0, s>>>(a->correctness, N, ws.minmax)));
   const int rb = nb < kRegBlocks ? nb : kRegBlocks;
   LF_LAUNCH("qmf_reg", s, (qmf_reg_kernel<<<rb, 256, 0, s>>>(*a, ws)));

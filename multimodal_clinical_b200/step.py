@@ -78,7 +78,7 @@ class LateFusionStep:
 
     def __init__(self, num_classes: int, mode: str = "jlogits", n_data: Optional[int] = None,
                  device: Optional[torch.device] = None, precision: str = "fp32", ema_smoothing: float = 0.05,
-                 process_group=None):
+                 process_group=None, qmf_state=None, ema=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.LfError("LateFusionStep needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -101,15 +101,30 @@ class LateFusionStep:
             if n_data is None:
                 raise ValueError("QMF mode needs n_data (args.num_samples)")
             self.n_data = int(n_data)
-            self.correctness = torch.zeros(2, self.n_data, dtype=torch.float64, device=dev)  # QMF.py:13
-            self.confidence = torch.zeros(2, self.n_data, dtype=torch.float64, device=dev)   # QMF.py:14
-            self.last_writer = torch.zeros(self.n_data, dtype=torch.int64, device=dev)
-            self.step_base = 1
-            self.qmf_ws = torch.empty(self.lib.lf_qmf_workspace_bytes(self.n_data), dtype=torch.uint8, device=dev)
+            if qmf_state is None:
+                from .existing_algos.QMF import _QmfState
+                qmf_state = _QmfState(2, self.n_data)
+            if qmf_state.n_data != self.n_data:
+                raise ValueError("QMF state length differs from n_data")
+            self.qmf_state = qmf_state.to(dev)       # History arrays (2,N) fp64 in HBM, shared with the QMF object
+        if ema is not None:                           # share the calibration state with a utils.EMA.EMA object
+            ema.to(dev)
+            self.ema_x, self.ema_offset, self.smoothing = ema.x, ema._offset, float(ema.smoothing)
+        self.ema = ema
+        self.fresh_outputs = False
         self._ws = None
         self._ws_key = None
         self._bufs = {}
         self.mod_ws = torch.empty(self.lib.lf_modulate_workspace_bytes(), dtype=torch.uint8, device=dev)
+
+    @property
+    def correctness(self) -> torch.Tensor:
+        """(2,N) fp64 History.correctness (existing_algos/QMF.py:13), device-resident."""
+        return self.qmf_state.correctness
+
+    @property
+    def confidence(self) -> torch.Tensor:
+        return self.qmf_state.confidence
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, B: int, D: int, need_dfeat: bool):
@@ -133,12 +148,28 @@ class LateFusionStep:
             b["qmf_g"] = torch.empty(2, B, device=dev) if qmf else None
             self._bufs = b
             self._ws_key = key
+        if self.fresh_outputs:
+            # tensors that escape to the caller (autograd, metric lists) get fresh storage every step from
+            # torch's caching allocator; scratch (dz, qmf_g, workspace) stays static
+            dev, Cn, b = self.device, self.C, dict(self._bufs)
+            b["logits"] = torch.empty(2, B, Cn, device=dev)
+            b["avg"] = torch.empty(B, Cn, device=dev)
+            if b["zdf"] is not None:
+                b["zdf"] = torch.empty(B, Cn, device=dev)
+                b["conf"] = torch.empty(2, B, device=dev)
+            if need_dfeat:
+                b["dfeat"] = torch.empty(2, B, D, device=dev)
+            b["grad_flat"] = torch.empty(2 * (Cn * D + Cn) + 2, device=dev)
+            return b
         return self._bufs
 
     # ------------------------------------------------------------------ the step
     def step(self, feats: Sequence[torch.Tensor], weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
              label: torch.Tensor, idx: Optional[torch.Tensor] = None, need_dfeat: bool = True,
-             update_ema: bool = True, ogm_alpha: Optional[float] = None) -> StepOutput:
+             update_ema: bool = True, ogm_alpha: Optional[float] = None, backward: bool = True) -> StepOutput:
+        """One fused step.  ``backward=False`` is the validation/test forward of the reference (loss, logits
+        and -- QMF -- the History update with the batch's indices, utils/BaseModel.py:1023-1026), without
+        gradients; ``update_ema=False`` leaves the calibration state alone like the reference's eval steps."""
         lib = self.lib
         f = [_f32c(feats[0], "features"), _f32c(feats[1], "features")]
         W = [_f32c(weights[0], "weight"), _f32c(weights[1], "weight")]
@@ -150,6 +181,9 @@ class LateFusionStep:
         label = label.to(device=self.device, dtype=torch.int64).contiguous()
         Bg = B * self.world
         bufs = self._buffers(B, D, need_dfeat)
+        if self.fresh_outputs:
+            self.stats = torch.zeros_like(self.stats)
+            self.loss = torch.empty_like(self.loss)
         n = Cn * D
         gf = bufs["grad_flat"]
         dW = [gf[0:n].view(Cn, D), gf[n + Cn:2 * n + Cn].view(Cn, D)]
@@ -180,6 +214,8 @@ class LateFusionStep:
             check(lib.lf_ema_update(_ptr(self.ema_x), _ptr(self.ema_offset), _ptr(self.stats), Cn, Bg,
                                     self.smoothing, st), "lf_ema_update")
             self.ema_counter += 1
+            if self.ema is not None:
+                self.ema.counter += 1
         if ogm_alpha is not None:
             check(lib.lf_ogm_coeff(_ptr(self.stats), float(ogm_alpha), _ptr(self.coeff), st), "lf_ogm_coeff")
         if qmf:
@@ -190,21 +226,25 @@ class LateFusionStep:
             q = LfQmfArgs()
             q.batch_global, q.n_data = Bg, self.n_data
             q.idx, q.conf = _ptr(idx_g), _ptr(conf_g)
-            q.correctness, q.confidence = _ptr(self.correctness), _ptr(self.confidence)
-            q.last_writer, q.step_base = _ptr(self.last_writer), self.step_base
+            qs = self.qmf_state
+            q.correctness, q.confidence = _ptr(qs.correctness), _ptr(qs.confidence)
+            q.last_writer, q.step_base = _ptr(qs.last_writer), qs.step_base
             q.stats, q.qmf_g, q.target_out = _ptr(self.stats), _ptr(bufs["qmf_g"]), None
             q.g_begin, q.g_count = parallel.shard_range(self.rank, B)
-            q.workspace, q.workspace_bytes = _ptr(self.qmf_ws), self.qmf_ws.numel()
+            q.workspace, q.workspace_bytes = _ptr(qs.ws), qs.ws.numel()
+            q.flags = _lib.LF_QMF_ALL
             check(lib.lf_qmf_history_step(C.byref(q), st), "lf_qmf_history_step")
-            self.step_base += Bg
-        check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
-        # head gradients + calibrated counts: one all-reduce
-        parallel.pack_grad_exchange(gf, 2 * (n + Cn), self.stats, STAT["CNT_X1_CAL"], STAT["CNT_X2_CAL"] + 1, self.pg)
+            qs.step_base += Bg
+        if backward:
+            check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
+            # head gradients + calibrated counts: one all-reduce
+            parallel.pack_grad_exchange(gf, 2 * (n + Cn), self.stats, STAT["CNT_X1_CAL"], STAT["CNT_X2_CAL"] + 1, self.pg)
         check(lib.lf_loss_finalize(_ptr(self.stats), self.mode, Bg, _ptr(self.loss), st), "lf_loss_finalize")
 
         return StepOutput(
             logits=[bufs["logits"][0], bufs["logits"][1]], avg_logits=bufs["avg"], logits_df=bufs["zdf"],
-            conf=bufs["conf"], loss=self.loss[0], dfeat=[bufs["dfeat"][0], bufs["dfeat"][1]] if need_dfeat else [None, None],
+            conf=bufs["conf"], loss=self.loss[0],
+            dfeat=[bufs["dfeat"][0], bufs["dfeat"][1]] if (need_dfeat and backward) else [None, None],
             dweight=dW, dbias=db, stats=self.stats, batch_global=Bg)
 
     # ------------------------------------------------------------------ OGM-GE modulation

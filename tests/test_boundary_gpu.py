@@ -1,0 +1,211 @@
+"""The drop-in Python boundary on the GPU: the FusionNet / LightningModule mirrors driven
+exactly like the reference's own modules were when tests/golden/*.npz was generated from them
+(tests/golden/make_golden.py), and the stand-alone algorithm API against the CPU oracle."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import late_fusion as O
+from tests.util import TOL_FP32, assert_close, cu, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(**kw):
+    d = dict(num_classes=6, num_samples=50, learning_rate=1e-3, use_scheduler=False, grad_mod_type="OGM", alpha=0.8,
+             encoder="precomputed")
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def _set_heads(lin1, lin2, g):
+    with torch.no_grad():
+        lin1.weight.copy_(cu(g["W1"])); lin1.bias.copy_(cu(g["b1"]))
+        lin2.weight.copy_(cu(g["W2"])); lin2.bias.copy_(cu(g["b2"]))
+
+
+def test_cremad_qmf_lightning_module_matches_reference_golden():
+    from multimodal_clinical_b200.cremad.joint_model_qmf import MultimodalCremadModel
+    g = load_golden("qmf_cremad_b64")
+    B, D, C, N, steps = [int(v) for v in g["meta"]]
+    m = MultimodalCremadModel(_args(num_classes=C, num_samples=N))
+    m.model.x1_model = nn.Identity(); m.model.x2_model = nn.Identity()
+    m = m.cuda().train()
+    _set_heads(m.model.x1_classifier, m.model.x2_classifier, g)
+    for s in range(steps):
+        p = f"s{s}_"
+        a = cu(g[p + "f1"]).view(B, D, 1, 1).requires_grad_(True)
+        v = cu(g[p + "f2"]).view(B, D, 1, 1).requires_grad_(True)
+        m.zero_grad()
+        loss = m.training_step((a, v, cu(g[p + "y"]), cu(g[p + "idx"])), s)
+        loss.backward()
+        assert_close(loss, g[p + "loss"], TOL_FP32, f"loss step {s}")
+        assert_close(m.model.x1_classifier.weight.grad, g[p + "dW1"], TOL_FP32, "dW1")
+        assert_close(m.model.x2_classifier.bias.grad, g[p + "db2"], TOL_FP32, "db2")
+        assert_close(a.grad.view(B, D), g[p + "df1"], TOL_FP32, "df1")
+        assert_close(v.grad.view(B, D), g[p + "df2"], TOL_FP32, "df2")
+        assert_close(m.ema_offset.x, g[p + "ema_x"], TOL_FP32, "EMA.x")
+        assert_close(m.ema_offset.offset, g[p + "ema_off"], 1e-4, "EMA.offset")
+        assert m.ema_offset.counter == s + 1
+        assert_close(m.model.qmf.history[0].correctness, g[p + "corr"][0], 1e-6, "history[0].correctness")
+        assert_close(m.model.qmf.history[1].confidence, g[p + "confid"][1], 1e-6, "history[1].confidence")
+        tm = m.train_metrics
+        for key, gk in (("train_x1_acc_uncal", "acc_x1_uncal"), ("train_x2_acc", "acc_x2_cal"), ("train_acc", "acc_joint"),
+                        ("train_df_acc", "acc_df")):
+            assert abs(float(tm[key][-1]) - float(g[p + gk])) < 1e-6, key
+        assert abs(float(m.logged["train_step/train_df_acc"]) - float(g[p + "acc_df"])) < 1e-6
+    m.on_train_epoch_end()
+    assert "train_epoch/train_avg_df_acc" in m.logged and m.train_metrics["train_loss"] == []
+
+
+def test_validation_step_updates_history_but_not_ema():
+    from multimodal_clinical_b200.cremad.joint_model_qmf import MultimodalCremadModel
+    g = load_golden("qmf_cremad_b64")
+    B, D, C, N, steps = [int(v) for v in g["meta"]]
+    m = MultimodalCremadModel(_args(num_classes=C, num_samples=N))
+    m.model.x1_model = nn.Identity(); m.model.x2_model = nn.Identity()
+    m = m.cuda().eval()
+    _set_heads(m.model.x1_classifier, m.model.x2_classifier, g)
+    p = "s0_"
+    with torch.no_grad():
+        loss = m.validation_step((cu(g[p + "f1"]).view(B, D, 1, 1), cu(g[p + "f2"]).view(B, D, 1, 1), cu(g[p + "y"]),
+                                  cu(g[p + "idx"])), 0)
+    assert_close(loss, g[p + "loss"], TOL_FP32, "val loss")                 # same forward as training
+    assert m.ema_offset.counter == 0 and float(m.ema_offset.x.abs().sum()) == 0.0
+    assert_close(m.model.qmf.history[0].correctness, g[p + "corr"][0], 1e-6, "history mutated by validation")
+    assert len(m.val_metrics["val_logits"]) == 1 and tuple(m.val_metrics["val_logits"][0].shape) == (B, 2, C)
+    m.on_validation_epoch_end()
+    assert "val_epoch/val_avg_acc" in m.logged and "val_epoch/val_avg_df_acc" in m.logged
+
+
+def test_cremad_ogm_ge_manual_optimisation_matches_reference_golden():
+    """OGMGEBaseModel.training_step: zero_grad -> backward -> ogm_ge -> step.  With modulation 'OGM' the
+    encoder (a Dirac 1x1 conv, as in make_golden.py) gradient must come out scaled by the golden coefficient."""
+    from multimodal_clinical_b200.cremad.joint_model_ogm_ge import MultimodalCremadModel
+    from multimodal_clinical_b200.utils import lightning_compat as lc
+    g = load_golden("ogm_cremad_b48")
+    B, D, C, _, steps = [int(v) for v in g["meta"]]
+    torch.backends.cudnn.allow_tf32 = False          # the stub encoder's conv backward is PyTorch's, keep it fp32
+    m = MultimodalCremadModel(_args(num_classes=C, alpha=float(g["alpha"]), learning_rate=0.0))
+
+    def stub():
+        conv = nn.Conv2d(D, D, 1, bias=False)
+        with torch.no_grad():
+            nn.init.dirac_(conv.weight)
+        return nn.Sequential(conv)
+    m.model.x1_model = stub(); m.model.x2_model = stub()
+    m = m.cuda().train()
+    _set_heads(m.model.x1_classifier, m.model.x2_classifier, g)
+    if not lc.HAVE_LIGHTNING:
+        tr = lc.Trainer(); m.trainer = tr; tr._configure(m)
+    for s in range(steps):
+        p = f"s{s}_"
+        a = cu(g[p + "f1"]).view(B, D, 1, 1); v = cu(g[p + "f2"]).view(B, D, 1, 1)
+        y = cu(g[p + "y"])
+        # unmodulated encoder gradient of the same step, from the oracle's feature gradients
+        ref = O.jlogits_step([torch.from_numpy(g[p + "f1"]), torch.from_numpy(g[p + "f2"])],
+                             [torch.from_numpy(g["W1"]), torch.from_numpy(g["W2"])],
+                             [torch.from_numpy(g["b1"]), torch.from_numpy(g["b2"])], torch.from_numpy(g[p + "y"]))
+        loss = m.training_step((a, v, y), s)
+        assert_close(loss, g[p + "loss"], TOL_FP32, "loss")
+        for k, (enc, f, df) in enumerate(((m.model.x1_model, g[p + "f1"], ref["dfeat"][0]),
+                                          (m.model.x2_model, g[p + "f2"], ref["dfeat"][1]))):
+            g_raw = df.double().t() @ torch.from_numpy(f).double()           # dL/dW of the 1x1 conv
+            want = g_raw * float(g[p + "coeff"][k])
+            assert_close(enc[0].weight.grad.view(D, D), want, 5e-5, f"modulated encoder grad {k} step {s}")
+        assert_close(m.model.x1_classifier.weight.grad, g[p + "dW1"], TOL_FP32, "dW1")
+        assert abs(float(m.train_metrics["train_x1_acc"][-1]) - float(g[p + "acc_x1_cal"])) < 1e-6
+
+
+def test_enrico_joint_logits_matches_reference_golden():
+    from multimodal_clinical_b200.enrico.joint_model import MultimodalEnricoModel
+    g = load_golden("jlogits_enrico_b32")
+    B, D, C, _, steps = [int(v) for v in g["meta"]]
+    m = MultimodalEnricoModel(_args(num_classes=C))
+    m.model.x1_model.model = nn.Identity(); m.model.x2_model.model = nn.Identity()
+    m = m.cuda().train()
+    _set_heads(m.model.x1_model.classifier, m.model.x2_model.classifier, g)
+    for s in range(steps):
+        p = f"s{s}_"
+        m.zero_grad()
+        loss = m.training_step((cu(g[p + "f1"]).view(B, D, 1, 1), cu(g[p + "f2"]).view(B, D, 1, 1), cu(g[p + "y"])), s)
+        loss.backward()
+        assert_close(loss, g[p + "loss"], TOL_FP32, "loss")
+        assert_close(m.model.x1_model.classifier.weight.grad, g[p + "dW1"], TOL_FP32, "dW1")
+        assert_close(m.model.x2_model.classifier.bias.grad, g[p + "db2"], TOL_FP32, "db2")
+        assert_close(m.ema_offset.x, g[p + "ema_x"], TOL_FP32, "EMA.x")
+        assert m.model.fused.last_step.dfeat[0] is None       # frozen encoders: no feature gradient produced
+
+
+def test_standalone_algorithm_api_matches_oracle():
+    from multimodal_clinical_b200.existing_algos.OGM_GE import ogm_ge
+    from multimodal_clinical_b200.existing_algos.QMF import QMF
+    from multimodal_clinical_b200.utils.EMA import EMA
+    B, C, N = 50, 11, 80
+    inp = O.make_inputs(B, 16, C, seed=3, n_data=N)
+    z = torch.stack([torch.randn(B, C, generator=torch.Generator().manual_seed(1)),
+                     torch.randn(B, C, generator=torch.Generator().manual_seed(2))])
+    q = QMF(2, N)
+    zdf, conf = q.df(z.cuda())
+    zdf_ref, conf_ref = O.qmf_df(z)
+    assert_close(zdf, zdf_ref, TOL_FP32, "QMF.df logits_df"); assert_close(conf, conf_ref, TOL_FP32, "QMF.df conf")
+    hist = O.HistoryState(N)
+    idx = inp["idx"]
+    for step in range(3):
+        idx = (idx * 7 + step) % N
+        for n in range(2):
+            loss_n = torch.tensor(0.5 + 0.3 * n + 0.1 * step)
+            O.history_update(hist, n, idx.numpy(), float(loss_n), conf_ref[n].numpy())
+            q.history[n].correctness_update(idx.cuda(), loss_n.cuda(), conf[n])
+        ref = O.qmf_reg_loss_literal(conf_ref, idx.numpy(), hist)
+        got = q.reg_loss(conf, idx.cuda())
+        assert_close(got, ref, 2e-5, f"reg_loss step {step}")
+    assert_close(q.history[1].correctness, hist.correctness[1], 1e-6, "history.correctness")
+    with pytest.raises(TypeError):
+        q.reg_loss(conf[:, :1], idx[:1].cuda())
+
+    e = EMA(torch.zeros(2, C)); x = torch.zeros(2, C)
+    for _ in range(3):
+        e.update(z.mean(dim=1).cuda()); x = O.ema_update(x, z[0], z[1])
+    assert_close(e.x, x, TOL_FP32, "EMA.x"); assert_close(e.offset, O.ema_offset(x), 1e-4, "EMA.offset")
+    assert e.counter == 3
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.x1_model = nn.Sequential(nn.Conv2d(4, 4, 3), nn.BatchNorm2d(4))
+            self.x2_model = nn.Sequential(nn.Conv2d(4, 4, 3), nn.BatchNorm2d(4))
+    net = Net().cuda()
+    for p in net.parameters():
+        p.grad = torch.randn_like(p)
+    before = {n: p.grad.clone() for n, p in net.named_parameters()}
+    y = inp["y"] % C
+    ogm_ge(net, z[0].cuda(), z[1].cuda(), y.cuda(), alpha=0.8, modulation="OGM")
+    k = O.ogm_coeffs(*[float(s) for s in O.ogm_scores(z[0], z[1], y)], 0.8)
+    for n, p in net.named_parameters():
+        want = before[n] * (k[0] if n.startswith("x1") else k[1]) if p.grad.dim() == 4 else before[n]
+        assert_close(p.grad, want, 1e-5, n)
+
+
+def test_main_entry_point_trains_food101_qmf_on_synthetic_embeddings(tmp_path, monkeypatch):
+    """`main.py --dir food101`: YAML -> get_model -> run_trainer -> fit/validate/checkpoint/test, end to end."""
+    import yaml
+    from multimodal_clinical_b200 import main
+    (tmp_path / "utils").mkdir(); (tmp_path / "food101").mkdir()
+    base = dict(num_classes=2, batch_size=64, learning_rate=1e-3, num_epochs=2, dropout_p=0.1, gpus=[0], num_cpus=0,
+                data_path=str(tmp_path / "data"), use_wandb=False, model_type="jlogits", group_name="t", seed=5,
+                use_scheduler=True, grad_mod_type="OGM_GE", alpha=0.1)
+    over = dict(num_classes=101, batch_size=128, learning_rate=0.02, model_type="qmf", encoder="precomputed",
+                synthetic_samples=512, precision="32-true")
+    (tmp_path / "utils" / "base_cfg.yaml").write_text(yaml.safe_dump(base))
+    (tmp_path / "food101" / "food101.yaml").write_text(yaml.safe_dump(over))
+    monkeypatch.chdir(tmp_path)
+    tr = main.main(["--dir", "food101"])
+    got = {k: float(v) for k, v in tr.callback_metrics.items()}
+    for k in ("train_epoch/train_avg_loss", "val_epoch/val_avg_acc", "val_epoch/val_avg_df_acc", "test_epoch/test_avg_acc",
+              "test_epoch/test_avg_x1_acc"):
+        assert k in got and np.isfinite(got[k]), k
+    assert 0.0 <= got["test_epoch/test_avg_acc"] <= 1.0

@@ -33,3 +33,7 @@ def assert_close(a, b, tol, what=""):
 
 def t(x):
     return torch.from_numpy(np.asarray(x))
+
+
+def cu(x):
+    return t(x).cuda()
