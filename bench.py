@@ -245,9 +245,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=None, help="override the workload's per-GPU batch (experiments)")
+    ap.add_argument("--dim", type=int, default=None, help="override the feature width (experiments)")
+    ap.add_argument("--classes", type=int, default=None, help="override the class count (experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.batch or args.dim or args.classes:
+        w.update(B=args.batch or w["B"], D=args.dim or w["D"], C=args.classes or w["C"])
+        w["desc"] += f" [overridden: B={w['B']} D={w['D']} C={w['C']}]"
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -2,6 +2,7 @@
 // workspace carving and kernel sequencing.  No torch types, no global state beyond a thread-local
 // error string.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <map>
@@ -15,6 +16,7 @@
 
 namespace lf {
 int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* dbpart, float* rowstat, cudaStream_t s);  // lf_tc_fwd.cu
+int tc_forward_parts(int B);
 }
 
 namespace lf {
@@ -76,7 +78,7 @@ HeadsWorkspace carve_heads_workspace(void* base, int B, int D, int C) {
   char* p = (char*)base;
   size_t off = 0;
   auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes, 256); return r; };
-  const int part_rows = div_up(B, 128) > kMaxRowBlocks ? div_up(B, 128) : kMaxRowBlocks;   // fused forward: one row per 128 samples
+  const int part_rows = div_up(B, 128) + 148 > kMaxRowBlocks ? div_up(B, 128) + 148 : kMaxRowBlocks;   // fused forward: one row per tile
   w.row_partials = (float*)take((size_t)part_rows * stat_len(C) * sizeof(float));
   w.dw_partials = (float*)take((size_t)2 * kMaxSplits * C * D * sizeof(float));
   w.db_partials = (float*)take((size_t)part_rows * 2 * C * sizeof(float));
@@ -140,6 +142,7 @@ static RowsArgs rows_args(const LfHeadsArgs* a, const HeadsWorkspace& w) {
   r.dbpart = w.db_partials; r.calpart = w.cal_partials;
   r.B = a->batch; r.B_global = a->batch_global; r.C = a->classes;
   r.ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
+  r.nb_total = row_blocks(a->batch);
   return r;
 }
 
@@ -197,7 +200,7 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
   for (int m = 0; m < 2; ++m) { g.A[m] = a->feat[m]; g.B[m] = a->weight[m]; g.bias[m] = a->bias[m]; g.C[m] = a->logits[m]; }
   g.M = a->batch; g.N = a->classes; g.K = a->dim;
   g.lda = a->dim; g.ldb = a->dim; g.ldc = a->classes;
-  if (use_tensor_pipe(a) && a->classes <= 256) {
+  if (use_tensor_pipe(a) && a->classes <= 256 && getenv("LF_FUSED_FWD")) {
     // logits GEMMs + all per-sample forward math in one kernel (lf_tc_fwd.cu)
     return tc_heads_forward(a, w.row_partials, w.db_partials, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), s);
   }
@@ -278,8 +281,8 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   rc = reduce_splits2(w.dw_partials, a->dweight[0], a->dweight[1], splits, kMaxSplits, cd, s);
   if (rc) return rc;
   // db_m (column sums of dZ_m, accumulated by the kernel that produced dZ) and the calibrated counts
-  const bool fused_fwd = tc && a->classes <= 256;
-  const int nb_db = (a->mode == LF_MODE_JLOGITS && fused_fwd) ? div_up(a->batch, 128) : row_blocks(a->batch);
+  const bool fused_fwd = tc && a->classes <= 256 && getenv("LF_FUSED_FWD");
+  const int nb_db = (a->mode == LF_MODE_JLOGITS && fused_fwd) ? tc_forward_parts(a->batch) : row_blocks(a->batch);
   return finalize_db_cal(w.db_partials, nb_db, a->classes, w.cal_partials, row_blocks(a->batch), a->dbias[0], a->dbias[1],
                          a->stats, s);
 }

@@ -296,8 +296,18 @@ int row_blocks(int B) {
   return nb < kMaxRowBlocks ? (nb < 1 ? 1 : nb) : kMaxRowBlocks;
 }
 
+bool rows_reg_supported(int C);                                                   // lf_rows_reg.cu
+int rows_forward_reg(const RowsArgs& a, int mode, int nb, cudaStream_t s);
+int rows_backward_reg(const RowsArgs& a, int mode, int nb, cudaStream_t s);
+
 int rows_forward(const RowsArgs& a, int mode, cudaStream_t s) {
   const int nb = row_blocks(a.B);
+  if (rows_reg_supported(a.C)) {
+    int rc = rows_forward_reg(a, mode, nb, s);
+    if (rc) return rc;
+    LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(a.C), 32), 1024, 0, s>>>(a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats)));
+    return check_launch("finalize_stats_kernel");
+  }
   const size_t sm = (size_t)8 * 3 * a.C * sizeof(float);
   if (sm > 200 * 1024) { set_error("classes=%d too wide for rows_forward shared memory", a.C); return LF_ERR_UNSUPPORTED; }
   if (mode == LF_MODE_QMF) {
@@ -319,6 +329,7 @@ void finalize_forward_stats(const float* partials, int nblocks, int C, double* s
 
 int rows_backward(const RowsArgs& a, int mode, cudaStream_t s) {
   const int nb = row_blocks(a.B);
+  if (rows_reg_supported(a.C)) return rows_backward_reg(a, mode, nb, s);
   const size_t sm = (size_t)8 * 2 * a.C * sizeof(float);
   if (mode == LF_MODE_QMF) {
     if (sm > 48 * 1024) cudaFuncSetAttribute(rows_backward_kernel<LF_MODE_QMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

@@ -21,6 +21,7 @@ struct RowsArgs {
   double* stats;
   int B, B_global, C;
   int ldz;               // row pitch of dz
+  int nb_total;          // partial rows the finalize kernels will sum; CTAs zero the rows beyond the grid
 };
 
 __host__ __device__ inline int stat_len_dev(int C) { return LF_STATS_HEADER + 2 * C; }

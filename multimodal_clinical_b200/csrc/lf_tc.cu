@@ -165,7 +165,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++li) {
       const Item w = decode_item(p, item);
       const uint32_t buf = li & 1;
-      mbar_wait(&tmem_full_bar[buf], (li >> 1) & 1);
+      mbar_wait_warp(&tmem_full_bar[buf], (li >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + buf * (uint32_t)p.acc_cols + ((uint32_t)(q * 32) << 16);
       const CUtensorMap* mapO = w.batch == 0 ? &mapO0 : &mapO1;
