@@ -74,21 +74,39 @@ def step_alg_bytes_per_sample(w):
 
 
 def kernel_alg_bytes(name, w, B):
-    """Algorithmic HBM bytes of ONE launch of kernel `name` (inputs read once + outputs written once)."""
+    """Algorithmic HBM bytes of ONE launch of kernel `name`: every input read once + every output written once
+    (DESIGN.md §4).  k = number of dL/dlogits matrices (1 for mean fusion: dz1 == dz2; 2 for QMF)."""
     D, C = w["D"], w["C"]
     f = 4
+    ldz = (C + 3) // 4 * 4
+    k = 2 if w["mode"] == "qmf" else 1
+    n_out = 4 if w["mode"] == "qmf" else 3
+    logits = 2 * (B * D + C * D + C + B * C) * f
+    dfeat = (k * B * ldz + 2 * C * D + 2 * B * D) * f
+    dweight = (k * B * ldz + 2 * B * D + 2 * C * D) * f
     table = {
-        "sgemm_logits": 2 * (B * D + C * D + C + B * C) * f,
+        "sgemm_logits": logits, "tc_logits": logits,
+        "tc_heads_forward": (2 * B * D + 2 * C * D + n_out * B * C) * f + 8 * B,
         "rows_forward_qmf": (2 * B * C + 2 * B * C + 2 * B + 4 * B) * f + 8 * B,
-        "rows_forward_jlogits": (2 * B * C + 2 * B * C) * f + 8 * B,
-        "rows_backward_qmf": (2 * B * C + 2 * B * C + 8 * B) * f + 8 * B,
+        "rows_forward_jlogits": (2 * B * C + B * C + B * ldz) * f + 8 * B,
+        "rows_backward_qmf": (2 * B * C + 2 * B * ldz + 8 * B) * f + 8 * B,
         "rows_calibrated": 2 * B * C * f + 8 * B,
-        "sgemm_dfeat": ((2 if w["mode"] == "qmf" else 1) * B * C + 2 * C * D + 2 * B * D) * f,
-        "sgemm_dweight": ((2 if w["mode"] == "qmf" else 1) * B * C + 2 * B * D) * f,
+        "sgemm_dfeat": dfeat, "tc_dfeat": dfeat,
+        "sgemm_dweight": dweight, "tc_dweight": dweight,
         "modulate_stats": 11_160_000 * f,
         "modulate_apply": 2 * 11_160_000 * f,
     }
     return table.get(name)
+
+
+def measured_traffic(workload, precision, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the
+    same command (profiles/traffic.json, written by tools/ncu_summary.py); None when no capture covers it."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(f"{workload}/{precision}", {}).get(kernel)
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -370,7 +388,8 @@ def main():
             ab = kernel_alg_bytes(dom, w, w["B"])
             ach = ab / (kern[dom]["avg_us"] * 1e-6) / 1e9 if ab else None
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": (ach / hbm_peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (ach / hbm_peak) if ach else None,
+                    "traffic": measured_traffic(args.workload, args.precision, dom), "peak_source": peak_src,
                     "alg_bytes_per_launch": ab, "avg_launch_us": kern[dom]["avg_us"], "share_of_step": kern[dom]["share"]}
         step_bytes = step_alg_bytes_per_sample(w) * w["B"]
         step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9

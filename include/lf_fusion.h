@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 2
+#define LF_ABI_VERSION 3
 
 /* error codes */
 #define LF_OK 0
@@ -86,6 +86,9 @@ typedef struct LfHeadsArgs {
   double* stats;          /* in/out packed statistics, see LF_STAT_* */
   void* workspace;        /* >= lf_workspace_bytes(batch, dim, classes) */
   size_t workspace_bytes;
+  int32_t fwd_only;       /* 1: validation / test forward, lf_heads_backward will not be called for this step.
+                             Lets the narrow-head path (C <= 32) fuse forward and backward into one pass otherwise. */
+  int32_t reserved;
 } LfHeadsArgs;
 
 /* Bytes of caller-provided scratch the heads calls need. */
@@ -158,6 +161,49 @@ size_t lf_qmf_workspace_bytes(int32_t n_data);
  *   QMF.reg_loss                existing_algos/QMF.py:119-141 (closed form, incl. the flattened roll)
  */
 int lf_qmf_history_step(const LfQmfArgs* args, void* stream);
+
+/*
+ * The middle of the step in ONE launch (lf_mid.cu): sums the per-rank partial statistics in rank order,
+ * updates the EMA (utils/EMA.py:29-38), computes the OGM-GE coefficients (existing_algos/OGM_GE.py:24-40),
+ * and -- QMF -- runs History.correctness_update, the global min/max, the ranking targets, the ranking
+ * loss and dL_reg/dconf (existing_algos/QMF.py:20-68, 119-141), then the total loss
+ * (cremad/joint_model_qmf.py:70).  Inputs are rank-major: the buffer a single all-gather of
+ * [stats | idx | conf] produces; with one GPU n_ranks = 1 and the pointers are the local buffers.
+ * Supersedes the sequence lf_ema_update, lf_ogm_coeff, lf_qmf_history_step, lf_loss_finalize.
+ */
+typedef struct LfMidArgs {
+  int32_t mode;            /* LF_MODE_* */
+  int32_t classes;
+  int32_t batch_global;    /* n_ranks * batch_local */
+  int32_t n_ranks;
+  int32_t batch_local;
+  int32_t rank;            /* qmf_g is produced for samples [rank*batch_local, (rank+1)*batch_local) */
+  int32_t n_data;          /* QMF: length N of the History arrays */
+  int32_t update_ema;      /* 0 on validation / test steps (utils/BaseModel.py:133-160) */
+  const double* stats_parts; /* rank r's LF_STATS_HEADER + 2C partial statistics at stats_parts + r*stats_stride */
+  int64_t stats_stride;      /* in doubles */
+  const int64_t* idx_parts;  /* QMF: rank r's idx (batch_local) at idx_parts + r*idx_stride (elements) */
+  int64_t idx_stride;
+  const float* conf_parts;   /* QMF: rank r's conf (2, batch_local) at conf_parts + r*conf_stride (elements) */
+  int64_t conf_stride;
+  double* stats;           /* out: global statistics (CNT_*_CAL entries are left alone; REG_SUM is written) */
+  float* ema_x;            /* in/out (2,C) */
+  float* ema_offset;       /* out (2,C) */
+  float smoothing;
+  float alpha;             /* OGM-GE alpha; used when coeff_out != NULL */
+  float* coeff_out;        /* out (2) or NULL */
+  double* correctness;     /* QMF in/out (2,N) */
+  double* confidence;      /* QMF in/out (2,N) */
+  int64_t* last_writer;    /* QMF in/out (N) tickets, zero-initialised once */
+  int64_t step_base;       /* QMF: strictly increasing by >= batch_global per call, starting at 1 */
+  float* qmf_g;            /* QMF out (2, batch_local) dL_reg/dconf of this rank's samples, or NULL (forward only) */
+  float* loss_out;         /* out (1) total loss, or NULL */
+  void* workspace;         /* QMF: >= lf_mid_workspace_bytes(batch_global) */
+  size_t workspace_bytes;
+} LfMidArgs;
+
+size_t lf_mid_workspace_bytes(int32_t batch_global);
+int lf_step_mid(const LfMidArgs* args, void* stream);
 
 typedef struct LfTensorList {
   int32_t count;          /* number of gradient tensors (<= LF_MAX_TENSORS) */

@@ -31,7 +31,7 @@ class LfHeadsArgs(C.Structure):
         ("logits", _P2), ("avg_logits", C.c_void_p), ("logits_df", C.c_void_p), ("conf", C.c_void_p),
         ("dlogits", _P2), ("dfeat", _P2), ("dweight", _P2), ("dbias", _P2),
         ("qmf_g", C.c_void_p), ("ema_offset", C.c_void_p), ("stats", C.c_void_p),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("fwd_only", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -43,6 +43,18 @@ class LfQmfArgs(C.Structure):
         ("target_out", C.c_void_p), ("g_begin", C.c_int32), ("g_count", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("flags", C.c_int32), ("reserved", C.c_int32), ("loss_uni", _P2),
+    ]
+
+
+class LfMidArgs(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("classes", C.c_int32), ("batch_global", C.c_int32), ("n_ranks", C.c_int32),
+        ("batch_local", C.c_int32), ("rank", C.c_int32), ("n_data", C.c_int32), ("update_ema", C.c_int32),
+        ("stats_parts", C.c_void_p), ("stats_stride", C.c_int64), ("idx_parts", C.c_void_p), ("idx_stride", C.c_int64),
+        ("conf_parts", C.c_void_p), ("conf_stride", C.c_int64), ("stats", C.c_void_p), ("ema_x", C.c_void_p),
+        ("ema_offset", C.c_void_p), ("smoothing", C.c_float), ("alpha", C.c_float), ("coeff_out", C.c_void_p),
+        ("correctness", C.c_void_p), ("confidence", C.c_void_p), ("last_writer", C.c_void_p), ("step_base", C.c_int64),
+        ("qmf_g", C.c_void_p), ("loss_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -64,6 +76,8 @@ SIGNATURES = {
     "lf_ogm_coeff": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "lf_qmf_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "lf_qmf_history_step": (C.c_int, [C.POINTER(LfQmfArgs), C.c_void_p]),
+    "lf_mid_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "lf_step_mid": (C.c_int, [C.POINTER(LfMidArgs), C.c_void_p]),
     "lf_modulate_workspace_bytes": (C.c_size_t, []),
     "lf_ogm_modulate": (C.c_int, [C.POINTER(LfTensorList), C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64,
                                   C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -30,7 +30,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + sources() + ["-lcuda"]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("LF_EXTRA_NVCC", "").split() + ["-o", OUT] + sources() + ["-lcuda"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -17,6 +17,12 @@
 namespace lf {
 int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* dbpart, float* rowstat, cudaStream_t s);  // lf_tc_fwd.cu
 int tc_forward_parts(int B);
+// lf_narrow.cu
+int narrow_tile(int C, int D, bool fwd_only);
+size_t narrow_dw_floats(int C, int D);
+int narrow_run(const LfHeadsArgs* a, int pass, float* partials, float* dbpart, float* calpart, float* dwpart,
+               float* rowstat, int nb_total, int* grid_out, cudaStream_t s);
+void finalize_forward_stats(const float* partials, int nblocks, int C, double* stats, cudaStream_t s);  // lf_rows.cu
 }
 
 namespace lf {
@@ -83,6 +89,7 @@ HeadsWorkspace carve_heads_workspace(void* base, int B, int D, int C) {
   w.dw_partials = (float*)take((size_t)2 * kMaxSplits * C * D * sizeof(float));
   w.db_partials = (float*)take((size_t)part_rows * 2 * C * sizeof(float));
   w.cal_partials = (float*)take((size_t)kMaxRowBlocks * 2 * sizeof(float));
+  w.narrow_dw = narrow_tile(C, D, false) > 0 ? (float*)take(narrow_dw_floats(C, D) * sizeof(float)) : nullptr;
   w.total = off + (size_t)B * 4 * sizeof(float) + 256;  // + rowstat
   return w;
 }
@@ -94,6 +101,17 @@ static float* rowstat_ptr(void* base, int B, int D, int C) {
 
 // The tensor pipe only pays for wide heads (C = 6/20 is HBM-bound on FMA).
 static bool use_tensor_pipe(const LfHeadsArgs* a) { return a->precision == LF_PREC_TF32 && a->classes >= 32; }
+// Narrow heads (C <= 32, HBM-bound on FMA): one fused kernel per pass over the features (lf_narrow.cu).
+static bool use_narrow(const LfHeadsArgs* a) {
+  return !use_tensor_pipe(a) && a->classes <= 32 && narrow_tile(a->classes, a->dim, false) > 0 && !getenv("LF_NO_NARROW");
+}
+static int narrow_grid(const LfHeadsArgs* a, bool fwd_only) {
+  const int S = narrow_tile(a->classes, a->dim, fwd_only);
+  int grid = div_up(a->batch, S);
+  if (grid > 148) grid = 148;
+  const int rpc = div_up(div_up(a->batch, grid), S) * S;
+  return div_up(a->batch, rpc);
+}
 
 static int tc_block_n(int n) {            // N tile: <= 256, multiple of 16, balanced over the tiles
   const int tiles = div_up(n, 256);
@@ -200,6 +218,19 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
   for (int m = 0; m < 2; ++m) { g.A[m] = a->feat[m]; g.B[m] = a->weight[m]; g.bias[m] = a->bias[m]; g.C[m] = a->logits[m]; }
   g.M = a->batch; g.N = a->classes; g.K = a->dim;
   g.lda = a->dim; g.ldb = a->dim; g.ldc = a->classes;
+  if (use_narrow(a)) {
+    // JLOGITS: forward AND backward of the heads in this one pass (unless the caller only wants the forward);
+    // QMF: forward pass, the backward pass follows the mid-step exchange
+    const int pass = a->mode == LF_MODE_QMF ? 1 : 0;
+    LfHeadsArgs b = *a;
+    if (a->mode == LF_MODE_JLOGITS && a->fwd_only) b.need_dfeat = 0;
+    int grid = 0;
+    rc = narrow_run(&b, (a->mode == LF_MODE_JLOGITS && a->fwd_only) ? 1 : pass, w.row_partials, w.db_partials, w.cal_partials,
+                    w.narrow_dw, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), 0, &grid, s);
+    if (rc) return rc;
+    finalize_forward_stats(w.row_partials, grid, a->classes, a->stats, s);
+    return check_launch("finalize_stats");
+  }
   if (use_tensor_pipe(a) && a->classes <= 256 && getenv("LF_FUSED_FWD")) {
     // logits GEMMs + all per-sample forward math in one kernel (lf_tc_fwd.cu)
     return tc_heads_forward(a, w.row_partials, w.db_partials, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), s);
@@ -225,6 +256,25 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   HeadsWorkspace w = carve_heads_workspace(a->workspace, a->batch, a->dim, a->classes);
+  if (use_narrow(a)) {
+    const size_t cdn = (size_t)a->classes * a->dim;
+    int grid = narrow_grid(a, false), nb_cal;
+    if (a->mode == LF_MODE_QMF) {
+      rc = narrow_run(a, 2, w.row_partials, w.db_partials, w.cal_partials, w.narrow_dw,
+                      rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), 0, &grid, s);
+      nb_cal = grid;
+    } else {
+      // dz, dfeat, dW and db partials were produced by the fused forward pass; only the calibrated counts
+      // (which need this step's EMA offsets) are left
+      if (a->fwd_only) { set_error("lf_heads_backward called for a step whose forward ran with fwd_only"); return LF_ERR_BAD_ARG; }
+      rc = rows_backward(rows_args(a, w), a->mode, s);
+      nb_cal = row_blocks(a->batch);
+    }
+    if (rc) return rc;
+    rc = reduce_splits2(w.narrow_dw, a->dweight[0], a->dweight[1], grid, 148, cdn, s);
+    if (rc) return rc;
+    return finalize_db_cal(w.db_partials, grid, a->classes, w.cal_partials, nb_cal, a->dbias[0], a->dbias[1], a->stats, s);
+  }
   rc = rows_backward(rows_args(a, w), a->mode, s);
   if (rc) return rc;
   const float* dz[2] = {a->dlogits[0], a->mode == LF_MODE_QMF ? a->dlogits[1] : a->dlogits[0]};

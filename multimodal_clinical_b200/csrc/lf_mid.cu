@@ -1,0 +1,311 @@
+// The middle of the step in ONE launch: everything that needs global-batch quantities between the
+// forward and the backward pass (SURVEY.md §8 a5-a8, a11 and the loss assembly a4).
+//
+//   global statistics   = sum over ranks of the per-rank partial statistics, in rank order (bit-identical
+//                         on every GPU, so replicated EMA / History state never diverges)
+//   EMA update          utils/EMA.py:29-38          OGM-GE coefficients   existing_algos/OGM_GE.py:24-40
+//   QMF History update  existing_algos/QMF.py:20-29 (scalar batch-mean CE, last duplicate wins)
+//   global min/max, ranking targets, ranking loss + dL/dconf   QMF.py:37-68, 119-141
+//   total loss          cremad/joint_model_qmf.py:70 / cremad/joint_model_ogm_ge.py:56
+//
+// The reference spreads this over ~15 host round trips; the previous version of this library over eight
+// small launches and (sharded) three collectives.  Here the inputs arrive as ONE rank-major gathered
+// buffer ([rank][stats | idx | conf], a single all-gather) and one thread-block CLUSTER of 8 CTAs walks
+// the dependent phases with hardware cluster barriers (barrier.cluster, release/acquire) in between:
+//   P0 sum statistics, EMA, coefficients   P1 ticket = last writer per index   P2 History update
+//   P3 min/max over all N                  P4 ranking terms, dL/dconf          P5 loss
+#include <cooperative_groups.h>
+#include "lf_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace lf {
+
+constexpr int kMidCtas = 8;          // portable cluster size
+constexpr int kMidThreads = 1024;
+
+// rank-major gathered batch: sample j of the global batch lives on rank j / Bl
+struct Gathered {
+  const int64_t* idx; long long idx_stride;     // elements between ranks
+  const float* conf; long long conf_stride;     // conf of one rank: [2][Bl]
+  int Bl, Bg;
+  __device__ __forceinline__ int64_t idx_at(int j) const {
+    const int r = j / Bl, i = j - r * Bl;
+    return idx[(size_t)r * idx_stride + i];
+  }
+  __device__ __forceinline__ float conf_at(int m, int j) const {
+    const int r = j / Bl, i = j - r * Bl;
+    return conf[(size_t)r * conf_stride + (size_t)m * Bl + i];
+  }
+};
+
+struct MidShared {
+  double lo[2], hi[2];
+  float s0, q0, q1;
+  float l0, l1;          // fp32 batch-mean unimodal CE handed to the History
+  float red[32];
+  int nan;
+};
+
+// After P3 the normalised correctness of every sample of the batch sits in two contiguous fp64 rows
+// A[m][j] = (corr_m[idx_j] - min_m) / (max_m - min_m)  (QMF.py:37-42, 51-52), so the pair terms below only
+// touch contiguous memory; the random History accesses happen once per sample, in the phase that fills A.
+__device__ __forceinline__ float a_pair_target(const double* __restrict__ A, int Bg, int j, float* margin) {
+  const int j2 = (j + 1 == Bg) ? 0 : j + 1;
+  const double a = A[j], b = A[j2];
+  if (margin) *margin = (float)fabs(a - b);
+  return (a > b ? 1.f : 0.f) - (a < b ? 1.f : 0.f);
+}
+__device__ __forceinline__ void g_pair_terms(const MidShared& sh, const double* __restrict__ A, const Gathered& g,
+                                             int j, float* x0, float* x1, float* t0, float* t1) {
+  *t0 = a_pair_target(A, g.Bg, j, nullptr);
+  *t1 = a_pair_target(A + g.Bg, g.Bg, j, nullptr);
+  const float r = (j + 1 < g.Bg) ? g.conf_at(0, j + 1) : g.conf_at(1, 0);   // flattened roll wraps into modality 1
+  *x0 = *t0 * (g.conf_at(0, j) - (r + sh.s0));                               // MarginRankingLoss(x1, x2, -t)
+  *x1 = *t1 * (g.conf_at(1, j) - ((r + sh.q0) + sh.q1));
+}
+
+struct MidParams {
+  LfMidArgs a;
+  double* minmax;     // [kMidCtas][2][2]
+  float* regpart;     // [kMidCtas]
+  double* A;          // [2][Bg] normalised correctness of the batch
+};
+
+__global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
+  const LfMidArgs& a = p.a;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int ncta = (int)cluster.num_blocks(), cta = (int)cluster.block_rank();
+  const int tid = cta * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x;
+  const int C = a.classes, len = LF_STATS_HEADER + 2 * C, Bg = a.batch_global, N = a.n_data;
+  extern __shared__ double s_stats[];                 // [len] global statistics (each CTA keeps a copy)
+  __shared__ MidShared sh;
+
+  // ---- P0: global statistics in rank order
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < a.n_ranks; ++r) s += a.stats_parts[(size_t)r * a.stats_stride + i];
+    s_stats[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sh.l0 = (float)(s_stats[LF_STAT_CE_X1] / (double)Bg);     // cremad/joint_model_qmf.py:64
+    sh.l1 = (float)(s_stats[LF_STAT_CE_X2] / (double)Bg);
+    sh.nan = 0;
+  }
+  if (cta == 0) {
+    for (int i = threadIdx.x; i < len; i += blockDim.x)
+      if (i != LF_STAT_CNT_X1_CAL && i != LF_STAT_CNT_X2_CAL) a.stats[i] = s_stats[i];
+    if (a.update_ema)
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {     // utils/EMA.py:33, 38
+        const float beta = a.smoothing;
+        const float mean1 = (float)(s_stats[LF_STATS_HEADER + c] / (double)Bg);
+        const float mean2 = (float)(s_stats[LF_STATS_HEADER + C + c] / (double)Bg);
+        const float x1 = mean1 * beta + a.ema_x[c] * (1.0f - beta);
+        const float x2 = mean2 * beta + a.ema_x[C + c] * (1.0f - beta);
+        a.ema_x[c] = x1; a.ema_x[C + c] = x2;
+        const float mu = (x1 + x2) / 2.f;
+        a.ema_offset[c] = mu - x1; a.ema_offset[C + c] = mu - x2;
+      }
+    if (a.coeff_out && threadIdx.x == 0) {                    // existing_algos/OGM_GE.py:24-40
+      const float s1 = (float)s_stats[LF_STAT_SCORE_X1], s2 = (float)s_stats[LF_STAT_SCORE_X2];
+      const float r1 = s1 / s2, r2 = 1.f / r1;
+      float k1 = 1.f, k2 = 1.f;
+      if (r1 > 1.f) k1 = 1.f - tanhf(a.alpha * fmaxf(r1, 0.f));
+      else k2 = 1.f - tanhf(a.alpha * fmaxf(r2, 0.f));
+      a.coeff_out[0] = k1; a.coeff_out[1] = k2;
+    }
+  }
+  __syncthreads();
+
+  if (a.mode != LF_MODE_QMF) {
+    if (cta == 0 && threadIdx.x == 0 && a.loss_out) a.loss_out[0] = (float)(s_stats[LF_STAT_CE_JOINT] / (double)Bg);
+    return;
+  }
+
+  Gathered g;
+  g.idx = a.idx_parts; g.idx_stride = a.idx_stride; g.conf = a.conf_parts; g.conf_stride = a.conf_stride;
+  g.Bl = a.batch_local; g.Bg = Bg;
+  const long long base = a.step_base;
+  long long* lw = (long long*)a.last_writer;
+
+  // ---- P1: the last duplicate of an index wins (numpy fancy assignment): ticket = position in the batch
+  for (int j = tid; j < Bg; j += nthr) {
+    const int64_t i = g.idx_at(j);
+    if ((unsigned long long)i < (unsigned long long)N) atomicMax(&lw[i], base + j);
+  }
+  cluster.sync();
+  // ---- P2: History.correctness_update (QMF.py:20-29), alpha = 0.1.  Four samples per thread per round so
+  // the dependent random accesses (idx -> ticket -> History entry) of different samples overlap.
+  for (int j0 = tid; j0 < Bg; j0 += 4 * nthr) {
+    int64_t ii[4]; long long w[4]; double c0[4], c1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int j = j0 + u * nthr; ii[u] = j < Bg ? g.idx_at(j) : -1; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = ((unsigned long long)ii[u] < (unsigned long long)N) ? lw[ii[u]] : -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool mine = w[u] == base + (j0 + u * nthr);
+      c0[u] = mine ? a.correctness[ii[u]] : 0.0; c1[u] = mine ? a.correctness[(size_t)N + ii[u]] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * nthr;
+      if (w[u] != base + j) continue;
+      a.correctness[ii[u]] = 0.9 * c0[u] + 0.1 * (double)sh.l0;
+      a.correctness[(size_t)N + ii[u]] = 0.9 * c1[u] + 0.1 * (double)sh.l1;
+      a.confidence[ii[u]] = (double)g.conf_at(0, j);
+      a.confidence[(size_t)N + ii[u]] = (double)g.conf_at(1, j);
+    }
+  }
+  cluster.sync();
+  // ---- P3: min / max over ALL N entries of both modalities (QMF.py:38-40), NaN-propagating like numpy
+  for (int m = 0; m < 2; ++m) {
+    const double* c = a.correctness + (size_t)m * N;
+    double lo = INFINITY, hi = -INFINITY;
+    bool nan = false;
+    for (int i = tid; i < N; i += nthr) { const double v = c[i]; nan |= (v != v); lo = fmin(lo, v); hi = fmax(hi, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(kFull, lo, o)); hi = fmax(hi, __shfl_xor_sync(kFull, hi, o)); }
+    if (nan) atomicOr(&sh.nan, 1 << m);
+    __shared__ double slo[32], shi[32];
+    if (threadIdx.x % 32 == 0) { slo[threadIdx.x / 32] = lo; shi[threadIdx.x / 32] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)blockDim.x / 32; ++w) { lo = fmin(lo, slo[w]); hi = fmax(hi, shi[w]); }
+      if (sh.nan & (1 << m)) { lo = NAN; hi = NAN; }
+      p.minmax[(cta * 2 + m) * 2 + 0] = lo; p.minmax[(cta * 2 + m) * 2 + 1] = hi;
+    }
+    __syncthreads();
+  }
+  cluster.sync();
+  if (threadIdx.x < 2) {
+    const int m = threadIdx.x;
+    double lo = p.minmax[m * 2], hi = p.minmax[m * 2 + 1];
+    bool nan = (lo != lo);
+    for (int b = 1; b < ncta; ++b) {
+      const double l = p.minmax[(b * 2 + m) * 2], h = p.minmax[(b * 2 + m) * 2 + 1];
+      nan |= (l != l);
+      lo = fmin(lo, l); hi = fmax(hi, h);
+    }
+    if (nan) { lo = NAN; hi = NAN; }
+    sh.lo[m] = lo; sh.hi[m] = hi;
+  }
+  __syncthreads();
+  // normalised correctness of the batch, four samples per thread per round (random History reads overlap)
+  for (int j0 = tid; j0 < Bg; j0 += 4 * nthr) {
+    int64_t ii[4]; double c0[4], c1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int j = j0 + u * nthr; ii[u] = j < Bg ? g.idx_at(j) : -1; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = (unsigned long long)ii[u] < (unsigned long long)N;      // out-of-range index -> NaN
+      c0[u] = ok ? a.correctness[ii[u]] : (double)NAN; c1[u] = ok ? a.correctness[(size_t)N + ii[u]] : (double)NAN;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * nthr;
+      if (j < Bg) { p.A[j] = (c0[u] - sh.lo[0]) / (sh.hi[0] - sh.lo[0]); p.A[Bg + j] = (c1[u] - sh.lo[1]) / (sh.hi[1] - sh.lo[1]); }
+    }
+  }
+  cluster.sync();
+  if (threadIdx.x == 0) {
+    float m00, m11;
+    const float t00 = a_pair_target(p.A, Bg, 0, &m00);
+    const float t01 = a_pair_target(p.A, Bg, 1, nullptr);
+    const float t11 = a_pair_target(p.A + Bg, Bg, 1, &m11);
+    const float z00 = t00 == 0.f ? 1.f : t00, z01 = t01 == 0.f ? 1.f : t01, z11 = t11 == 0.f ? 1.f : t11;
+    sh.s0 = m00 / z00;     // rank_margin[0] / rank_target_nonzero, row 0   (QMF.py:134, n = 0)
+    sh.q0 = m00 / z01;     // same matrix, row 1 (picked up by n = 1)
+    sh.q1 = m11 / z11;     // n = 1: rank_margin[1] / rank_target_nonzero, row 1
+  }
+  __syncthreads();
+  // ---- P4: ranking terms and dL_reg/dconf for this rank's slice
+  float reg = 0.f;
+  const float invB = 1.f / (float)Bg;
+  const int g_begin = a.rank * a.batch_local, g_end = g_begin + a.batch_local;
+  for (int j = tid; j < Bg; j += nthr) {
+    float x0, x1, t0, t1;
+    g_pair_terms(sh, p.A, g, j, &x0, &x1, &t0, &t1);
+    reg += relu_nan(x0) + relu_nan(x1);
+    if (j >= g_begin && j < g_end && a.qmf_g) {
+      const float u0 = (x0 >= 0.f) ? t0 * invB : 0.f;       // clamp_min backward mask is (x >= 0)
+      const float u1 = (x1 >= 0.f) ? t1 * invB : 0.f;
+      const int jp = (j == 0) ? Bg - 1 : j - 1;
+      float px0, px1, pt0, pt1;
+      g_pair_terms(sh, p.A, g, jp, &px0, &px1, &pt0, &pt1);
+      const float v = -(((px0 >= 0.f) ? pt0 * invB : 0.f) + ((px1 >= 0.f) ? pt1 * invB : 0.f));
+      a.qmf_g[j - g_begin] = u0 + (j >= 1 ? v : 0.f);       // pair jp's rolled operand is conf0[j] for j >= 1
+      a.qmf_g[a.batch_local + (j - g_begin)] = u1 + (j == 0 ? v : 0.f);   // ... and conf1[0] for j == 0
+    }
+  }
+  reg = warp_sum(reg);
+  if (threadIdx.x % 32 == 0) sh.red[threadIdx.x / 32] = reg;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    bool nan = false;
+    for (int w = 0; w < (int)blockDim.x / 32; ++w) { s += sh.red[w]; nan |= (sh.red[w] != sh.red[w]); }
+    p.regpart[cta] = nan ? NAN : s;
+  }
+  cluster.sync();
+  // ---- P5: loss = CE(z_df) + CE(z1) + CE(z2) + L_reg, each a separate fp32 mean like the reference
+  if (cta == 0 && threadIdx.x == 0) {
+    double rs = 0.0;
+    for (int b = 0; b < ncta; ++b) rs += (double)p.regpart[b];
+    a.stats[LF_STAT_REG_SUM] = rs;
+    if (a.loss_out) {
+      const double inv = 1.0 / (double)Bg;
+      const float uni = (float)(s_stats[LF_STAT_CE_X1] * inv) + (float)(s_stats[LF_STAT_CE_X2] * inv);
+      a.loss_out[0] = ((float)(s_stats[LF_STAT_CE_JOINT] * inv) + uni) + (float)(rs * inv);
+    }
+  }
+}
+
+}  // namespace lf
+
+using namespace lf;
+
+extern "C" size_t lf_mid_workspace_bytes(int32_t batch_global) {
+  return 512 + sizeof(double) * kMidCtas * 4 + sizeof(double) * 2 * (size_t)(batch_global > 0 ? batch_global : 0);
+}
+
+extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
+  if (!a || !a->stats_parts || !a->stats || a->classes < 1 || a->batch_global < 1 || a->n_ranks < 1 ||
+      a->batch_local < 1 || a->batch_local * a->n_ranks != a->batch_global || a->rank < 0 || a->rank >= a->n_ranks) {
+    set_error("lf_step_mid: bad argument");
+    return LF_ERR_BAD_ARG;
+  }
+  if (a->update_ema && (!a->ema_x || !a->ema_offset)) { set_error("lf_step_mid: update_ema needs ema_x / ema_offset"); return LF_ERR_BAD_ARG; }
+  const bool qmf = a->mode == LF_MODE_QMF;
+  if (qmf) {
+    if (!a->idx_parts || !a->conf_parts || !a->correctness || !a->confidence || !a->last_writer || !a->workspace ||
+        a->n_data < 1 || a->step_base < 1) { set_error("lf_step_mid: QMF mode needs idx/conf/History/workspace"); return LF_ERR_BAD_ARG; }
+    if (a->batch_global < 2) {
+      set_error("lf_step_mid: batch_global must be >= 2 (reference raises for a batch of one)");
+      return LF_ERR_BAD_ARG;
+    }
+    if (a->workspace_bytes < lf_mid_workspace_bytes(a->batch_global)) { set_error("lf_step_mid: workspace too small"); return LF_ERR_WORKSPACE; }
+  } else if (a->mode != LF_MODE_JLOGITS) { set_error("lf_step_mid: bad mode %d", a->mode); return LF_ERR_BAD_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  MidParams p;
+  p.a = *a;
+  p.minmax = qmf ? (double*)a->workspace : nullptr;
+  p.regpart = qmf ? (float*)((char*)a->workspace + 256) : nullptr;
+  p.A = qmf ? (double*)((char*)a->workspace + 512) : nullptr;
+  const size_t smem = sizeof(double) * (LF_STATS_HEADER + 2 * (size_t)a->classes);
+  cudaLaunchConfig_t cfg = {};
+  const int ncta = qmf ? kMidCtas : 1;
+  cfg.gridDim = dim3(ncta, 1, 1);
+  cfg.blockDim = dim3(qmf ? kMidThreads : 256, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaSuccess;
+  LF_LAUNCH("step_mid", s, (e = cudaLaunchKernelEx(&cfg, mid_kernel, p)));
+  if (e != cudaSuccess) { set_error("lf_step_mid: %s", cudaGetErrorString(e)); return LF_ERR_CUDA; }
+  return check_launch("lf_step_mid");
+}

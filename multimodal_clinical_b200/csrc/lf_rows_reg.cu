@@ -13,47 +13,9 @@
 // Reference arithmetic: see lf_rows.cu (same formulas; this file only changes the mapping to the machine).
 #include "lf_common.cuh"
 #include "lf_rows.cuh"
+#include "lf_rowmath.cuh"
 
 namespace lf {
-
-__device__ __forceinline__ unsigned f2ord(float f) {
-  const unsigned b = __float_as_uint(f + 0.f);                 // + 0.f folds -0 into +0 (they compare equal)
-  return b ^ ((b & 0x80000000u) ? 0xffffffffu : 0x80000000u);
-}
-__device__ __forceinline__ float ord2f(unsigned u) {
-  return __uint_as_float(u ^ ((u & 0x80000000u) ? 0x80000000u : 0xffffffffu));
-}
-// warp max + first index attaining it (torch.argmax semantics); v[k] holds class lane + 32 k
-template <int NCH>
-__device__ __forceinline__ void warp_max_arg(const float (&v)[NCH], int lane, float& mx, int& arg) {
-  float lm = v[0];
-#pragma unroll
-  for (int k = 1; k < NCH; ++k) lm = fmaxf(lm, v[k]);
-  mx = ord2f(__reduce_max_sync(kFull, f2ord(lm)));
-  unsigned idx = 0x7fffffffu;
-#pragma unroll
-  for (int k = NCH - 1; k >= 0; --k) idx = (v[k] == mx) ? (unsigned)(lane + 32 * k) : idx;
-  arg = (int)__reduce_min_sync(kFull, idx);
-}
-// exp(x - m) with the scale folded into one FFMA: ex2(x * log2e - m * log2e)
-__device__ __forceinline__ float exp_sub(float x, float m_log2e) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(x, 1.4426950408889634f, -m_log2e)));
-  return r;
-}
-template <int NCH>
-__device__ __forceinline__ float pick_class(const float (&v)[NCH], int y) {   // value of class y, broadcast
-  float r = 0.f;
-#pragma unroll
-  for (int k = 0; k < NCH; ++k) r = ((y >> 5) == k) ? v[k] : r;
-  return __shfl_sync(kFull, r, y & 31);
-}
-__device__ __forceinline__ void warp_sum3(float& a, float& b, float& c) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); c += __shfl_xor_sync(kFull, c, o);
-  }
-}
 
 template <int NCH>
 __device__ __forceinline__ void load_row(const float* __restrict__ z1, const float* __restrict__ z2, size_t off, int C,
@@ -113,7 +75,8 @@ __global__ void __launch_bounds__(256) rows_forward_reg_kernel(RowsArgs a) {
     warp_sum3(s1, s2, sa);
     const float lse1 = m1 + __logf(s1), lse2 = m2 + __logf(s2), lsea = ma + __logf(sa);
     const bool yok = (unsigned)y < (unsigned)C;
-    const float zy1 = yok ? pick_class<NCH>(v1, y) : 0.f, zy2 = yok ? pick_class<NCH>(v2, y) : 0.f;
+    const float py1 = pick_class<NCH>(v1, y), py2 = pick_class<NCH>(v2, y);
+    const float zy1 = yok ? py1 : 0.f, zy2 = yok ? py2 : 0.f;
 
     float ce_joint;
     int cnt_df = 0;
@@ -136,7 +99,8 @@ __global__ void __launch_bounds__(256) rows_forward_reg_kernel(RowsArgs a) {
       for (int k = 0; k < NCH; ++k) sd += exp_sub(vd[k], md * 1.4426950408889634f);
       sd = warp_sum(sd);
       const float lsed = md + __logf(sd);
-      const float zyd = yok ? pick_class<NCH>(vd, y) : 0.f;
+      const float pyd = pick_class<NCH>(vd, y);
+      const float zyd = yok ? pyd : 0.f;
       ce_joint = lsed - zyd;
       cnt_df = (idf == y);
       if (lane == 0) {

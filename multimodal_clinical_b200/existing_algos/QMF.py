@@ -52,9 +52,16 @@ class _QmfState:
             self.confidence = torch.zeros(2, self.n_data, dtype=torch.float64, device=device)    # QMF.py:14
         self.last_writer = torch.zeros(self.n_data, dtype=torch.int64, device=device)
         self.ws = torch.empty(lib.lf_qmf_workspace_bytes(self.n_data), dtype=torch.uint8, device=device)
+        self.mid_ws = None
         self.stats = torch.zeros(_lib.LF_STATS_HEADER, dtype=torch.float64, device=device)
         self.device = device
         return self
+
+    def mid_workspace(self, batch_global: int) -> torch.Tensor:
+        need = _lib.load().lf_mid_workspace_bytes(int(batch_global))
+        if self.mid_ws is None or self.mid_ws.numel() < need:
+            self.mid_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self.mid_ws
 
     def run(self, idx: torch.Tensor, conf: torch.Tensor, flags: int, loss_uni=(None, None),
             qmf_g: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -35,6 +35,17 @@ def allreduce_sum_(t: torch.Tensor, pg=None) -> torch.Tensor:
     return t
 
 
+def gather_payload(payload: torch.Tensor, pg=None) -> torch.Tensor:
+    """Every rank's [stats | idx | conf] byte payload -> (world, nbytes), rank-major: the ONE exchange between
+    the forward and the backward pass.  lf_step_mid consumes the rank-major layout directly."""
+    rank, ws = world(pg)
+    if ws == 1:
+        return payload
+    out = torch.empty(ws * payload.numel(), dtype=payload.dtype, device=payload.device)
+    dist.all_gather_into_tensor(out, payload, group=pg)
+    return out
+
+
 def gather_batch(idx_local: torch.Tensor, conf_local: torch.Tensor, pg=None
                  ) -> Tuple[torch.Tensor, torch.Tensor]:
     """idx (B,) int64 and conf (2,B) of every rank -> idx (Bg,), conf (2,Bg) in global batch order."""

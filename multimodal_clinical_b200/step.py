@@ -5,8 +5,9 @@ collectives of the batch-sharded (data-parallel) layout.
 One process per GPU.  Rank r holds samples [r*B/G, (r+1)*B/G) of the global batch; heads, EMA state and
 the QMF History are replicated and stay bit-identical across ranks because every rank applies the same
 update from all-reduced / all-gathered inputs.  Exchanges per step:
-  JLOGITS / OGM-GE : all-reduce(stats)                          -> all-reduce([dW1|db1|dW2|db2|cal counts])
-  QMF              : all-reduce(stats), all-gather(idx, conf)   -> all-reduce([dW1|db1|dW2|db2|cal counts])
+  forward -> all-gather([partial stats | idx | conf])  -> lf_step_mid (sums the partials in rank order)
+          -> backward -> all-reduce([dW1|db1|dW2|db2|calibrated counts])
+i.e. two collectives per step for every head type (idx / conf are only present for QMF).
 No host synchronisation happens inside a step; metrics are read from ``stats`` lazily.
 """
 from __future__ import annotations
@@ -20,7 +21,7 @@ import torch.distributed as dist
 
 from . import _lib, parallel
 from ._lib import (LF_MODE_JLOGITS, LF_MODE_QMF, LF_PREC_FP32, LF_PREC_TF32, LF_STATS_HEADER, STAT,
-                   LfHeadsArgs, LfQmfArgs, LfTensorList, check)
+                   LfHeadsArgs, LfMidArgs, LfQmfArgs, LfTensorList, check)
 
 _MOD = {"OGM_GE": _lib.LF_MOD_OGM_GE, "OGM": _lib.LF_MOD_OGM, "noise": _lib.LF_MOD_NOISE}
 
@@ -112,6 +113,8 @@ class LateFusionStep:
             self.ema_x, self.ema_offset, self.smoothing = ema.x, ema._offset, float(ema.smoothing)
         self.ema = ema
         self.fresh_outputs = False
+        self._pay = None
+        self._pay_key = None
         self._ws = None
         self._ws_key = None
         self._bufs = {}
@@ -163,6 +166,21 @@ class LateFusionStep:
             return b
         return self._bufs
 
+    def _payload(self, B: int, qmf: bool):
+        n_stats = LF_STATS_HEADER + 2 * self.C
+        self._off_idx = 8 * n_stats
+        self._off_conf = self._off_idx + (8 * B if qmf else 0)
+        nbytes = self._off_conf + (8 * B if qmf else 0)
+        key = (B, qmf)
+        if self.fresh_outputs or self._pay_key != key:
+            self._pay = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._pay_key = key
+        pay = self._pay
+        p_stats = pay[:self._off_idx].view(torch.float64)
+        p_idx = pay[self._off_idx:self._off_conf].view(torch.int64) if qmf else None
+        p_conf = pay[self._off_conf:].view(torch.float32).view(2, B) if qmf else None
+        return pay, p_stats, p_idx, p_conf
+
     # ------------------------------------------------------------------ the step
     def step(self, feats: Sequence[torch.Tensor], weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
              label: torch.Tensor, idx: Optional[torch.Tensor] = None, need_dfeat: bool = True,
@@ -189,11 +207,19 @@ class LateFusionStep:
         dW = [gf[0:n].view(Cn, D), gf[n + Cn:2 * n + Cn].view(Cn, D)]
         db = [gf[n:n + Cn], gf[2 * n + Cn:2 * n + 2 * Cn]]
         qmf = self.mode == LF_MODE_QMF
+        # this rank's contribution to the one exchange before the backward pass:
+        # [partial statistics (16+2C) f64 | idx (B) i64 | conf (2,B) f32], 8-byte aligned pieces
+        pay, p_stats, p_idx, p_conf = self._payload(B, qmf)
+        if qmf:
+            if idx is None:
+                raise ValueError("QMF step needs the dataset indices of the batch (idx)")
+            p_idx.copy_(idx.reshape(-1))
 
         a = LfHeadsArgs()
         a.batch, a.batch_global, a.dim, a.classes = B, Bg, D, Cn
         a.mode, a.precision, a.need_dfeat = self.mode, self.precision, int(need_dfeat)
         a.ld_dlogits = bufs["ldz"]
+        a.fwd_only = int(not backward)
         for m in range(2):
             a.feat[m] = _ptr(f[m]); a.weight[m] = _ptr(W[m]); a.bias[m] = _ptr(bb[m])
             a.logits[m] = _ptr(bufs["logits"][m])
@@ -201,45 +227,47 @@ class LateFusionStep:
             a.dweight[m] = _ptr(dW[m]); a.dbias[m] = _ptr(db[m])
         a.label = _ptr(label)
         a.avg_logits = _ptr(bufs["avg"])
-        a.logits_df = _ptr(bufs["zdf"]); a.conf = _ptr(bufs["conf"])
+        a.logits_df = _ptr(bufs["zdf"]); a.conf = _ptr(p_conf)
         a.dlogits[0] = _ptr(bufs["dz"][0]); a.dlogits[1] = _ptr(bufs["dz"][1]) if qmf else None
         a.qmf_g = _ptr(bufs["qmf_g"]); a.ema_offset = _ptr(self.ema_offset)
-        a.stats = _ptr(self.stats)
+        a.stats = _ptr(p_stats)                                   # forward writes the LOCAL partial sums
         a.workspace = _ptr(self._ws); a.workspace_bytes = self._ws.numel()
         st = _stream()
 
         check(lib.lf_heads_forward(C.byref(a), st), "lf_heads_forward")
-        parallel.allreduce_sum_(self.stats, self.pg)              # score sums, CE sums, logit sums, counts
+        gathered = parallel.gather_payload(pay, self.pg)          # (world, payload bytes); identity on one GPU
+        stride = pay.numel()
+        mid = LfMidArgs()
+        mid.mode, mid.classes, mid.batch_global, mid.n_ranks = self.mode, Cn, Bg, self.world
+        mid.batch_local, mid.rank, mid.n_data, mid.update_ema = B, self.rank, self.n_data or 0, int(update_ema)
+        base = gathered.data_ptr()
+        mid.stats_parts, mid.stats_stride = base, stride // 8
+        if qmf:
+            qs = self.qmf_state
+            mid.idx_parts, mid.idx_stride = base + self._off_idx, stride // 8
+            mid.conf_parts, mid.conf_stride = base + self._off_conf, stride // 4
+            mid.correctness, mid.confidence = _ptr(qs.correctness), _ptr(qs.confidence)
+            mid.last_writer, mid.step_base = _ptr(qs.last_writer), qs.step_base
+            mid.qmf_g = _ptr(bufs["qmf_g"]) if backward else None
+            mws = qs.mid_workspace(Bg)
+            mid.workspace, mid.workspace_bytes = _ptr(mws), mws.numel()
+            qs.step_base += Bg
+        mid.stats = _ptr(self.stats)
+        mid.ema_x, mid.ema_offset, mid.smoothing = _ptr(self.ema_x), _ptr(self.ema_offset), self.smoothing
+        if ogm_alpha is not None:
+            mid.alpha, mid.coeff_out = float(ogm_alpha), _ptr(self.coeff)
+        mid.loss_out = _ptr(self.loss)
+        check(lib.lf_step_mid(C.byref(mid), st), "lf_step_mid")
         if update_ema:
-            check(lib.lf_ema_update(_ptr(self.ema_x), _ptr(self.ema_offset), _ptr(self.stats), Cn, Bg,
-                                    self.smoothing, st), "lf_ema_update")
             self.ema_counter += 1
             if self.ema is not None:
                 self.ema.counter += 1
-        if ogm_alpha is not None:
-            check(lib.lf_ogm_coeff(_ptr(self.stats), float(ogm_alpha), _ptr(self.coeff), st), "lf_ogm_coeff")
-        if qmf:
-            if idx is None:
-                raise ValueError("QMF step needs the dataset indices of the batch (idx)")
-            idx = idx.to(device=self.device, dtype=torch.int64).contiguous().view(-1)
-            idx_g, conf_g = parallel.gather_batch(idx, bufs["conf"], self.pg)
-            q = LfQmfArgs()
-            q.batch_global, q.n_data = Bg, self.n_data
-            q.idx, q.conf = _ptr(idx_g), _ptr(conf_g)
-            qs = self.qmf_state
-            q.correctness, q.confidence = _ptr(qs.correctness), _ptr(qs.confidence)
-            q.last_writer, q.step_base = _ptr(qs.last_writer), qs.step_base
-            q.stats, q.qmf_g, q.target_out = _ptr(self.stats), _ptr(bufs["qmf_g"]), None
-            q.g_begin, q.g_count = parallel.shard_range(self.rank, B)
-            q.workspace, q.workspace_bytes = _ptr(qs.ws), qs.ws.numel()
-            q.flags = _lib.LF_QMF_ALL
-            check(lib.lf_qmf_history_step(C.byref(q), st), "lf_qmf_history_step")
-            qs.step_base += Bg
         if backward:
+            a.stats = _ptr(self.stats)                            # calibrated counts join the GLOBAL statistics
             check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
             # head gradients + calibrated counts: one all-reduce
             parallel.pack_grad_exchange(gf, 2 * (n + Cn), self.stats, STAT["CNT_X1_CAL"], STAT["CNT_X2_CAL"] + 1, self.pg)
-        check(lib.lf_loss_finalize(_ptr(self.stats), self.mode, Bg, _ptr(self.loss), st), "lf_loss_finalize")
+        bufs = dict(bufs, conf=p_conf if qmf else None)
 
         return StepOutput(
             logits=[bufs["logits"][0], bufs["logits"][1]], avg_logits=bufs["avg"], logits_df=bufs["zdf"],

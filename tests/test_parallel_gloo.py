@@ -56,8 +56,19 @@ def _worker(rank, world, port, B, D, C, N, q):
         stats[3], stats[4] = float(s1), float(s2)
         stats[16:16 + C] = z[0].detach().sum(0).double()
         stats[16 + C:] = z[1].detach().sum(0).double()
-        parallel.allreduce_sum_(stats)                                   # exchange 1
-        idx_g, conf_g = parallel.gather_batch(idx, conf.detach())        # exchange 2 (QMF)
+        # ---- exchange 1: ONE all-gather of the byte payload [stats f64 | idx i64 | conf (2,B) f32], then the
+        # rank-major decode lf_step_mid performs on the device (sum of the partial statistics in rank order)
+        n_stats = 16 + 2 * C
+        pay = torch.empty(8 * n_stats + 8 * B + 8 * B, dtype=torch.uint8)
+        pay[:8 * n_stats].view(torch.float64).copy_(stats)
+        pay[8 * n_stats:8 * n_stats + 8 * B].view(torch.int64).copy_(idx)
+        pay[8 * n_stats + 8 * B:].view(torch.float32).view(2, B).copy_(conf.detach())
+        gathered = parallel.gather_payload(pay).view(world, -1)
+        stats = torch.zeros_like(stats)
+        for r in range(world):
+            stats += gathered[r, :8 * n_stats].view(torch.float64)
+        idx_g = torch.cat([gathered[r, 8 * n_stats:8 * n_stats + 8 * B].view(torch.int64) for r in range(world)])
+        conf_g = torch.cat([gathered[r, 8 * n_stats + 8 * B:].view(torch.float32).view(2, B) for r in range(world)], dim=1)
         assert idx_g.shape == (Bg,) and conf_g.shape == (2, Bg)
         assert torch.equal(idx_g, full["idx"])
 
@@ -80,7 +91,7 @@ def _worker(rank, world, port, B, D, C, N, q):
         flat[0:n] = Wl[0].grad.flatten(); flat[n:n + C] = bl[0].grad
         flat[n + C:2 * n + C] = Wl[1].grad.flatten(); flat[2 * n + C:2 * n + 2 * C] = bl[1].grad
         stats[9], stats[10] = 3.0 + rank, 5.0 + rank                     # stand-in calibrated counts
-        parallel.pack_grad_exchange(flat, 2 * (n + C), stats, 9, 11)     # exchange 3
+        parallel.pack_grad_exchange(flat, 2 * (n + C), stats, 9, 11)     # exchange 2
         assert stats[9].item() == 3.0 * world + sum(range(world))
         assert stats[10].item() == 5.0 * world + sum(range(world))
         total_loss = (stats[0] + stats[1] + stats[2]).item() / Bg + reg.item()
