@@ -224,8 +224,9 @@ def run_reference(args, w, rank, world):
 def workload_config(w, args, world):
     return {"workload": f"{args.workload}: {w['desc']}", "head": w["mode"], "batch_per_gpu": w["B"],
             "global_batch": w["B"] * world, "feature_dim": w["D"], "classes": w["C"], "history_len": w["N"],
-            "precision": args.precision, "parallelism": f"dp{world}",
-            "l2": "inputs rotate over buffer sets totalling > 126 MB L2 (or a single set already larger)"}
+            "precision": args.precision, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+            "l2": ("inputs rotate over buffer sets totalling > 2x the 126 MB L2" if 2 * w["B"] * w["D"] * 4 * 8 >= 2 * L2_BYTES
+                   else "256 MB L2 flush between steps, outside the per-step CUDA-event brackets")}
 
 
 def cpu_baseline(w, budget_s=20.0):
@@ -263,6 +264,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--batch", type=int, default=None, help="override the workload's per-GPU batch (experiments)")
     ap.add_argument("--dim", type=int, default=None, help="override the feature width (experiments)")
     ap.add_argument("--classes", type=int, default=None, help="override the class count (experiments)")
@@ -293,19 +295,68 @@ def main():
     W, b = head_params(w)
     W = [x.to(dev) for x in W]; b = [x.to(dev) for x in b]
     in_bytes = 2 * w["B"] * w["D"] * 4
-    n_sets = max(2, min(1024, -(-2 * L2_BYTES // in_bytes)))
+    need_sets = max(2, -(-2 * L2_BYTES // in_bytes))
+    # few, large sets: rotating over them keeps every step's inputs out of L2.  Small workloads would need
+    # hundreds of sets; they use 8 and an explicit L2 flush (256 MB fill) between steps, outside the per-step
+    # CUDA-event brackets.
+    flush_l2 = need_sets > 8
+    n_sets = min(need_sets, 8)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if flush_l2 else None
     host_sets = make_batches(w, n_sets, dev, seed=100 + rank)
     dev_sets = [{k: v.to(dev) for k, v in s.items()} for s in host_sets]
     enc_grads = None
     if w["modulate"]:
         enc_grads = [[torch.randn(s, device=dev) * 1e-3 for s in resnet18_conv_shapes(c)] for c in (1, 3)]
 
-    def one_step(s, i):
+    def modulate(i):
+        for m in range(2):
+            eng.modulate(enc_grads[m], which=m, modulation="OGM_GE", seed=5, offset=i * (1 << 24))
+
+    def eager_step(s, i):
         out = eng.step([s["f1"], s["f2"]], W, b, s["y"], idx=s.get("idx"), need_dfeat=w["dfeat"], ogm_alpha=w["alpha"])
         if enc_grads is not None:
-            for m in range(2):
-                eng.modulate(enc_grads[m], which=m, modulation="OGM_GE", seed=5, offset=i * (1 << 24))
+            modulate(i)
         return out
+
+    # One CUDA graph per input set (the step's kernels, its collectives and the OGM-GE modulation): the
+    # step is ~10 launches of 5-60 us, so launch latency and host time are a first-order cost when issued
+    # eagerly.  All step state is device-resident, so a replay advances EMA / History like an eager call.
+    # (The Philox offset of the noise is baked per graph: a replay re-draws the same noise stream.)
+    graphs = {}
+    use_graph = not args.no_graph
+
+    def one_step(s, i):
+        if not use_graph:
+            return eager_step(s, i)
+        key = id(s)
+        if key not in graphs:
+            n0 = lib.lf_launch_count()
+            g, out = eng.capture([s["f1"], s["f2"]], W, b, s["y"], idx=s.get("idx"), need_dfeat=w["dfeat"],
+                                 ogm_alpha=w["alpha"], extra=(lambda: modulate(i)) if enc_grads is not None else None, warmup=2)
+            graphs[key] = (g, out, (lib.lf_launch_count() - n0) // 3)      # 2 warm-up steps + the captured one
+        g, out, _ = graphs[key]
+        g.replay()
+        return out
+
+    def timed_steps(n, step_fn):
+        """n steps on rotating input sets -> (device ms, launches).  Without flush: one event pair around the loop.
+        With flush: one pair per step, the L2 flush between steps stays outside the brackets."""
+        if not flush_l2:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n):
+                step_fn(dev_sets[i % n_sets], i)
+            e1.record()
+            barrier()
+            return e0.elapsed_time(e1)
+        evs = []
+        for i in range(n):
+            flush_buf.fill_(i & 0xff)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step_fn(dev_sets[i % n_sets], i); e1.record()
+            evs.append((e0, e1))
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in evs)
 
     def barrier():
         if world > 1:
@@ -313,20 +364,15 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (value)
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, n_sets if use_graph else 0)):      # also captures every set's graph
         one_step(dev_sets[i % n_sets], i)
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     c0 = clocks.mark() if clocks else 0
     l0 = lib.lf_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        one_step(dev_sets[i % n_sets], i)
-    e1.record()
-    barrier()
-    launches = lib.lf_launch_count() - l0
-    ms = e0.elapsed_time(e1)
+    ms = timed_steps(args.steps, one_step)
+    launches = (lib.lf_launch_count() - l0) if not use_graph else args.steps * next(iter(graphs.values()))[2]
     c1 = clocks.mark() if clocks else 0
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -338,7 +384,7 @@ def main():
     # ---------------- per-kernel CUDA-event timing of the same steps -> roofline of the dominant kernel
     lib.lf_profile_enable(1)
     for i in range(args.steps):
-        one_step(dev_sets[i % n_sets], i)
+        eager_step(dev_sets[i % n_sets], i)            # per-kernel events need eager launches
     prof = _lib.profile_report()
     lib.lf_profile_enable(0)
 

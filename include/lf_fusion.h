@@ -132,8 +132,9 @@ typedef struct LfQmfArgs {
   const float* conf;     /* (2,Bg) */
   double* correctness;   /* in/out (2,N) History.correctness  existing_algos/QMF.py:13 */
   double* confidence;    /* in/out (2,N) History.confidence   existing_algos/QMF.py:14 */
-  int64_t* last_writer;  /* in/out (N) scratch owned by the History, zero-initialised once */
-  int64_t step_base;     /* strictly increasing by >= Bg per call, starting at 1 */
+  int64_t* last_writer;  /* in/out (N [+1]) scratch owned by the History, zero-initialised once */
+  int64_t step_base;     /* strictly increasing by >= Bg per call, starting at 1; 0 = use the device-resident
+                            counter kept at last_writer[N] (then last_writer has N+1 entries) */
   double* stats;         /* in: global CE sums (LF_STAT_CE_X1/X2); out: LF_STAT_REG_SUM */
   float* qmf_g;          /* out (2,Bg) dL_reg/dconf (already divided by Bg) */
   float* target_out;     /* out (2,Bg) ranking targets in {-1,0,1}, or NULL */
@@ -195,7 +196,7 @@ typedef struct LfMidArgs {
   double* correctness;     /* QMF in/out (2,N) */
   double* confidence;      /* QMF in/out (2,N) */
   int64_t* last_writer;    /* QMF in/out (N) tickets, zero-initialised once */
-  int64_t step_base;       /* QMF: strictly increasing by >= batch_global per call, starting at 1 */
+  int64_t step_base;       /* QMF: as in LfQmfArgs; 0 = device-resident counter at last_writer[N] (graph-replayable) */
   float* qmf_g;            /* QMF out (2, batch_local) dL_reg/dconf of this rank's samples, or NULL (forward only) */
   float* loss_out;         /* out (1) total loss, or NULL */
   void* workspace;         /* QMF: >= lf_mid_workspace_bytes(batch_global) */

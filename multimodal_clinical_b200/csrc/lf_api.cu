@@ -109,7 +109,7 @@ static int narrow_grid(const LfHeadsArgs* a, bool fwd_only) {
   const int S = narrow_tile(a->classes, a->dim, fwd_only);
   int grid = div_up(a->batch, S);
   if (grid > 148) grid = 148;
-  const int rpc = div_up(div_up(a->batch, grid), S) * S;
+  const int rpc = div_up(a->batch, grid);
   return div_up(a->batch, rpc);
 }
 
@@ -242,7 +242,7 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
     d.M = a->batch; d.N = a->classes; d.K = a->dim;
     d.lda = a->dim; d.ldb = a->dim; d.ld_out = a->classes;
     d.a_mn_major = 0; d.b_mn_major = 0; d.block_n = tc_block_n(a->classes);
-    d.splits = 1; d.split_stride = 0; d.name = "tc_logits";
+    d.splits = 1; d.split_stride = 0; d.balance_m = 1; d.name = "tc_logits";
     rc = tc_gemm(d, s);
   } else {
     rc = gemm_logits(g, 2, s);
@@ -293,7 +293,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
       d.M = a->batch; d.N = a->dim; d.K = a->classes;
       d.lda = ldz; d.ldb = a->dim; d.ld_out = a->dim;
       d.a_mn_major = 0; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 32) * 32;
-      d.splits = 1; d.split_stride = 0; d.name = "tc_dfeat";
+      d.splits = 1; d.split_stride = 0; d.balance_m = 0; d.name = "tc_dfeat";
       rc = tc_gemm(d, s);
     } else {
       rc = gemm_dfeat(g, 2, s);
@@ -321,7 +321,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     if (splits > by_rows) splits = by_rows;
     if (splits > kMaxSplits) splits = kMaxSplits;
     if (splits < 1) splits = 1;
-    d.splits = splits; d.split_stride = (long long)cd; d.name = "tc_dweight";
+    d.splits = splits; d.split_stride = (long long)cd; d.balance_m = 0; d.name = "tc_dweight";
     rc = tc_gemm(d, s);
   } else {
     g.splits = splits; g.k_chunk = div_up(a->batch, splits); g.split_stride = cd;

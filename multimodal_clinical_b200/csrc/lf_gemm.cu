@@ -122,9 +122,32 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __re
   out[i] = s;
 }
 
-// both modalities in one launch: blockIdx.y = modality, partials [m][max_splits][n]
-__global__ void reduce_splits2_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1,
-                                      int splits, int max_splits, size_t n) {
+// both modalities in one launch: blockIdx.y = modality, partials [m][max_splits][n].  32 columns x 8 split
+// groups per CTA: group g adds splits g, g+8, ... in order, then the eight group sums are added in order --
+// a fixed summation tree (bit-reproducible) whose dependent-load chains are 8x shorter than one thread
+// walking all splits.
+__global__ void __launch_bounds__(256) reduce_splits2_kernel(const float* __restrict__ part, float* __restrict__ out0,
+                                                             float* __restrict__ out1, int splits, int max_splits, size_t n) {
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const size_t i = (size_t)blockIdx.x * 32 + tx;
+  const float* p = part + (size_t)blockIdx.y * max_splits * n;
+  float s = 0.f;
+  if (i < n)
+    for (int k = ty; k < splits; k += 8) s += p[(size_t)k * n + i];
+  __shared__ float sm[8][33];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += sm[g][tx];
+    (blockIdx.y == 0 ? out0 : out1)[i] = t;
+  }
+}
+
+// few splits: one thread per element walks them (fewer, fatter CTAs)
+__global__ void reduce_splits2_flat_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1,
+                                           int splits, int max_splits, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* p = part + (size_t)blockIdx.y * max_splits * n;
@@ -134,7 +157,11 @@ __global__ void reduce_splits2_kernel(const float* __restrict__ part, float* __r
 }
 
 int reduce_splits2(const float* part, float* out0, float* out1, int splits, int max_splits, size_t n, cudaStream_t s) {
-  LF_LAUNCH("reduce_dweight", s, (reduce_splits2_kernel<<<dim3(div_up((long long)n, 256), 2), 256, 0, s>>>(part, out0, out1, splits, max_splits, n)));
+  if (splits <= 32) {
+    LF_LAUNCH("reduce_dweight", s, (reduce_splits2_flat_kernel<<<dim3(div_up((long long)n, 256), 2), 256, 0, s>>>(part, out0, out1, splits, max_splits, n)));
+    return check_launch("reduce_splits2_flat_kernel");
+  }
+  LF_LAUNCH("reduce_dweight", s, (reduce_splits2_kernel<<<dim3(div_up((long long)n, 32), 2), 256, 0, s>>>(part, out0, out1, splits, max_splits, n)));
   return check_launch("reduce_splits2_kernel");
 }
 

@@ -126,8 +126,10 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
   Gathered g;
   g.idx = a.idx_parts; g.idx_stride = a.idx_stride; g.conf = a.conf_parts; g.conf_stride = a.conf_stride;
   g.Bl = a.batch_local; g.Bg = Bg;
-  const long long base = a.step_base;
   long long* lw = (long long*)a.last_writer;
+  // tickets: host-provided base, or (step_base == 0) the device-resident counter at last_writer[N], which
+  // makes the launch replayable from a CUDA graph
+  const long long base = a.step_base ? a.step_base : lw[N] + 1;
 
   // ---- P1: the last duplicate of an index wins (numpy fancy assignment): ticket = position in the batch
   for (int j = tid; j < Bg; j += nthr) {
@@ -254,6 +256,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     double rs = 0.0;
     for (int b = 0; b < ncta; ++b) rs += (double)p.regpart[b];
     a.stats[LF_STAT_REG_SUM] = rs;
+    if (!a.step_base) lw[N] = base - 1 + Bg;
     if (a.loss_out) {
       const double inv = 1.0 / (double)Bg;
       const float uni = (float)(s_stats[LF_STAT_CE_X1] * inv) + (float)(s_stats[LF_STAT_CE_X2] * inv);
@@ -280,7 +283,7 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
   const bool qmf = a->mode == LF_MODE_QMF;
   if (qmf) {
     if (!a->idx_parts || !a->conf_parts || !a->correctness || !a->confidence || !a->last_writer || !a->workspace ||
-        a->n_data < 1 || a->step_base < 1) { set_error("lf_step_mid: QMF mode needs idx/conf/History/workspace"); return LF_ERR_BAD_ARG; }
+        a->n_data < 1 || a->step_base < 0) { set_error("lf_step_mid: QMF mode needs idx/conf/History/workspace"); return LF_ERR_BAD_ARG; }
     if (a->batch_global < 2) {
       set_error("lf_step_mid: batch_global must be >= 2 (reference raises for a batch of one)");
       return LF_ERR_BAD_ARG;

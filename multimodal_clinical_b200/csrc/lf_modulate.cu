@@ -16,15 +16,27 @@ struct ModTable {
   float* data[LF_MAX_TENSORS];
   long long numel[LF_MAX_TENSORS];
   long long start[LF_MAX_TENSORS];   // first element's position in the encoder-wide noise stream (multiple of 4)
+  int chunk0[LF_MAX_TENSORS + 1];    // work items: tensor t owns chunks [chunk0[t], chunk0[t+1]) of kModChunk elements
 };
+constexpr int kModChunk = 16384;     // elements per work item: 256 threads x 4 rounds x 4 float4
+
+__device__ __forceinline__ int mod_find_tensor(const ModTable& tb, int item) {
+  int lo = 0, hi = tb.count - 1;       // largest t with chunk0[t] <= item
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tb.chunk0[mid] <= item) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: any element's draw is addressable ----------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    const unsigned long long p0 = (unsigned long long)M0 * ctr.x, p1 = (unsigned long long)M1 * ctr.z;   // one IMAD.WIDE each
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
     key.x += W0; key.y += W1;
   }
@@ -48,71 +60,108 @@ __device__ __forceinline__ float4 normal4(unsigned long long group, unsigned lon
   return make_float4(a0 * c0, a0 * s0, a1 * c1, a1 * s1);
 }
 
+// Persistent grid over (tensor, 16K-element chunk) work items: a ResNet18's 20 conv tensors span 3 K .. 2.4 M
+// elements, so one CTA per tensor slice would leave most CTAs nearly empty.  Four independent 128-bit loads in
+// flight per thread (tools/membench.cu: ~64 KB in flight per SM are needed to cover HBM latency).
 __global__ void __launch_bounds__(256) modulate_stats_kernel(ModTable tb, double* __restrict__ ws) {
-  const int t = blockIdx.y;
-  const float* __restrict__ g = tb.data[t];
-  const long long n = tb.numel[t];
-  double s = 0.0, ss = 0.0;
-  const bool vec = ((((uintptr_t)g) & 15) == 0);
-  const long long n4 = vec ? n / 4 : 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);   // keep in L2 for the update pass
-    s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
-    ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
-  }
-  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double v = g[i];
-    s += v; ss += v * v;
-  }
-  s = warp_sum(s); ss = warp_sum(ss);
+  const int total = tb.chunk0[tb.count];
   __shared__ double a[8], b[8];
-  if (threadIdx.x % 32 == 0) { a[threadIdx.x / 32] = s; b[threadIdx.x / 32] = ss; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) { s += a[w]; ss += b[w]; }
-    if (s != 0.0 || ss != 0.0) { atomicAdd(&ws[2 * t], s); atomicAdd(&ws[2 * t + 1], ss); }
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int t = mod_find_tensor(tb, item);
+    const float* __restrict__ g = tb.data[t];
+    const long long n = tb.numel[t];
+    const long long e0 = (long long)(item - tb.chunk0[t]) * kModChunk, e1 = min(n, e0 + kModChunk);
+    double s = 0.0, ss = 0.0;
+    if ((((uintptr_t)g) & 15) == 0) {
+      const float4* g4 = reinterpret_cast<const float4*>(g);
+      const long long q0 = e0 / 4, q1 = e1 / 4;                      // e0 is a multiple of 4
+      for (long long i = q0 + threadIdx.x; i < q1; i += 4 * 256) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (i + u * 256 < q1) ? __ldg(g4 + i + u * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          s += (double)v[u].x + (double)v[u].y + (double)v[u].z + (double)v[u].w;
+          ss += (double)v[u].x * v[u].x + (double)v[u].y * v[u].y + (double)v[u].z * v[u].z + (double)v[u].w * v[u].w;
+        }
+      }
+      for (long long i = q1 * 4 + threadIdx.x; i < e1; i += 256) { const double v = g[i]; s += v; ss += v * v; }
+    } else {
+      for (long long i = e0 + threadIdx.x; i < e1; i += 256) { const double v = g[i]; s += v; ss += v * v; }
+    }
+    s = warp_sum(s); ss = warp_sum(ss);
+    __syncthreads();
+    if (threadIdx.x % 32 == 0) { a[threadIdx.x / 32] = s; b[threadIdx.x / 32] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) { s += a[w]; ss += b[w]; }
+      if (s != 0.0 || ss != 0.0) { atomicAdd(&ws[2 * t], s); atomicAdd(&ws[2 * t + 1], ss); }
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) modulate_apply_kernel(ModTable tb, const double* __restrict__ ws,
                                                              const float* __restrict__ coeff_dev,
                                                              unsigned long long seed, unsigned long long offset) {
-  const int t = blockIdx.y;
-  float* __restrict__ g = tb.data[t];
-  const long long n = tb.numel[t];
+  const int total = tb.chunk0[tb.count];
   const int mode = tb.mode;
   const float k = (mode == LF_MOD_NOISE) ? 1.f : coeff_dev[0];
-  float sigma = 0.f;
-  if (mode != LF_MOD_OGM) {
-    const double mean = ws[2 * t] / (double)n;
-    double var = (ws[2 * t + 1] - (double)n * mean * mean) / (double)(n - 1);   // unbiased (torch.std default)
-    if (var < 0.0) var = 0.0;
-    sigma = (float)((double)(float)sqrt(var) + 1e-8);                            // OGM_GE.py:50
-  }
-  const unsigned long long gbase = (unsigned long long)tb.start[t] / 4;
-  const bool vec = ((((uintptr_t)g) & 15) == 0);
-  const long long n4 = vec ? n / 4 : 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 v = reinterpret_cast<float4*>(g)[i];
-    if (mode == LF_MOD_OGM) {
-      v.x *= k; v.y *= k; v.z *= k; v.w *= k;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int t = mod_find_tensor(tb, item);
+    float* __restrict__ g = tb.data[t];
+    const long long n = tb.numel[t];
+    const long long e0 = (long long)(item - tb.chunk0[t]) * kModChunk, e1 = min(n, e0 + kModChunk);
+    float sigma = 0.f;
+    if (mode != LF_MOD_OGM) {
+      const double mean = ws[2 * t] / (double)n;
+      double var = (ws[2 * t + 1] - (double)n * mean * mean) / (double)(n - 1);   // unbiased (torch.std default)
+      if (var < 0.0) var = 0.0;
+      sigma = (float)((double)(float)sqrt(var) + 1e-8);                            // OGM_GE.py:50
+    }
+    const unsigned long long gbase = (unsigned long long)tb.start[t] / 4;
+    if ((((uintptr_t)g) & 15) == 0) {
+      float4* g4 = reinterpret_cast<float4*>(g);
+      const long long q0 = e0 / 4, q1 = e1 / 4;
+      for (long long i0 = q0 + threadIdx.x; i0 < q1; i0 += 4 * 256) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (i0 + u * 256 < q1) v[u] = g4[i0 + u * 256];      // loads first, all in flight
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long i = i0 + u * 256;
+          if (i >= q1) break;
+          if (mode == LF_MOD_OGM) {
+            v[u].x *= k; v[u].y *= k; v[u].z *= k; v[u].w *= k;
+          } else {
+            const float4 z = normal4(gbase + (unsigned long long)i, seed, offset);
+            v[u].x = v[u].x * k + z.x * sigma; v[u].y = v[u].y * k + z.y * sigma;
+            v[u].z = v[u].z * k + z.z * sigma; v[u].w = v[u].w * k + z.w * sigma;
+          }
+          g4[i] = v[u];
+        }
+      }
+      for (long long i = q1 * 4 + threadIdx.x; i < e1; i += 256) {     // scalar tail: lanes pick their Philox component
+        float v = g[i];
+        if (mode == LF_MOD_OGM) v *= k;
+        else {
+          const float4 z = normal4(gbase + (unsigned long long)(i / 4), seed, offset);
+          const int r = (int)(i & 3);
+          v = v * k + (r == 0 ? z.x : r == 1 ? z.y : r == 2 ? z.z : z.w) * sigma;
+        }
+        g[i] = v;
+      }
     } else {
-      const float4 z = normal4(gbase + (unsigned long long)i, seed, offset);
-      v.x = v.x * k + z.x * sigma; v.y = v.y * k + z.y * sigma;
-      v.z = v.z * k + z.z * sigma; v.w = v.w * k + z.w * sigma;
+      for (long long i = e0 + threadIdx.x; i < e1; i += 256) {
+        float v = g[i];
+        if (mode == LF_MOD_OGM) v *= k;
+        else {
+          const float4 z = normal4(gbase + (unsigned long long)(i / 4), seed, offset);
+          const int r = (int)(i & 3);
+          v = v * k + (r == 0 ? z.x : r == 1 ? z.y : r == 2 ? z.z : z.w) * sigma;
+        }
+        g[i] = v;
+      }
     }
-    reinterpret_cast<float4*>(g)[i] = v;
-  }
-  // scalar tail / unaligned tensors: one Philox call per group of 4, lanes pick their component
-  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float v = g[i];
-    if (mode == LF_MOD_OGM) v *= k;
-    else {
-      const float4 z = normal4(gbase + (unsigned long long)(i / 4), seed, offset);
-      const int r = (int)(i & 3);
-      v = v * k + (r == 0 ? z.x : r == 1 ? z.y : r == 2 ? z.z : z.w) * sigma;
-    }
-    g[i] = v;
   }
 }
 
@@ -132,17 +181,18 @@ extern "C" int lf_ogm_modulate(const LfTensorList* list, const float* coeff_dev,
   cudaStream_t s = (cudaStream_t)stream;
   ModTable tb;
   tb.count = list->count; tb.mode = mode;
-  long long pos = 0, maxn = 0;
+  long long pos = 0;
+  int chunks = 0;
   for (int i = 0; i < list->count; ++i) {
     if (!list->data[i] || list->numel[i] < 0) { set_error("lf_ogm_modulate: bad tensor %d", i); return LF_ERR_BAD_ARG; }
     tb.data[i] = list->data[i]; tb.numel[i] = list->numel[i]; tb.start[i] = pos;
     pos += (list->numel[i] + 3) / 4 * 4;
-    if (list->numel[i] > maxn) maxn = list->numel[i];
+    tb.chunk0[i] = chunks;
+    chunks += div_up(list->numel[i], kModChunk);
   }
-  int gx = div_up(maxn, 256 * 4 * 4);
-  if (gx < 1) gx = 1;
-  if (gx > 296) gx = 296;
-  dim3 grid(gx, list->count);
+  tb.chunk0[list->count] = chunks;
+  if (chunks == 0) return LF_OK;
+  const int grid = chunks < 148 * 8 ? chunks : 148 * 8;
   if (mode != LF_MOD_OGM) {
     cudaMemsetAsync(workspace, 0, lf_modulate_workspace_bytes(), s);
     LF_LAUNCH("modulate_stats", s, (modulate_stats_kernel<<<grid, 256, 0, s>>>(tb, (double*)workspace)));

@@ -26,12 +26,11 @@
 namespace lf {
 
 constexpr int PASS_BOTH = 0, PASS_FWD = 1, PASS_BWD = 2;
-constexpr int NARROW_THREADS = 256;
 constexpr int kNarrowMaxCtas = 148;
 
 struct NarrowParams {
   int B, Bg, D, C, S;            // S = samples per tile (<= 16)
-  int rows_per_cta;              // multiple of S
+  int rows_per_cta;
   int need_dfeat;
   int ldz;
   const float* feat[2];
@@ -84,7 +83,9 @@ __device__ __forceinline__ float transpose_reduce(float (&v)[CMAX], int lane) {
   return v[0];
 }
 
-template <int MODE, int PASS, int CMAX, int KV>
+// NARROW_THREADS: 512 for the small-class variants (one sample per warp and one dW column per thread per tile
+// at D = 512; twice the warps to hide latency), 256 where the register budget of the wide variants needs it.
+template <int MODE, int PASS, int CMAX, int KV, int NARROW_THREADS>
 __global__ void __launch_bounds__(NARROW_THREADS, 1) narrow_kernel(NarrowParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int C = p.C, D = p.D, S = p.S;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) narrow_kernel(NarrowParams 
   float* dWs = Ws + 2 * cd;                                       // [2][C][D]   (PASS != FWD)
   float* tiles = dWs + (PASS == PASS_FWD ? 0 : 2 * cd);           // [2 bufs][2 mods][S][D]
   float* dzs = tiles + (size_t)4 * S * D;                         // [S][2][CMAX]
-  float* red = dzs + (size_t)S * 2 * CMAX;                        // [8 warps][3*CMAX + 12] end-of-kernel reduction
+  float* red = dzs + (size_t)S * 2 * CMAX;                        // [16 warps][3*CMAX + 12] end-of-kernel reduction
   uint64_t* bars = (uint64_t*)(red + nwarp * (3 * CMAX + 12));    // [2]
 
   const int r_begin = blockIdx.x * p.rows_per_cta;
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) narrow_kernel(NarrowParams 
 // ---------------------------------------------------------------------------------- host side
 static size_t narrow_smem(int C, int D, int S, int cmax, bool fwd_only) {
   const size_t cd = (size_t)C * D;
-  return sizeof(float) * ((fwd_only ? 2 : 4) * cd + (size_t)4 * S * D + (size_t)S * 2 * cmax + 8 * (3 * cmax + 12)) + 64;
+  return sizeof(float) * ((fwd_only ? 2 : 4) * cd + (size_t)4 * S * D + (size_t)S * 2 * cmax + 16 * (3 * cmax + 12)) + 64;
 }
 
 // Largest tile (<= 16 samples) that fits next to the resident weights; 0 = shape not supported here.
@@ -390,8 +391,9 @@ static int narrow_launch(const NarrowParams& p, int grid, size_t smem, cudaStrea
 #define LF_NARROW_GO(CM, KVV)                                                                                     \
   do {                                                                                                            \
     static bool attr = false;                                                                                     \
-    if (!attr) { cudaFuncSetAttribute(narrow_kernel<MODE, PASS, CM, KVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; } \
-    LF_LAUNCH(name, s, (narrow_kernel<MODE, PASS, CM, KVV><<<grid, NARROW_THREADS, smem, s>>>(p)));               \
+    constexpr int NT = (CM <= 16 && KVV == 4) ? 512 : 256;                                                       \
+    if (!attr) { cudaFuncSetAttribute(narrow_kernel<MODE, PASS, CM, KVV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; } \
+    LF_LAUNCH(name, s, (narrow_kernel<MODE, PASS, CM, KVV, NT><<<grid, NT, smem, s>>>(p)));                       \
     return check_launch(name);                                                                                    \
   } while (0)
   if (p.C <= 8) { if (kv == 4) LF_NARROW_GO(8, 4); else LF_NARROW_GO(8, 8); }
@@ -410,7 +412,7 @@ int narrow_run(const LfHeadsArgs* a, int pass, float* partials, float* dbpart, f
   if (p.S == 0) { set_error("narrow heads: shape C=%d D=%d not supported", a->classes, a->dim); return LF_ERR_UNSUPPORTED; }
   int grid = div_up(a->batch, p.S);
   if (grid > kNarrowMaxCtas) grid = kNarrowMaxCtas;
-  p.rows_per_cta = div_up(div_up(a->batch, grid), p.S) * p.S;
+  p.rows_per_cta = div_up(a->batch, grid);          // any row count: the last tile of a range is partial
   grid = div_up(a->batch, p.rows_per_cta);
   p.need_dfeat = a->need_dfeat;
   p.ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;

@@ -23,10 +23,13 @@ struct QmfWs {
   float* regpart;   // [kRegBlocks]
 };
 
+__global__ void qmf_bump_kernel(long long* counter, int Bg) { *counter += Bg; }
+
 __global__ void qmf_mark_kernel(const int64_t* __restrict__ idx, int Bg, int N, long long base,
                                 long long* __restrict__ last_writer) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Bg) return;
+  if (base == 0) base = last_writer[N] + 1;           // device-resident ticket counter
   const int64_t i = idx[j];
   if ((unsigned long long)i < (unsigned long long)N) atomicMax(&last_writer[i], base + j);
 }
@@ -38,6 +41,7 @@ __global__ void qmf_update_kernel(const int64_t* __restrict__ idx, const float* 
                                   const float* __restrict__ loss1) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Bg) return;
+  if (base == 0) base = last_writer[N] + 1;
   const int64_t i = idx[j];
   if ((unsigned long long)i >= (unsigned long long)N) return;   // out-of-range index: ignored (numpy would raise)
   if (last_writer[i] != base + j) return;
@@ -203,7 +207,7 @@ extern "C" int lf_qmf_history_step(const LfQmfArgs* a, void* stream) {
     set_error("lf_qmf_history_step: batch_global must be >= 2 (reference raises for a batch of one)");
     return LF_ERR_BAD_ARG;
   }
-  if (a->n_data < 1 || a->step_base < 1 || a->g_begin < 0 || a->g_count < 0 ||
+  if (a->n_data < 1 || a->step_base < 0 || a->g_begin < 0 || a->g_count < 0 ||
       a->g_begin + a->g_count > a->batch_global) { set_error("lf_qmf_history_step: bad sizes"); return LF_ERR_BAD_ARG; }
   if (a->workspace_bytes < lf_qmf_workspace_bytes(a->n_data)) { set_error("lf_qmf_history_step: workspace too small"); return LF_ERR_WORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
@@ -217,6 +221,7 @@ extern "C" int lf_qmf_history_step(const LfQmfArgs* a, void* stream) {
     LF_LAUNCH("qmf_update", s, (qmf_update_kernel<<<nb, 256, 0, s>>>(a->idx, a->conf, Bg, N, (long long)a->step_base,
                                         (const long long*)a->last_writer, a->stats, a->correctness, a->confidence,
                                         a->flags, a->loss_uni[0], a->loss_uni[1])));
+    if (a->step_base == 0) LF_LAUNCH("qmf_bump", s, (qmf_bump_kernel<<<1, 1, 0, s>>>((long long*)a->last_writer + N, Bg)));
   }
   if (!(a->flags & LF_QMF_REG)) return check_launch("lf_qmf_history_step");
   LF_LAUNCH("qmf_minmax", s, (qmf_minmax_kernel<<<dim3(kMinMaxBlocks, 2), 256, 0, s>>>(a->correctness, N, ws.minmax)));

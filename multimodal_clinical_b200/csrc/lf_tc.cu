@@ -50,7 +50,7 @@ __device__ __forceinline__ Item decode_item(const TcGemmParams& p, int item) {
   const int n_t = item % p.n_tiles; int r = item / p.n_tiles;
   const int m_t = r % p.m_tiles; r /= p.m_tiles;
   it.split = r % p.splits; it.batch = r / p.splits;
-  it.m0 = m_t * TC_BLOCK_M; it.n0 = n_t * p.block_n;
+  it.m0 = m_t * p.tile_m; it.n0 = n_t * p.block_n;
   it.k_begin = it.split * p.k_per_split;
   it.k_end = min(p.K, it.k_begin + p.k_per_split);
   it.num_kb = it.k_end > it.k_begin ? (it.k_end - it.k_begin + TC_BLOCK_K - 1) / TC_BLOCK_K : 0;
@@ -103,7 +103,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+          mbar_expect_tx(&full_bar[s], (p.a_mn_major ? a_bytes : (uint32_t)p.tile_m * TC_BLOCK_K * 4) + b_bytes);
           const int k0 = w.k_begin + kb * TC_BLOCK_K;
           if (!p.a_mn_major) {
             tma_load_2d(mapA, &full_bar[s], sa, k0, w.m0);                      // [32 k x 128 rows]
@@ -213,7 +213,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const int col = w.n0 + c0 + lane;
           const bool col_ok = (c0 + lane < p.block_n) && col < p.N;
           const float bv = (bias && col_ok) ? bias[col] : 0.f;
-          const int nrows = min(32, p.M - row0);
+          const int nrows = max(0, min(min(32, p.tile_m - q * 32), p.M - row0));
 #pragma unroll 4
           for (int r = 0; r < nrows; ++r)
             if (col_ok) out[(size_t)(row0 + r) * p.ld_out + col] = tile[r * 33 + lane] + bv;
@@ -307,8 +307,19 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   p.tma_store = aligned ? 1 : 0;
   p.acc_cols = d.block_n <= 32 ? 32 : d.block_n <= 64 ? 64 : d.block_n <= 128 ? 128 : 256;
   p.tmem_cols = 2 * p.acc_cols;
-  p.m_tiles = div_up(d.M, TC_BLOCK_M);
+  p.tile_m = TC_BLOCK_M;
   p.n_tiles = div_up(d.N, d.block_n);
+  if (d.balance_m && !d.a_mn_major && !p.tma_store) {
+    // smallest number of M tiles >= ceil(M/128) that makes items a multiple of 148, if it costs < 15% extra tiles
+    const int per_m = p.n_tiles * p.splits * d.nbatch;
+    const int base = div_up(d.M, TC_BLOCK_M);
+    for (int mt = base; mt <= base + base / 6 + 1; ++mt)
+      if ((mt * per_m) % 148 == 0 || (mt * per_m) % 148 > 140) {
+        const int tm = div_up(div_up(d.M, mt), 8) * 8;
+        if (tm <= TC_BLOCK_M && tm >= 64) { p.tile_m = tm; break; }
+      }
+  }
+  p.m_tiles = div_up(d.M, p.tile_m);
   p.total_items = p.m_tiles * p.n_tiles * p.splits * d.nbatch;
 
   CUtensorMap mA[2], mB[2], mO[2];
@@ -316,7 +327,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
     int rc;
     // K-major: inner = K, outer = MN rows, box [32 x rows].  MN-major: inner = MN, outer = K rows, box [32 x 32].
     rc = d.a_mn_major ? make_map(&mA[b], d.A[b], d.M, d.K, d.lda, 32, TC_BLOCK_K, true)
-                      : make_map(&mA[b], d.A[b], d.K, d.M, d.lda, TC_BLOCK_K, TC_BLOCK_M, false);
+                      : make_map(&mA[b], d.A[b], d.K, d.M, d.lda, TC_BLOCK_K, p.tile_m, false);
     if (rc) return rc;
     rc = d.b_mn_major ? make_map(&mB[b], d.B[b], d.N, d.K, d.ldb, 32, TC_BLOCK_K, true)
                       : make_map(&mB[b], d.B[b], d.K, d.N, d.ldb, TC_BLOCK_K, d.block_n, false);
@@ -362,6 +373,6 @@ extern "C" int lf_debug_tc_gemm(const float* A, const float* B, const float* bia
   d.A[1] = A; d.B[1] = B; d.bias[1] = bias; d.out[1] = out;
   d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ld_out = ld_out;
   d.a_mn_major = a_mn_major; d.b_mn_major = b_mn_major; d.block_n = block_n;
-  d.splits = splits; d.split_stride = split_stride; d.name = "tc_gemm_debug";
+  d.splits = splits; d.split_stride = split_stride; d.balance_m = 0; d.name = "tc_gemm_debug";
   return lf::tc_gemm(d, (cudaStream_t)stream);
 }

@@ -16,6 +16,7 @@ struct TcGemmParams {
   int tmem_cols;           // 2 * acc_cols (double-buffered)
   int a_mn_major, b_mn_major;
   int tma_store;           // epilogue writes through cp.async.bulk.tensor (needs a 16-byte output pitch)
+  int tile_m;              // rows per M tile (<= 128): A box rows; smaller tiles balance the item count over the SMs
   int m_tiles, n_tiles, total_items;
   float* out[2];
   const float* bias[2];
@@ -40,6 +41,7 @@ struct TcGemmDesc {
   int block_n;
   int splits;
   long long split_stride;
+  int balance_m;           // 1: pick tile_m so that the number of work items is a multiple of the SM count (K-major A, plain-store epilogue only)
   const char* name;
 };
 

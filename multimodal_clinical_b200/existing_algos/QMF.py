@@ -36,7 +36,6 @@ class _QmfState:
         self.n_data = int(n_data)
         self.device: Optional[torch.device] = None
         self.correctness = self.confidence = self.last_writer = self.ws = self.stats = None
-        self.step_base = 1
 
     def to(self, device) -> "_QmfState":
         device = torch.device(device)
@@ -50,7 +49,7 @@ class _QmfState:
         else:
             self.correctness = torch.zeros(2, self.n_data, dtype=torch.float64, device=device)   # QMF.py:13
             self.confidence = torch.zeros(2, self.n_data, dtype=torch.float64, device=device)    # QMF.py:14
-        self.last_writer = torch.zeros(self.n_data, dtype=torch.int64, device=device)
+        self.last_writer = torch.zeros(self.n_data + 1, dtype=torch.int64, device=device)   # [N] = ticket counter
         self.ws = torch.empty(lib.lf_qmf_workspace_bytes(self.n_data), dtype=torch.uint8, device=device)
         self.mid_ws = None
         self.stats = torch.zeros(_lib.LF_STATS_HEADER, dtype=torch.float64, device=device)
@@ -71,7 +70,7 @@ class _QmfState:
         q.batch_global, q.n_data = Bg, self.n_data
         q.idx, q.conf = idx.data_ptr(), conf.data_ptr()
         q.correctness, q.confidence = self.correctness.data_ptr(), self.confidence.data_ptr()
-        q.last_writer, q.step_base = self.last_writer.data_ptr(), self.step_base
+        q.last_writer, q.step_base = self.last_writer.data_ptr(), 0      # device-resident ticket counter
         stats = self.stats if stats is None else stats
         q.stats = stats.data_ptr()
         q.qmf_g = qmf_g.data_ptr() if qmf_g is not None else None
@@ -82,7 +81,6 @@ class _QmfState:
         for m in range(2):
             q.loss_uni[m] = loss_uni[m].data_ptr() if loss_uni[m] is not None else None
         check(_lib.load().lf_qmf_history_step(C.byref(q), _stream()), "lf_qmf_history_step")
-        self.step_base += Bg
         return stats
 
 

@@ -247,11 +247,10 @@ class LateFusionStep:
             mid.idx_parts, mid.idx_stride = base + self._off_idx, stride // 8
             mid.conf_parts, mid.conf_stride = base + self._off_conf, stride // 4
             mid.correctness, mid.confidence = _ptr(qs.correctness), _ptr(qs.confidence)
-            mid.last_writer, mid.step_base = _ptr(qs.last_writer), qs.step_base
+            mid.last_writer, mid.step_base = _ptr(qs.last_writer), 0      # device-resident ticket counter
             mid.qmf_g = _ptr(bufs["qmf_g"]) if backward else None
             mws = qs.mid_workspace(Bg)
             mid.workspace, mid.workspace_bytes = _ptr(mws), mws.numel()
-            qs.step_base += Bg
         mid.stats = _ptr(self.stats)
         mid.ema_x, mid.ema_offset, mid.smoothing = _ptr(self.ema_x), _ptr(self.ema_offset), self.smoothing
         if ogm_alpha is not None:
@@ -274,6 +273,32 @@ class LateFusionStep:
             conf=bufs["conf"], loss=self.loss[0],
             dfeat=[bufs["dfeat"][0], bufs["dfeat"][1]] if (need_dfeat and backward) else [None, None],
             dweight=dW, dbias=db, stats=self.stats, batch_global=Bg)
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, feats, weights, biases, label, idx=None, extra=None, warmup: int = 2, **kw):
+        """Capture one step (plus ``extra()``, e.g. the OGM-GE modulation calls) reading the GIVEN tensors into a
+        CUDA graph.  ``graph.replay()`` then re-runs the step on whatever those tensors hold at that time; the
+        returned StepOutput aliases the engine's static buffers.  All device state the step mutates (EMA,
+        History, ticket counter) lives in device memory, so replays advance it exactly like eager calls.
+        The ``warmup`` eager steps needed before capture also advance that state."""
+        if self.fresh_outputs:
+            raise _lib.LfError("capture() needs static buffers (fresh_outputs=False)")
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                out = self.step(feats, weights, biases, label, idx=idx, **kw)
+                if extra is not None:
+                    extra()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.step(feats, weights, biases, label, idx=idx, **kw)
+            if extra is not None:
+                extra()
+        return graph, out
 
     # ------------------------------------------------------------------ OGM-GE modulation
     def modulate(self, grads: Sequence[torch.Tensor], which: int, modulation: str, seed: int, offset: int) -> None:
