@@ -93,6 +93,10 @@ def kernel_alg_bytes(name, w, B):
         "rows_calibrated": 2 * B * C * f + 8 * B,
         "sgemm_dfeat": dfeat, "tc_dfeat": dfeat,
         "sgemm_dweight": dweight, "tc_dweight": dweight,
+        "narrow_step_jlogits": (2 * B * D + (2 * B * D if w["dfeat"] else 0) + 3 * B * C + B * ldz) * f + 8 * B,
+        "narrow_forward_qmf": (2 * B * D + 4 * B * C + 6 * B) * f + 8 * B,
+        "narrow_backward_qmf": (2 * B * D + (2 * B * D if w["dfeat"] else 0) + 2 * B * C + 2 * B * ldz + 8 * B) * f + 8 * B,
+        "step_mid": 16 * B + 16 * (w["N"] or 0),
         "modulate_stats": 11_160_000 * f,
         "modulate_apply": 2 * 11_160_000 * f,
     }
@@ -262,7 +266,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="k4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32"],
+                    help="auto: tf32 tensor pipe for wide heads (C >= 32), exact fp32 FMA for narrow heads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--batch", type=int, default=None, help="override the workload's per-GPU batch (experiments)")
@@ -271,6 +276,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = dict(WORKLOADS[args.workload])
+    if args.precision == "auto":
+        args.precision = "tf32" if (args.classes or w["C"]) >= 32 else "fp32"
     if args.batch or args.dim or args.classes:
         w.update(B=args.batch or w["B"], D=args.dim or w["D"], C=args.classes or w["C"])
         w["desc"] += f" [overridden: B={w['B']} D={w['D']} C={w['C']}]"
@@ -453,8 +460,13 @@ def main():
             line["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # captured graphs hold NCCL work: drop them and drain the device before leaving; skip
+        # destroy_process_group (it can block on communicators referenced by graphs) and exit directly
+        graphs.clear()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -42,15 +42,17 @@ def test_struct_layout_matches_c(tmp_path):
     from multimodal_clinical_b200 import _lib
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lf_fusion.h"\nint main(){'
-                    'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(LfHeadsArgs), offsetof(LfHeadsArgs, feat),'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(LfHeadsArgs), offsetof(LfHeadsArgs, feat),'
                     'offsetof(LfHeadsArgs, stats), sizeof(LfQmfArgs), offsetof(LfQmfArgs, step_base),'
-                    'offsetof(LfQmfArgs, workspace), sizeof(LfTensorList)); return 0;}')
+                    'offsetof(LfQmfArgs, workspace), sizeof(LfTensorList), sizeof(LfMidArgs), offsetof(LfMidArgs, stats),'
+                    'offsetof(LfMidArgs, step_base), offsetof(LfHeadsArgs, fwd_only)); return 0;}')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(_lib.LfHeadsArgs), _lib.LfHeadsArgs.feat.offset, _lib.LfHeadsArgs.stats.offset,
             C.sizeof(_lib.LfQmfArgs), _lib.LfQmfArgs.step_base.offset, _lib.LfQmfArgs.workspace.offset,
-            C.sizeof(_lib.LfTensorList)]
+            C.sizeof(_lib.LfTensorList), C.sizeof(_lib.LfMidArgs), _lib.LfMidArgs.stats.offset,
+            _lib.LfMidArgs.step_base.offset, _lib.LfHeadsArgs.fwd_only.offset]
     assert got == want
 
 
