@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 3
+#define LF_ABI_VERSION 4
 
 /* error codes */
 #define LF_OK 0
@@ -164,6 +164,40 @@ size_t lf_qmf_workspace_bytes(int32_t n_data);
 int lf_qmf_history_step(const LfQmfArgs* args, void* stream);
 
 /*
+ * Peer-memory communicator for the batch-sharded step (lf_peer.cu): one process per GPU, every rank's
+ * symmetric buffer (lf_comm_alloc) is mapped into every peer through CUDA IPC over NVLink / NVSwitch.
+ * All pointers below are device pointers valid on THIS rank; index r addresses rank r's buffer.
+ */
+#define LF_MAX_RANKS 8
+typedef struct LfPeerComm {
+  int32_t n_ranks;
+  int32_t rank;
+  void* flags[LF_MAX_RANKS];        /* rank r's flag array: 2 sets x LF_MAX_RANKS int64 (set 0 payload, set 1 gradients) */
+  void* recv_payload[LF_MAX_RANKS]; /* rank r's payload receive area: [2 parities][n_ranks][payload bytes] */
+  void* recv_grad[LF_MAX_RANKS];    /* rank r's gradient receive area: [2 parities][n_ranks][n_padded floats] */
+  int64_t* epoch;                   /* local, device-resident: epoch[0] payload exchanges done, epoch[1] gradient exchanges */
+  int32_t* error;                   /* local: set to 1 when a peer did not arrive within ~2 s */
+} LfPeerComm;
+
+typedef struct LfPeerReduceArgs {
+  LfPeerComm comm;
+  float* buf;          /* in: this rank's n floats; out: the sum over ranks (rank order, identical on every rank) */
+  int32_t n;
+  int32_t n_padded;    /* slot size in floats, multiple of 4, >= n */
+  double* tail_dst;    /* optional: the last tail_n sums are also written here as doubles (calibrated counts) */
+  int32_t tail_n;
+  int32_t reserved;
+} LfPeerReduceArgs;
+
+int lf_comm_alloc(size_t bytes, void** ptr);                 /* cudaMalloc + zero fill (host call) */
+int lf_comm_free(void* ptr);
+int lf_comm_ipc_handle(void* ptr, void* handle64);           /* 64-byte CUDA IPC handle of an lf_comm_alloc buffer */
+int lf_comm_ipc_open(const void* handle64, void** ptr);      /* map a peer's buffer (enables peer access lazily) */
+int lf_comm_ipc_close(void* ptr);
+/* One-shot all-reduce(sum) of the packed head gradients [dW1|db1|dW2|db2|calibrated counts] over peer memory. */
+int lf_peer_allreduce(const LfPeerReduceArgs* args, void* stream);
+
+/*
  * The middle of the step in ONE launch (lf_mid.cu): sums the per-rank partial statistics in rank order,
  * updates the EMA (utils/EMA.py:29-38), computes the OGM-GE coefficients (existing_algos/OGM_GE.py:24-40),
  * and -- QMF -- runs History.correctness_update, the global min/max, the ranking targets, the ranking
@@ -201,6 +235,17 @@ typedef struct LfMidArgs {
   float* loss_out;         /* out (1) total loss, or NULL */
   void* workspace;         /* QMF: >= lf_mid_workspace_bytes(batch_global) */
   size_t workspace_bytes;
+  /* optional fused exchange: when use_peer != 0 the kernel first pushes this rank's payload (payload_bytes,
+     multiple of 16, laid out [stats | idx | conf] like the gathered buffer) into every peer's receive area and
+     waits for all peers, then consumes the LOCAL receive area; stats_parts / idx_parts / conf_parts are
+     ignored (their byte offsets inside the payload are off_idx / off_conf). */
+  int32_t use_peer;
+  int32_t reserved;
+  const void* payload_local;
+  int64_t payload_bytes;
+  int64_t off_idx;
+  int64_t off_conf;
+  LfPeerComm comm;
 } LfMidArgs;
 
 size_t lf_mid_workspace_bytes(int32_t batch_global);

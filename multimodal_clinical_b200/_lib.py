@@ -46,6 +46,20 @@ class LfQmfArgs(C.Structure):
     ]
 
 
+LF_MAX_RANKS = 8
+_P8 = C.c_void_p * LF_MAX_RANKS
+
+
+class LfPeerComm(C.Structure):
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("flags", _P8), ("recv_payload", _P8), ("recv_grad", _P8),
+                ("epoch", C.c_void_p), ("error", C.c_void_p)]
+
+
+class LfPeerReduceArgs(C.Structure):
+    _fields_ = [("comm", LfPeerComm), ("buf", C.c_void_p), ("n", C.c_int32), ("n_padded", C.c_int32),
+                ("tail_dst", C.c_void_p), ("tail_n", C.c_int32), ("reserved", C.c_int32)]
+
+
 class LfMidArgs(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("classes", C.c_int32), ("batch_global", C.c_int32), ("n_ranks", C.c_int32),
@@ -55,6 +69,8 @@ class LfMidArgs(C.Structure):
         ("ema_offset", C.c_void_p), ("smoothing", C.c_float), ("alpha", C.c_float), ("coeff_out", C.c_void_p),
         ("correctness", C.c_void_p), ("confidence", C.c_void_p), ("last_writer", C.c_void_p), ("step_base", C.c_int64),
         ("qmf_g", C.c_void_p), ("loss_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("use_peer", C.c_int32), ("reserved", C.c_int32), ("payload_local", C.c_void_p), ("payload_bytes", C.c_int64),
+        ("off_idx", C.c_int64), ("off_conf", C.c_int64), ("comm", LfPeerComm),
     ]
 
 
@@ -76,6 +92,12 @@ SIGNATURES = {
     "lf_ogm_coeff": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "lf_qmf_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "lf_qmf_history_step": (C.c_int, [C.POINTER(LfQmfArgs), C.c_void_p]),
+    "lf_comm_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "lf_comm_free": (C.c_int, [C.c_void_p]),
+    "lf_comm_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lf_comm_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "lf_comm_ipc_close": (C.c_int, [C.c_void_p]),
+    "lf_peer_allreduce": (C.c_int, [C.POINTER(LfPeerReduceArgs), C.c_void_p]),
     "lf_mid_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "lf_step_mid": (C.c_int, [C.POINTER(LfMidArgs), C.c_void_p]),
     "lf_modulate_workspace_bytes": (C.c_size_t, []),

@@ -16,6 +16,7 @@
 //   P3 min/max over all N                  P4 ranking terms, dL/dconf          P5 loss
 #include <cooperative_groups.h>
 #include "lf_common.cuh"
+#include "lf_peer.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -81,10 +82,28 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
   extern __shared__ double s_stats[];                 // [len] global statistics (each CTA keeps a copy)
   __shared__ MidShared sh;
 
+  // ---- exchange (sharded runs): push this rank's [stats | idx | conf] to every peer, wait for all peers,
+  // then read the local receive area, which has the same rank-major layout an all-gather would produce
+  const double* stats_parts = a.stats_parts;
+  long long stats_stride = a.stats_stride;
+  const int64_t* idx_parts = a.idx_parts; long long idx_stride = a.idx_stride;
+  const float* conf_parts = a.conf_parts; long long conf_stride = a.conf_stride;
+  long long epoch = 0;
+  if (a.use_peer) {
+    epoch = a.comm.epoch[0] + 1;
+    const int parity = (int)(epoch & 1);
+    peer_push(a.comm, a.comm.recv_payload, a.payload_local, (size_t)a.payload_bytes, parity, tid, nthr);
+    peer_barrier(a.comm, 0, epoch, cluster);
+    const char* base = (const char*)a.comm.recv_payload[a.comm.rank] + (size_t)parity * a.n_ranks * a.payload_bytes;
+    stats_parts = (const double*)base; stats_stride = a.payload_bytes / 8;
+    idx_parts = (const int64_t*)(base + a.off_idx); idx_stride = a.payload_bytes / 8;
+    conf_parts = (const float*)(base + a.off_conf); conf_stride = a.payload_bytes / 4;
+  }
+
   // ---- P0: global statistics in rank order
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
     double s = 0.0;
-    for (int r = 0; r < a.n_ranks; ++r) s += a.stats_parts[(size_t)r * a.stats_stride + i];
+    for (int r = 0; r < a.n_ranks; ++r) s += stats_parts[(size_t)r * stats_stride + i];
     s_stats[i] = s;
   }
   __syncthreads();
@@ -119,12 +138,15 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
   __syncthreads();
 
   if (a.mode != LF_MODE_QMF) {
-    if (cta == 0 && threadIdx.x == 0 && a.loss_out) a.loss_out[0] = (float)(s_stats[LF_STAT_CE_JOINT] / (double)Bg);
+    if (cta == 0 && threadIdx.x == 0) {
+      if (a.loss_out) a.loss_out[0] = (float)(s_stats[LF_STAT_CE_JOINT] / (double)Bg);
+      if (a.use_peer) a.comm.epoch[0] = epoch;
+    }
     return;
   }
 
   Gathered g;
-  g.idx = a.idx_parts; g.idx_stride = a.idx_stride; g.conf = a.conf_parts; g.conf_stride = a.conf_stride;
+  g.idx = idx_parts; g.idx_stride = idx_stride; g.conf = conf_parts; g.conf_stride = conf_stride;
   g.Bl = a.batch_local; g.Bg = Bg;
   long long* lw = (long long*)a.last_writer;
   // tickets: host-provided base, or (step_base == 0) the device-resident counter at last_writer[N], which
@@ -257,6 +279,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     for (int b = 0; b < ncta; ++b) rs += (double)p.regpart[b];
     a.stats[LF_STAT_REG_SUM] = rs;
     if (!a.step_base) lw[N] = base - 1 + Bg;
+    if (a.use_peer) a.comm.epoch[0] = epoch;
     if (a.loss_out) {
       const double inv = 1.0 / (double)Bg;
       const float uni = (float)(s_stats[LF_STAT_CE_X1] * inv) + (float)(s_stats[LF_STAT_CE_X2] * inv);
@@ -274,7 +297,12 @@ extern "C" size_t lf_mid_workspace_bytes(int32_t batch_global) {
 }
 
 extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
-  if (!a || !a->stats_parts || !a->stats || a->classes < 1 || a->batch_global < 1 || a->n_ranks < 1 ||
+  if (a && a->use_peer && (!a->payload_local || a->payload_bytes < 16 || a->payload_bytes % 16 || !a->comm.epoch || !a->comm.error ||
+                           a->comm.n_ranks != a->n_ranks || a->comm.rank != a->rank)) {
+    set_error("lf_step_mid: bad peer-exchange arguments");
+    return LF_ERR_BAD_ARG;
+  }
+  if (!a || (!a->stats_parts && !a->use_peer) || !a->stats || a->classes < 1 || a->batch_global < 1 || a->n_ranks < 1 ||
       a->batch_local < 1 || a->batch_local * a->n_ranks != a->batch_global || a->rank < 0 || a->rank >= a->n_ranks) {
     set_error("lf_step_mid: bad argument");
     return LF_ERR_BAD_ARG;
@@ -282,7 +310,7 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
   if (a->update_ema && (!a->ema_x || !a->ema_offset)) { set_error("lf_step_mid: update_ema needs ema_x / ema_offset"); return LF_ERR_BAD_ARG; }
   const bool qmf = a->mode == LF_MODE_QMF;
   if (qmf) {
-    if (!a->idx_parts || !a->conf_parts || !a->correctness || !a->confidence || !a->last_writer || !a->workspace ||
+    if ((!a->use_peer && (!a->idx_parts || !a->conf_parts)) || !a->correctness || !a->confidence || !a->last_writer || !a->workspace ||
         a->n_data < 1 || a->step_base < 0) { set_error("lf_step_mid: QMF mode needs idx/conf/History/workspace"); return LF_ERR_BAD_ARG; }
     if (a->batch_global < 2) {
       set_error("lf_step_mid: batch_global must be >= 2 (reference raises for a batch of one)");

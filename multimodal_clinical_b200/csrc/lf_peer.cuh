@@ -1,0 +1,47 @@
+// Device helpers of the peer-memory exchanges (protocol described in lf_peer.cu), shared by lf_peer.cu and lf_mid.cu.
+#pragma once
+#include <cooperative_groups.h>
+#include "lf_common.cuh"
+
+namespace lf {
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by every thread of the cluster after its peer stores.  flags_set: 0 = payload, 1 = gradients.
+__device__ __forceinline__ void peer_barrier(const LfPeerComm& c, int flags_set, long long epoch, cg::cluster_group& cluster) {
+  __threadfence_system();
+  cluster.sync();
+  if (cluster.block_rank() == 0 && (int)threadIdx.x < c.n_ranks) {
+    const int r = threadIdx.x;
+    st_release_sys((long long*)c.flags[r] + flags_set * LF_MAX_RANKS + c.rank, epoch);       // my flag on rank r
+    const long long* mine = (const long long*)c.flags[c.rank] + flags_set * LF_MAX_RANKS + r;  // rank r's flag here
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) < epoch) {
+      if (clock64() - t0 > 4000000000LL) { c.error[0] = 1; break; }                            // ~2 s
+      __nanosleep(64);
+    }
+  }
+  cluster.sync();
+}
+
+// Push `bytes` (multiple of 16) from src into slot [parity][rank] of every rank's receive area.
+__device__ __forceinline__ void peer_push(const LfPeerComm& c, void* const recv[LF_MAX_RANKS], const void* src, size_t bytes, int parity,
+                          int tid, int nthr) {
+  const size_t n16 = bytes / 16;
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  for (int r = 0; r < c.n_ranks; ++r) {
+    uint4* d = reinterpret_cast<uint4*>((char*)recv[r] + ((size_t)parity * c.n_ranks + c.rank) * bytes);
+    for (size_t i = tid; i < n16; i += nthr) d[i] = s[i];
+  }
+}
+
+
+}  // namespace lf

@@ -69,3 +69,59 @@ def pack_grad_exchange(grad_flat: torch.Tensor, n_head: int, stats: torch.Tensor
     grad_flat[n_head:n_head + (cal_hi - cal_lo)] = stats[cal_lo:cal_hi].to(grad_flat.dtype)
     dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=pg)
     stats[cal_lo:cal_hi] = grad_flat[n_head:n_head + (cal_hi - cal_lo)].to(stats.dtype)
+
+
+class PeerComm:
+    """Peer-memory communicator: one symmetric buffer per rank (flags + double-buffered receive areas for the
+    payload and the gradient exchange), mapped into every peer with CUDA IPC.  torch.distributed is only used
+    here, once, to exchange the 64-byte IPC handles; the per-step exchanges are the kernels in csrc/lf_peer.cu
+    and the fused push inside lf_step_mid (NVLink stores + system-scope flags, no NCCL call)."""
+
+    def __init__(self, payload_bytes: int, grad_floats: int, pg=None):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        self.rank, self.world = world(pg)
+        if self.world > _lib.LF_MAX_RANKS:
+            raise _lib.LfError(f"PeerComm supports up to {_lib.LF_MAX_RANKS} ranks on one NVSwitch domain")
+        self.payload_bytes = (payload_bytes + 15) // 16 * 16
+        self.grad_padded = (grad_floats + 3) // 4 * 4
+        flags_bytes = 2 * _lib.LF_MAX_RANKS * 8
+        self.off_payload = 256
+        self.off_grad = self.off_payload + (2 * self.world * self.payload_bytes + 255) // 256 * 256
+        total = self.off_grad + 2 * self.world * self.grad_padded * 4
+        assert flags_bytes <= self.off_payload
+        base = C.c_void_p()
+        _lib.check(lib.lf_comm_alloc(total, C.byref(base)), "lf_comm_alloc")
+        self.local = base.value
+        handle = C.create_string_buffer(64)
+        _lib.check(lib.lf_comm_ipc_handle(self.local, handle), "lf_comm_ipc_handle")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=pg)
+        self.bases = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.bases.append(self.local)
+            else:
+                p = C.c_void_p()
+                _lib.check(lib.lf_comm_ipc_open(C.create_string_buffer(h, 64), C.byref(p)), "lf_comm_ipc_open")
+                self.bases.append(p.value)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.epoch = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.barrier(group=pg)                      # every rank has mapped every buffer before the first push
+
+    def fill(self, comm) -> None:
+        """Populate an LfPeerComm struct."""
+        comm.n_ranks, comm.rank = self.world, self.rank
+        for r, b in enumerate(self.bases):
+            comm.flags[r] = b
+            comm.recv_payload[r] = b + self.off_payload
+            comm.recv_grad[r] = b + self.off_grad
+        comm.epoch = self.epoch.data_ptr()
+        comm.error = self.error.data_ptr()
+
+    def check(self) -> None:
+        if int(self.error.item()) != 0:
+            from . import _lib
+            raise _lib.LfError("peer exchange timed out waiting for another rank")

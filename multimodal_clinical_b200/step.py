@@ -79,7 +79,7 @@ class LateFusionStep:
 
     def __init__(self, num_classes: int, mode: str = "jlogits", n_data: Optional[int] = None,
                  device: Optional[torch.device] = None, precision: str = "fp32", ema_smoothing: float = 0.05,
-                 process_group=None, qmf_state=None, ema=None):
+                 process_group=None, qmf_state=None, ema=None, comm: str = "auto"):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.LfError("LateFusionStep needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -112,6 +112,11 @@ class LateFusionStep:
             ema.to(dev)
             self.ema_x, self.ema_offset, self.smoothing = ema.x, ema._offset, float(ema.smoothing)
         self.ema = ema
+        # "peer": exchanges through NVLink peer memory (csrc/lf_peer.cu); "nccl": torch.distributed collectives;
+        # "auto": peer when several CUDA ranks share one node and the IPC mapping succeeds
+        self.comm_mode = comm
+        self.peer = None
+        self._peer_key = None
         self.fresh_outputs = False
         self._pay = None
         self._pay_key = None
@@ -147,7 +152,7 @@ class LateFusionStep:
             b["dfeat"] = torch.empty(2, B, D, device=dev) if need_dfeat else None
             # one flat buffer [dW1 | db1 | dW2 | db2 | cal1 cal2] so the gradient exchange is ONE all-reduce
             n = Cn * D
-            b["grad_flat"] = torch.empty(2 * (n + Cn) + 2, device=dev)
+            b["grad_flat"] = torch.empty((2 * (n + Cn) + 2 + 3) // 4 * 4, device=dev)[:2 * (n + Cn) + 2]   # 16-B padded slot
             b["qmf_g"] = torch.empty(2, B, device=dev) if qmf else None
             self._bufs = b
             self._ws_key = key
@@ -162,15 +167,34 @@ class LateFusionStep:
                 b["conf"] = torch.empty(2, B, device=dev)
             if need_dfeat:
                 b["dfeat"] = torch.empty(2, B, D, device=dev)
-            b["grad_flat"] = torch.empty(2 * (Cn * D + Cn) + 2, device=dev)
+            b["grad_flat"] = torch.empty((2 * (Cn * D + Cn) + 2 + 3) // 4 * 4, device=dev)[:2 * (Cn * D + Cn) + 2]
             return b
         return self._bufs
+
+    def _peer_comm(self, payload_bytes: int, grad_floats: int):
+        """The peer-memory communicator for these sizes (built once; collective over the process group)."""
+        if self.world == 1 or self.comm_mode == "nccl" or self.device.type != "cuda":
+            return None
+        key = (payload_bytes, grad_floats)
+        if self._peer_key != key:
+            try:
+                self.peer = parallel.PeerComm(payload_bytes, grad_floats, self.pg)
+            except _lib.LfError:
+                if self.comm_mode == "peer":
+                    raise
+                self.peer = None                        # e.g. IPC not permitted: stay on the NCCL collectives
+            ok = torch.tensor([1 if self.peer is not None else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg)
+            if int(ok.item()) == 0:
+                self.peer = None
+            self._peer_key = key
+        return self.peer
 
     def _payload(self, B: int, qmf: bool):
         n_stats = LF_STATS_HEADER + 2 * self.C
         self._off_idx = 8 * n_stats
         self._off_conf = self._off_idx + (8 * B if qmf else 0)
-        nbytes = self._off_conf + (8 * B if qmf else 0)
+        nbytes = (self._off_conf + (8 * B if qmf else 0) + 15) // 16 * 16
         key = (B, qmf)
         if self.fresh_outputs or self._pay_key != key:
             self._pay = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -235,9 +259,17 @@ class LateFusionStep:
         st = _stream()
 
         check(lib.lf_heads_forward(C.byref(a), st), "lf_heads_forward")
-        gathered = parallel.gather_payload(pay, self.pg)          # (world, payload bytes); identity on one GPU
+        peer = self._peer_comm(pay.numel(), gf.numel())
         stride = pay.numel()
         mid = LfMidArgs()
+        if peer is not None:
+            # the exchange is fused into lf_step_mid: push over NVLink, flag barrier, consume the local receive area
+            mid.use_peer, mid.payload_local, mid.payload_bytes = 1, _ptr(pay), stride
+            mid.off_idx, mid.off_conf = self._off_idx, self._off_conf
+            peer.fill(mid.comm)
+            gathered = pay
+        else:
+            gathered = parallel.gather_payload(pay, self.pg)      # (world, payload bytes); identity on one GPU
         mid.mode, mid.classes, mid.batch_global, mid.n_ranks = self.mode, Cn, Bg, self.world
         mid.batch_local, mid.rank, mid.n_data, mid.update_ema = B, self.rank, self.n_data or 0, int(update_ema)
         base = gathered.data_ptr()
@@ -265,7 +297,15 @@ class LateFusionStep:
             a.stats = _ptr(self.stats)                            # calibrated counts join the GLOBAL statistics
             check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
             # head gradients + calibrated counts: one all-reduce
-            parallel.pack_grad_exchange(gf, 2 * (n + Cn), self.stats, STAT["CNT_X1_CAL"], STAT["CNT_X2_CAL"] + 1, self.pg)
+            if peer is not None:
+                gf[2 * (n + Cn):] = self.stats[STAT["CNT_X1_CAL"]:STAT["CNT_X2_CAL"] + 1].to(gf.dtype)
+                ra = _lib.LfPeerReduceArgs()
+                peer.fill(ra.comm)
+                ra.buf, ra.n, ra.n_padded = _ptr(gf), gf.numel(), peer.grad_padded
+                ra.tail_dst, ra.tail_n = self.stats[STAT["CNT_X1_CAL"]:].data_ptr(), 2
+                check(lib.lf_peer_allreduce(C.byref(ra), st), "lf_peer_allreduce")
+            else:
+                parallel.pack_grad_exchange(gf, 2 * (n + Cn), self.stats, STAT["CNT_X1_CAL"], STAT["CNT_X2_CAL"] + 1, self.pg)
         bufs = dict(bufs, conf=p_conf if qmf else None)
 
         return StepOutput(

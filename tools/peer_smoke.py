@@ -1,0 +1,41 @@
+"""2+ ranks under torchrun: the peer-memory exchange path must reproduce the NCCL path bit for bit, and both must
+equal the single-GPU result on the concatenated batch.  Run:  torchrun --nproc-per-node 2 tools/peer_smoke.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from multimodal_clinical_b200.step import LateFusionStep
+from oracle import late_fusion as O
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+ok = True
+for mode, B, D, Cn, N, prec in (("qmf", 96, 512, 6, 500, "fp32"), ("jlogits", 64, 256, 20, None, "fp32"), ("qmf", 256, 768, 101, 2000, "tf32")):
+    Bg = B * world
+    full = O.make_inputs(Bg, D, Cn, seed=3, n_data=N)
+    sl = slice(rank * B, (rank + 1) * B)
+    W = [full["W1"].to(dev), full["W2"].to(dev)]; b = [full["b1"].to(dev), full["b2"].to(dev)]
+    res = {}
+    for comm in ("nccl", "peer"):
+        eng = LateFusionStep(Cn, mode=mode, n_data=N, device=dev, precision=prec, comm=comm)
+        for s in range(3):
+            inp = O.make_inputs(Bg, D, Cn, seed=10 + s, n_data=N)
+            out = eng.step([inp["f1"][sl].to(dev), inp["f2"][sl].to(dev)], W, b, inp["y"][sl].to(dev),
+                           idx=inp["idx"][sl].to(dev) if N else None, ogm_alpha=0.8 if not N else None)
+        torch.cuda.synchronize()
+        if comm == "peer":
+            assert eng.peer is not None, "peer communicator was not built"
+            eng.peer.check()
+        res[comm] = [out.loss.clone(), out.dweight[0].clone(), out.dbias[1].clone(), out.stats.clone(), eng.ema_x.clone()] + \
+                    ([eng.correctness.clone()] if N else [eng.coeff.clone()])
+    same = all(torch.equal(a, c) for a, c in zip(res["nccl"], res["peer"]))
+    if rank == 0:
+        ref = (O.qmf_step if N else O.jlogits_step)
+        print(mode, Cn, "peer == nccl:", same, "loss", float(res["peer"][0]), flush=True)
+    ok = ok and same
+dist.barrier()
+torch.cuda.synchronize()
+if rank == 0:
+    print("PEER SMOKE", "OK" if ok else "MISMATCH", flush=True)
+os._exit(0 if ok else 1)
