@@ -88,7 +88,9 @@ typedef struct LfHeadsArgs {
   size_t workspace_bytes;
   int32_t fwd_only;       /* 1: validation / test forward, lf_heads_backward will not be called for this step.
                              Lets the narrow-head path (C <= 32) fuse forward and backward into one pass otherwise. */
-  int32_t reserved;
+  int32_t bwd_phase;      /* lf_heads_backward: 0 = everything; 1 = dL/dz, dW, db, calibrated counts (all but dfeat);
+                             2 = dfeat only (after a phase-1 call).  Lets the caller start the gradient exchange of
+                             dW/db on a second stream while dfeat, which no other rank needs, is still being written. */
 } LfHeadsArgs;
 
 /* Bytes of caller-provided scratch the heads calls need. */

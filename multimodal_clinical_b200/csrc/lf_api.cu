@@ -256,7 +256,10 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   HeadsWorkspace w = carve_heads_workspace(a->workspace, a->batch, a->dim, a->classes);
+  const int phase = a->bwd_phase;
+  if (phase < 0 || phase > 2) { set_error("bad bwd_phase %d", phase); return LF_ERR_BAD_ARG; }
   if (use_narrow(a)) {
+    if (phase == 2) return LF_OK;                 // dfeat is produced inside the fused narrow kernel
     const size_t cdn = (size_t)a->classes * a->dim;
     int grid = narrow_grid(a, false), nb_cal;
     if (a->mode == LF_MODE_QMF) {
@@ -275,13 +278,15 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     if (rc) return rc;
     return finalize_db_cal(w.db_partials, grid, a->classes, w.cal_partials, nb_cal, a->dbias[0], a->dbias[1], a->stats, s);
   }
-  rc = rows_backward(rows_args(a, w), a->mode, s);
-  if (rc) return rc;
+  if (phase != 2) {
+    rc = rows_backward(rows_args(a, w), a->mode, s);
+    if (rc) return rc;
+  }
   const float* dz[2] = {a->dlogits[0], a->mode == LF_MODE_QMF ? a->dlogits[1] : a->dlogits[0]};
   const int ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
   const bool tc = use_tensor_pipe(a);
   GemmArgs g;
-  if (a->need_dfeat) {
+  if (a->need_dfeat && phase != 1) {
     memset(&g, 0, sizeof(g));
     for (int m = 0; m < 2; ++m) { g.A[m] = dz[m]; g.B[m] = a->weight[m]; g.bias[m] = nullptr; g.C[m] = a->dfeat[m]; }
     g.M = a->batch; g.N = a->dim; g.K = a->classes;
@@ -300,6 +305,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     }
     if (rc) return rc;
   }
+  if (phase == 2) return LF_OK;
   // dW_m = dZ_m^T F_m : split-K over the batch, partials reduced in fixed order
   int splits = dw_splits(a->batch, a->dim, a->classes);
   const size_t cd = (size_t)a->classes * a->dim;

@@ -10,8 +10,9 @@
 //
 // The reference spreads this over ~15 host round trips; the previous version of this library over eight
 // small launches and (sharded) three collectives.  Here the inputs arrive as ONE rank-major gathered
-// buffer ([rank][stats | idx | conf], a single all-gather) and one thread-block CLUSTER of 8 CTAs walks
-// the dependent phases with hardware cluster barriers (barrier.cluster, release/acquire) in between:
+// buffer ([rank][stats | idx | conf]: a single all-gather, or the peer-memory push fused in below) and one
+// cooperatively launched grid (up to 128 CTAs x 1024 threads, ~2 samples per thread however large the
+// GLOBAL batch is) walks the dependent phases with grid-wide barriers in between:
 //   P0 sum statistics, EMA, coefficients   P1 ticket = last writer per index   P2 History update
 //   P3 min/max over all N                  P4 ranking terms, dL/dconf          P5 loss
 #include <cooperative_groups.h>
@@ -22,7 +23,7 @@ namespace cg = cooperative_groups;
 
 namespace lf {
 
-constexpr int kMidCtas = 8;          // portable cluster size
+constexpr int kMidMaxCtas = 128;     // cooperative grid: all CTAs co-resident (<= 2 x 148 at 1024 threads)
 constexpr int kMidThreads = 1024;
 
 // rank-major gathered batch: sample j of the global batch lives on rank j / Bl
@@ -68,15 +69,15 @@ __device__ __forceinline__ void g_pair_terms(const MidShared& sh, const double* 
 
 struct MidParams {
   LfMidArgs a;
-  double* minmax;     // [kMidCtas][2][2]
-  float* regpart;     // [kMidCtas]
+  double* minmax;     // [kMidMaxCtas][2][2]
+  float* regpart;     // [kMidMaxCtas]
   double* A;          // [2][Bg] normalised correctness of the batch
 };
 
 __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
   const LfMidArgs& a = p.a;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int ncta = (int)cluster.num_blocks(), cta = (int)cluster.block_rank();
+  cg::grid_group grid = cg::this_grid();                 // grid-wide barriers (cooperative launch)
+  const int ncta = (int)gridDim.x, cta = (int)blockIdx.x;
   const int tid = cta * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x;
   const int C = a.classes, len = LF_STATS_HEADER + 2 * C, Bg = a.batch_global, N = a.n_data;
   extern __shared__ double s_stats[];                 // [len] global statistics (each CTA keeps a copy)
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     epoch = a.comm.epoch[0] + 1;
     const int parity = (int)(epoch & 1);
     peer_push(a.comm, a.comm.recv_payload, a.payload_local, (size_t)a.payload_bytes, parity, tid, nthr);
-    peer_barrier(a.comm, 0, epoch, cluster);
+    peer_barrier(a.comm, 0, epoch, grid);
     const char* base = (const char*)a.comm.recv_payload[a.comm.rank] + (size_t)parity * a.n_ranks * a.payload_bytes;
     stats_parts = (const double*)base; stats_stride = a.payload_bytes / 8;
     idx_parts = (const int64_t*)(base + a.off_idx); idx_stride = a.payload_bytes / 8;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     const int64_t i = g.idx_at(j);
     if ((unsigned long long)i < (unsigned long long)N) atomicMax(&lw[i], base + j);
   }
-  cluster.sync();
+  grid.sync();
   // ---- P2: History.correctness_update (QMF.py:20-29), alpha = 0.1.  Four samples per thread per round so
   // the dependent random accesses (idx -> ticket -> History entry) of different samples overlap.
   for (int j0 = tid; j0 < Bg; j0 += 4 * nthr) {
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
       a.confidence[(size_t)N + ii[u]] = (double)g.conf_at(1, j);
     }
   }
-  cluster.sync();
+  grid.sync();
   // ---- P3: min / max over ALL N entries of both modalities (QMF.py:38-40), NaN-propagating like numpy
   for (int m = 0; m < 2; ++m) {
     const double* c = a.correctness + (size_t)m * N;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     }
     __syncthreads();
   }
-  cluster.sync();
+  grid.sync();
   if (threadIdx.x < 2) {
     const int m = threadIdx.x;
     double lo = p.minmax[m * 2], hi = p.minmax[m * 2 + 1];
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
       if (j < Bg) { p.A[j] = (c0[u] - sh.lo[0]) / (sh.hi[0] - sh.lo[0]); p.A[Bg + j] = (c1[u] - sh.lo[1]) / (sh.hi[1] - sh.lo[1]); }
     }
   }
-  cluster.sync();
+  grid.sync();
   if (threadIdx.x == 0) {
     float m00, m11;
     const float t00 = a_pair_target(p.A, Bg, 0, &m00);
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     for (int w = 0; w < (int)blockDim.x / 32; ++w) { s += sh.red[w]; nan |= (sh.red[w] != sh.red[w]); }
     p.regpart[cta] = nan ? NAN : s;
   }
-  cluster.sync();
+  grid.sync();
   // ---- P5: loss = CE(z_df) + CE(z1) + CE(z2) + L_reg, each a separate fp32 mean like the reference
   if (cta == 0 && threadIdx.x == 0) {
     double rs = 0.0;
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
 using namespace lf;
 
 extern "C" size_t lf_mid_workspace_bytes(int32_t batch_global) {
-  return 512 + sizeof(double) * kMidCtas * 4 + sizeof(double) * 2 * (size_t)(batch_global > 0 ? batch_global : 0);
+  return 8192 + sizeof(double) * 2 * (size_t)(batch_global > 0 ? batch_global : 0);
 }
 
 extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
@@ -322,18 +323,26 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
   MidParams p;
   p.a = *a;
   p.minmax = qmf ? (double*)a->workspace : nullptr;
-  p.regpart = qmf ? (float*)((char*)a->workspace + 256) : nullptr;
-  p.A = qmf ? (double*)((char*)a->workspace + 512) : nullptr;
+  p.regpart = qmf ? (float*)((char*)a->workspace + 4096) : nullptr;        // minmax: 128 x 4 doubles = 4096 B
+  p.A = qmf ? (double*)((char*)a->workspace + 8192) : nullptr;
   const size_t smem = sizeof(double) * (LF_STATS_HEADER + 2 * (size_t)a->classes);
   cudaLaunchConfig_t cfg = {};
-  const int ncta = qmf ? kMidCtas : 1;
+  // QMF: ~2 samples (and ~2 History entries) per thread, so the dependent random accesses of the phases are
+  // one or two round trips deep however large the GLOBAL batch is (every rank walks all of it)
+  int ncta = 1;
+  if (qmf) {
+    const long long work = a->batch_global > a->n_data ? a->batch_global : a->n_data;
+    ncta = div_up(work, 2 * kMidThreads);
+    if (ncta > kMidMaxCtas) ncta = kMidMaxCtas;
+    if (ncta < 1) ncta = 1;
+  }
   cfg.gridDim = dim3(ncta, 1, 1);
   cfg.blockDim = dim3(qmf ? kMidThreads : 256, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t e = cudaSuccess;
   LF_LAUNCH("step_mid", s, (e = cudaLaunchKernelEx(&cfg, mid_kernel, p)));

@@ -20,23 +20,37 @@ namespace cg = cooperative_groups;
 
 namespace lf {
 
-__global__ void __launch_bounds__(1024) peer_allreduce_kernel(LfPeerReduceArgs a) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int tid = cluster.block_rank() * blockDim.x + threadIdx.x, nthr = cluster.num_blocks() * blockDim.x;
+__global__ void __launch_bounds__(512) peer_allreduce_kernel(LfPeerReduceArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
   const LfPeerComm& c = a.comm;
   const long long epoch = c.epoch[1] + 1;
   const int parity = (int)(epoch & 1);
   const size_t bytes = (size_t)a.n_padded * sizeof(float);
   peer_push(c, a.comm.recv_grad, a.buf, bytes, parity, tid, nthr);
-  peer_barrier(c, 1, epoch, cluster);
-  const float* base = (const float*)c.recv_grad[c.rank] + (size_t)parity * c.n_ranks * a.n_padded;
-  for (int i = tid; i < a.n; i += nthr) {
-    float s = 0.f;
-    for (int r = 0; r < c.n_ranks; ++r) s += base[(size_t)r * a.n_padded + i];     // rank order: identical everywhere
-    a.buf[i] = s;
-    if (a.tail_dst && i >= a.n - a.tail_n) a.tail_dst[i - (a.n - a.tail_n)] = (double)s;
+  peer_barrier(c, 1, epoch, grid);
+  const float4* base = reinterpret_cast<const float4*>((const float*)c.recv_grad[c.rank] + (size_t)parity * c.n_ranks * a.n_padded);
+  const int n4 = a.n_padded / 4;
+  for (int i = tid; i < n4; i += nthr) {
+    float4 v[LF_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < LF_MAX_RANKS; ++r)
+      if (r < c.n_ranks) v[r] = base[(size_t)r * n4 + i];                // all ranks' loads in flight together
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < LF_MAX_RANKS; ++r)                              // rank order: identical on every rank
+      if (r < c.n_ranks) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+    const float e[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = 4 * i + k;
+      if (j < a.n) {
+        a.buf[j] = e[k];
+        if (a.tail_dst && j >= a.n - a.tail_n) a.tail_dst[j - (a.n - a.tail_n)] = (double)e[k];
+      }
+    }
   }
-  cluster.sync();
+  grid.sync();
   if (tid == 0) c.epoch[1] = epoch;
 }
 
@@ -73,10 +87,13 @@ extern "C" int lf_peer_allreduce(const LfPeerReduceArgs* a, void* stream) {
   if (!a || !a->buf || a->n < 1 || a->n_padded < a->n || a->n_padded % 4 || a->comm.n_ranks < 1 ||
       a->comm.n_ranks > LF_MAX_RANKS || !a->comm.epoch || !a->comm.error) { set_error("lf_peer_allreduce: bad argument"); return LF_ERR_BAD_ARG; }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(8, 1, 1); cfg.blockDim = dim3(1024, 1, 1); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+  int ctas = div_up(a->n_padded / 4, 512 * 2);          // ~2 float4 per thread per rank
+  if (ctas > 64) ctas = 64;
+  if (ctas < 1) ctas = 1;
+  cfg.gridDim = dim3(ctas, 1, 1); cfg.blockDim = dim3(512, 1, 1); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].id = cudaLaunchAttributeCooperative;          // grid-wide barrier between push, flag exchange and reduction
+  attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t e = cudaSuccess;
   LF_LAUNCH("peer_allreduce", cfg.stream, (e = cudaLaunchKernelEx(&cfg, peer_allreduce_kernel, *a)));

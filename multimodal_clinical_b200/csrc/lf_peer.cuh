@@ -15,11 +15,11 @@ __device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
   return v;
 }
 
-// Called by every thread of the cluster after its peer stores.  flags_set: 0 = payload, 1 = gradients.
-__device__ __forceinline__ void peer_barrier(const LfPeerComm& c, int flags_set, long long epoch, cg::cluster_group& cluster) {
+// Called by every thread of the (cooperatively launched) grid after its peer stores.  flags_set: 0 = payload, 1 = gradients.
+__device__ __forceinline__ void peer_barrier(const LfPeerComm& c, int flags_set, long long epoch, cg::grid_group& grid) {
   __threadfence_system();
-  cluster.sync();
-  if (cluster.block_rank() == 0 && (int)threadIdx.x < c.n_ranks) {
+  grid.sync();
+  if (blockIdx.x == 0 && (int)threadIdx.x < c.n_ranks) {
     const int r = threadIdx.x;
     st_release_sys((long long*)c.flags[r] + flags_set * LF_MAX_RANKS + c.rank, epoch);       // my flag on rank r
     const long long* mine = (const long long*)c.flags[c.rank] + flags_set * LF_MAX_RANKS + r;  // rank r's flag here
@@ -29,7 +29,7 @@ __device__ __forceinline__ void peer_barrier(const LfPeerComm& c, int flags_set,
       __nanosleep(64);
     }
   }
-  cluster.sync();
+  grid.sync();
 }
 
 // Push `bytes` (multiple of 16) from src into slot [parity][rank] of every rank's receive area.
@@ -39,7 +39,12 @@ __device__ __forceinline__ void peer_push(const LfPeerComm& c, void* const recv[
   const uint4* s = reinterpret_cast<const uint4*>(src);
   for (int r = 0; r < c.n_ranks; ++r) {
     uint4* d = reinterpret_cast<uint4*>((char*)recv[r] + ((size_t)parity * c.n_ranks + c.rank) * bytes);
-    for (size_t i = tid; i < n16; i += nthr) d[i] = s[i];
+    size_t i = tid;
+    for (; i + 3 * (size_t)nthr < n16; i += 4 * (size_t)nthr) {          // four loads in flight, then four peer stores
+      const uint4 v0 = s[i], v1 = s[i + nthr], v2 = s[i + 2 * (size_t)nthr], v3 = s[i + 3 * (size_t)nthr];
+      d[i] = v0; d[i + nthr] = v1; d[i + 2 * (size_t)nthr] = v2; d[i + 3 * (size_t)nthr] = v3;
+    }
+    for (; i < n16; i += nthr) d[i] = s[i];
   }
 }
 

@@ -190,6 +190,11 @@ class LateFusionStep:
             self._peer_key = key
         return self.peer
 
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _payload(self, B: int, qmf: bool):
         n_stats = LF_STATS_HEADER + 2 * self.C
         self._off_idx = 8 * n_stats
@@ -295,17 +300,30 @@ class LateFusionStep:
                 self.ema.counter += 1
         if backward:
             a.stats = _ptr(self.stats)                            # calibrated counts join the GLOBAL statistics
-            check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
-            # head gradients + calibrated counts: one all-reduce
-            if peer is not None:
-                gf[2 * (n + Cn):] = self.stats[STAT["CNT_X1_CAL"]:STAT["CNT_X2_CAL"] + 1].to(gf.dtype)
-                ra = _lib.LfPeerReduceArgs()
-                peer.fill(ra.comm)
-                ra.buf, ra.n, ra.n_padded = _ptr(gf), gf.numel(), peer.grad_padded
-                ra.tail_dst, ra.tail_n = self.stats[STAT["CNT_X1_CAL"]:].data_ptr(), 2
-                check(lib.lf_peer_allreduce(C.byref(ra), st), "lf_peer_allreduce")
+            if self.world == 1:
+                check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
             else:
-                parallel.pack_grad_exchange(gf, 2 * (n + Cn), self.stats, STAT["CNT_X1_CAL"], STAT["CNT_X2_CAL"] + 1, self.pg)
+                # dW / db first, then their exchange on a side stream while dfeat (which no other rank needs) is
+                # still being written on the main stream
+                a.bwd_phase = 1
+                check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
+                cur = torch.cuda.current_stream()
+                side = self._side_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    sst = side.cuda_stream
+                    if peer is not None:
+                        gf[2 * (n + Cn):] = self.stats[STAT["CNT_X1_CAL"]:STAT["CNT_X2_CAL"] + 1].to(gf.dtype)
+                        ra = _lib.LfPeerReduceArgs()
+                        peer.fill(ra.comm)
+                        ra.buf, ra.n, ra.n_padded = _ptr(gf), gf.numel(), peer.grad_padded
+                        ra.tail_dst, ra.tail_n = self.stats[STAT["CNT_X1_CAL"]:].data_ptr(), 2
+                        check(lib.lf_peer_allreduce(C.byref(ra), sst), "lf_peer_allreduce")
+                    else:
+                        parallel.pack_grad_exchange(gf, 2 * (n + Cn), self.stats, STAT["CNT_X1_CAL"], STAT["CNT_X2_CAL"] + 1, self.pg)
+                a.bwd_phase = 2
+                check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
+                cur.wait_stream(side)
         bufs = dict(bufs, conf=p_conf if qmf else None)
 
         return StepOutput(
