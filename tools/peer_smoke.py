@@ -1,5 +1,5 @@
-"""2+ ranks under torchrun: the peer-memory exchange path must reproduce the NCCL path bit for bit, and both must
-equal the single-GPU result on the concatenated batch.  Run:  torchrun --nproc-per-node 2 tools/peer_smoke.py"""
+"""2+ ranks under torchrun: the peer-memory exchange path must reproduce the NCCL path (state bit for bit, gradients to
+rounding: NCCL sums in its own order beyond 2 ranks) and leave every rank with identical results.  Run:  torchrun --nproc-per-node 2 tools/peer_smoke.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
@@ -29,10 +29,22 @@ for mode, B, D, Cn, N, prec in (("qmf", 96, 512, 6, 500, "fp32"), ("jlogits", 64
             eng.peer.check()
         res[comm] = [out.loss.clone(), out.dweight[0].clone(), out.dbias[1].clone(), out.stats.clone(), eng.ema_x.clone()] + \
                     ([eng.correctness.clone()] if N else [eng.coeff.clone()])
-    same = all(torch.equal(a, c) for a, c in zip(res["nccl"], res["peer"]))
+    # statistics, EMA and History are summed in rank order on both paths (bit-identical); the gradient all-reduce
+    # of NCCL uses its own summation tree for > 2 ranks, so gradients agree to rounding
+    def rel(a, c):
+        a, c = a.double(), c.double()
+        return float((a - c).norm() / c.norm().clamp_min(1e-30))
+    exact = all(torch.equal(a, c) for a, c in zip(res["nccl"][3:], res["peer"][3:]))
+    close = max(rel(a, c) for a, c in zip(res["nccl"][:3], res["peer"][:3]))
+    # all ranks hold identical results on the peer path
+    mine = torch.cat([t.double().flatten() for t in res["peer"]])
+    allr = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    identical = all(torch.equal(allr[0], t) for t in allr)
+    same = exact and close < 1e-5 and identical
     if rank == 0:
-        ref = (O.qmf_step if N else O.jlogits_step)
-        print(mode, Cn, "peer == nccl:", same, "loss", float(res["peer"][0]), flush=True)
+        print(mode, Cn, "state bit-identical:", exact, "grad rel diff vs nccl: %.2e" % close, "ranks identical:", identical,
+              "loss", float(res["peer"][0]), flush=True)
     ok = ok and same
 dist.barrier()
 torch.cuda.synchronize()
