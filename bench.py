@@ -401,23 +401,41 @@ def main():
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
 
-    def e2e_step(i):
-        p = pinned[i % len(pinned)]
-        for k in stage:
-            stage[k].copy_(p[k], non_blocking=True)
-        out = one_step(stage, i)
-        loss_host.copy_(out.loss.view(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the user reads the loss every step
-        return float(loss_host[0])
+    def host_batches(n):
+        for i in range(n):
+            yield pinned[i % len(pinned)]
 
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
-    e1.record()
-    barrier()
+    if use_graph:
+        # the public host-fed API: H2D of batch i+1 on a copy stream under the replay of step i, loss read back
+        # (D2H + sync) every step.  Graph capture and staging allocation happen before the first yield.
+        gen = eng.stream_from_host(host_batches(args.steps + 3), W, b, need_dfeat=w["dfeat"], ogm_alpha=w["alpha"],
+                                   extra=(lambda: modulate(0)) if enc_grads is not None else None)
+        for _ in range(3):
+            next(gen)
+        barrier()
+        e0.record()
+        for _ in gen:
+            pass
+        e1.record()
+        barrier()
+    else:
+        def e2e_step(i):
+            p = pinned[i % len(pinned)]
+            for k in stage:
+                stage[k].copy_(p[k], non_blocking=True)
+            out = eager_step(stage, i)
+            loss_host.copy_(out.loss.view(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the user reads the loss every step
+            return float(loss_host[0])
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        e1.record()
+        barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -358,6 +358,53 @@ class LateFusionStep:
                 extra()
         return graph, out
 
+    # ------------------------------------------------------------------ host-fed steps
+    def stream_from_host(self, host_batches, weights, biases, extra=None, **kw):
+        """Generator over ``host_batches`` (iterable of dicts of PINNED host tensors with keys f1, f2, y[, idx]):
+        yields the loss of every step as a Python float.  Each batch is copied host->device on a copy stream into
+        one of two staging sets while the previous step computes; the step itself is a CUDA-graph replay on the
+        staging set (one graph per set).  The loss is read back (device->host) every step, as the reference's
+        training loop does when it logs it."""
+        cur = torch.cuda.current_stream()
+        copy = torch.cuda.Stream(device=self.device)
+        it = iter(host_batches)
+        stages, graphs, ready, done = [], [], [], []
+        loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def upload(slot, hb):
+            if done[slot] is not None:
+                copy.wait_event(done[slot])              # the step that last read this staging set has finished
+            with torch.cuda.stream(copy):
+                for k, v in stages[slot].items():
+                    v.copy_(hb[k], non_blocking=True)
+                ready[slot].record(copy)
+
+        first = next(it, None)
+        if first is None:
+            return
+        for slot in range(2):
+            st = {k: torch.empty_like(v, device=self.device) for k, v in first.items()}
+            stages.append(st); ready.append(torch.cuda.Event()); done.append(None)
+            for k, v in st.items():
+                v.copy_(first[k])
+            graphs.append(self.capture([st["f1"], st["f2"]], weights, biases, st["y"], idx=st.get("idx"), extra=extra, **kw))
+        copy.wait_stream(cur)
+        upload(0, first)
+        slot, nxt = 0, next(it, None)
+        while True:
+            cur.wait_event(ready[slot])
+            if nxt is not None:
+                upload(1 - slot, nxt)                    # overlaps the replay below
+            g, out = graphs[slot]
+            g.replay()
+            done[slot] = torch.cuda.Event(); done[slot].record(cur)
+            loss_host.copy_(out.loss.view(1), non_blocking=True)
+            cur.synchronize()
+            yield float(loss_host[0])
+            if nxt is None:
+                return
+            slot, nxt = 1 - slot, next(it, None)
+
     # ------------------------------------------------------------------ OGM-GE modulation
     def modulate(self, grads: Sequence[torch.Tensor], which: int, modulation: str, seed: int, offset: int) -> None:
         """In-place OGM-GE add_factor over the 4-D gradients of encoder ``which`` (existing_algos/OGM_GE.py:42-54)."""

@@ -176,3 +176,25 @@ def test_full_size_properties(name, mode, B, D, Cn, N, prec):
     assert_close(o.dweight[0].double() @ probe, want, tol, "dW1 . probe")
     dzm = dz[1 if mode == "qmf" else 0]
     assert_close(o.dfeat[1].double() @ probe, dzm @ (s["W2"].double() @ probe), tol, "df2 . probe")
+
+
+def test_stream_from_host_matches_eager_steps():
+    """The host-fed pipeline (pinned batches -> copy stream -> graph replay, loss read back every step) yields the
+    same losses and final state as eager steps on the same batches (the two capture warm-ups replay batch 0)."""
+    B, D, Cn, N = 128, 512, 6, 400
+    host = []
+    for s in range(4):
+        inp = O.make_inputs(B, D, Cn, seed=40 + s, n_data=N)
+        host.append({k: inp[k].pin_memory() for k in ("f1", "f2", "y", "idx")})
+    base = O.make_inputs(B, D, Cn, seed=1, n_data=N)
+    W = [base["W1"].cuda(), base["W2"].cuda()]; b = [base["b1"].cuda(), base["b2"].cuda()]
+    ea = _eng(num_classes=Cn, mode="qmf", n_data=N)
+    # capture of the two staging sets runs 2 warm-up steps each on batch 0 -> 4 extra steps on batch 0
+    want = []
+    for hb in [host[0]] * 4 + host:
+        o = ea.step([hb["f1"].cuda(), hb["f2"].cuda()], W, b, hb["y"].cuda(), idx=hb["idx"].cuda())
+        want.append(float(o.loss))
+    eg = _eng(num_classes=Cn, mode="qmf", n_data=N)
+    got = list(eg.stream_from_host(iter(host), W, b))
+    assert got == want[4:]
+    assert torch.equal(eg.correctness, ea.correctness) and torch.equal(eg.ema_x, ea.ema_x)
