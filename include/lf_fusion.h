@@ -308,6 +308,11 @@ size_t lf_ogm_scores_workspace_bytes(void);
 int lf_ogm_scores(const float* z1, const float* z2, const int64_t* label, int32_t batch, int32_t classes,
                   double* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same test hook for bf16 operands (kind::f16): A, B bf16; out fp32, or bf16 when out_bf16 != 0. */
+int lf_debug_tc_gemm16(const void* A, const void* B, void* out, int32_t M, int32_t N, int32_t K, int32_t lda,
+                       int32_t ldb, int32_t ld_out, int32_t a_mn_major, int32_t b_mn_major, int32_t block_n,
+                       int32_t splits, int64_t split_stride, int32_t out_bf16, void* stream);
+
 /* Last error message of the calling thread (host string). */
 const char* lf_last_error(void);
 int32_t lf_abi_version(void);

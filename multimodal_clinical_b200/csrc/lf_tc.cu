@@ -22,6 +22,8 @@
 // Ragged edges: TMA zero-fills out-of-bounds loads and clips stores, so C = 101/309 and K = 101/309 need
 // no padding copies.  Parity class: 2e-2 (tests/test_tc_gemm_gpu.py, tests/test_parity_gpu.py).
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
 #include "lf_common.cuh"
 #include "lf_tc.cuh"
 #include "lf_tc_ptx.cuh"
@@ -53,7 +55,7 @@ __device__ __forceinline__ Item decode_item(const TcGemmParams& p, int item) {
   it.m0 = m_t * p.tile_m; it.n0 = n_t * p.block_n;
   it.k_begin = it.split * p.k_per_split;
   it.k_end = min(p.K, it.k_begin + p.k_per_split);
-  it.num_kb = it.k_end > it.k_begin ? (it.k_end - it.k_begin + TC_BLOCK_K - 1) / TC_BLOCK_K : 0;
+  it.num_kb = it.k_end > it.k_begin ? (it.k_end - it.k_begin + p.kb_elems - 1) / p.kb_elems : 0;
   return it;
 }
 
@@ -104,19 +106,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           mbar_expect_tx(&full_bar[s], (p.a_mn_major ? a_bytes : (uint32_t)p.tile_m * TC_BLOCK_K * 4) + b_bytes);
-          const int k0 = w.k_begin + kb * TC_BLOCK_K;
+          const int k0 = w.k_begin + kb * p.kb_elems;
           if (!p.a_mn_major) {
             tma_load_2d(mapA, &full_bar[s], sa, k0, w.m0);                      // [32 k x 128 rows]
           } else {
 #pragma unroll
-            for (int i = 0; i < TC_BLOCK_M / 32; ++i)                           // [32 m x 32 k] boxes
-              tma_load_2d(mapA, &full_bar[s], sa + i * 4096, w.m0 + 32 * i, k0);
+            for (int i = 0; i < TC_BLOCK_M / p.mn_box; ++i)                     // [mn_box m x kb_elems k] boxes of 128-B rows
+              tma_load_2d(mapA, &full_bar[s], sa + i * p.mn_box_bytes, w.m0 + p.mn_box * i, k0);
           }
           if (!p.b_mn_major) {
             tma_load_2d(mapB, &full_bar[s], sb, k0, w.n0);                      // [32 k x block_n rows]
           } else {
-            for (int i = 0; i < p.block_n / 32; ++i)
-              tma_load_2d(mapB, &full_bar[s], sb + i * 4096, w.n0 + 32 * i, k0);
+            for (int i = 0; i < p.block_n / p.mn_box; ++i)
+              tma_load_2d(mapB, &full_bar[s], sb + i * p.mn_box_bytes, w.n0 + p.mn_box * i, k0);
           }
         }
       }
@@ -124,7 +126,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, p.block_n, p.a_mn_major, p.b_mn_major);
+      const uint32_t idesc = p.elem == 4 ? make_idesc_tf32(TC_BLOCK_M, p.block_n, p.a_mn_major, p.b_mn_major)
+                                         : make_idesc_bf16(TC_BLOCK_M, p.block_n, p.a_mn_major, p.b_mn_major);
       uint32_t it = 0, li = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++li) {
         const Item w = decode_item(p, item);
@@ -139,17 +142,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          const int krem = w.k_end - (w.k_begin + kb * TC_BLOCK_K);
-          const int ksteps = krem >= TC_BLOCK_K ? TC_BLOCK_K / TC_UMMA_K : (krem + TC_UMMA_K - 1) / TC_UMMA_K;
+          const int krem = w.k_end - (w.k_begin + kb * p.kb_elems);
+          const int ksteps = krem >= p.kb_elems ? 4 : (krem + p.umma_k - 1) / p.umma_k;       // 32 B of K per instruction
           for (int k = 0; k < ksteps; ++k) {
             // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); step 32 B inside the row.
             // MN-major SW128/32B-base: rows are k, 128 B = 32 mn each; the atom is 4 k-rows (512 B, SBO),
             //   32-element MN chunks are 4096 B apart (LBO); one instruction eats 8 k-rows -> step 1024 B.
-            const uint64_t da = p.a_mn_major ? make_smem_desc(sa + k * 1024, 4096, 512, 1)
+            const uint64_t da = p.a_mn_major ? make_smem_desc(sa + k * p.mn_step, p.mn_lbo, p.mn_sbo, p.mn_lt)
                                              : make_smem_desc(sa + k * 32, 16, 1024, 2);
-            const uint64_t db = p.b_mn_major ? make_smem_desc(sb + k * 1024, 4096, 512, 1)
+            const uint64_t db = p.b_mn_major ? make_smem_desc(sb + k * p.mn_step, p.mn_lbo, p.mn_sbo, p.mn_lt)
                                              : make_smem_desc(sb + k * 32, 16, 1024, 2);
-            umma_tf32(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (p.elem == 4) umma_tf32(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_f16(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);               // frees the stage once the MMAs above have read it
         }
@@ -170,13 +174,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const uint32_t acc = tmem_base + buf * (uint32_t)p.acc_cols + ((uint32_t)(q * 32) << 16);
       const CUtensorMap* mapO = w.batch == 0 ? &mapO0 : &mapO1;
       if (p.tma_store) {
-        for (int c0 = 0; c0 < p.block_n; c0 += 32, ++cc) {
-          float v[32];
-          tmem_ld16(acc + c0, v);
-          tmem_ld16(acc + c0 + 16, v + 16);
-          if (w.num_kb == 0) {
+        const int ccols = 128 / p.out_elem;                 // output columns per 128-byte staging row: 32 fp32 / 64 bf16
+        for (int c0 = 0; c0 < p.block_n; c0 += ccols, ++cc) {
+          uint32_t pk[32];                                   // 128 bytes of this thread's output row
+          if (p.out_elem == 4) {
+            float v[32];
+            tmem_ld16(acc + c0, v);
+            tmem_ld16(acc + c0 + 16, v + 16);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            for (int i = 0; i < 32; ++i) pk[i] = w.num_kb == 0 ? 0u : __float_as_uint(v[i]);
+          } else {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              float v[16];
+              tmem_ld16(acc + c0 + 16 * h, v);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                pk[8 * h + i] = w.num_kb == 0 ? 0u : *reinterpret_cast<const uint32_t*>(&b2);
+              }
+            }
           }
           uint8_t* box = staging + (cc & 1) * (TC_BLOCK_M * 128);
           if (et == 0) tma_store_wait_read<1>();     // the store that last used this box has read it
@@ -184,7 +201,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           uint8_t* rowp = box + row_in_tile * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)                 // SWIZZLE_128B: 16-byte chunk j of row r lives at j ^ (r & 7)
-            *reinterpret_cast<float4*>(rowp + ((j ^ (row_in_tile & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row_in_tile & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           fence_proxy_async();
           named_bar_sync(1, 128);
           if (et == 0) {
@@ -196,7 +213,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // transposing path: 32x32 blocks through a padded per-warp tile, 128 contiguous bytes per store
         float* tile = reinterpret_cast<float*>(staging) + q * (32 * 33);
         const int row0 = w.m0 + q * 32;
-        float* out = p.out[w.batch] + (size_t)w.split * p.split_stride;
+        float* out = (float*)p.out[w.batch] + (size_t)w.split * p.split_stride;
         const float* bias = p.bias[w.batch];
         for (int c0 = 0; c0 < p.block_n; c0 += 32) {
           float v[32];
@@ -251,35 +268,35 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch ld elements.
-int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld,
-             int box_inner, int box_outer, bool mn_major) {
+// 2-D tensor map: `inner` contiguous elements per row, `outer` rows, row pitch ld elements.
+int make_map(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld,
+             int box_inner, int box_outer, bool mn_major, int elem, int mn_swizzle) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return LF_ERR_CUDA; }
-  if (((uintptr_t)base & 15) || (ld * 4) % 16) { set_error("TMA operand must be 16-byte aligned with a 16-byte row pitch"); return LF_ERR_BAD_ARG; }
+  if (((uintptr_t)base & 15) || (ld * elem) % 16) { set_error("TMA operand must be 16-byte aligned with a 16-byte row pitch"); return LF_ERR_BAD_ARG; }
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
+  if (mn_major) swz = mn_swizzle ? (CUtensorMapSwizzle)mn_swizzle : (elem == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+  CUresult r = enc(map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return LF_ERR_CUDA; }
   return LF_OK;
 }
 
 // 3-D output map for the TMA-store epilogue: (cols, rows, splits), box [32 x 128 x 1], SWIZZLE_128B.
-static int make_store_map(CUtensorMap* map, float* base, long long cols, long long rows, long long ld,
-                          long long splits, long long split_stride) {
+static int make_store_map(CUtensorMap* map, void* base, long long cols, long long rows, long long ld,
+                          long long splits, long long split_stride, int elem) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return LF_ERR_CUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)splits};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(splits > 1 ? split_stride : rows * ld) * 4};
-  cuuint32_t box[3] = {32, (cuuint32_t)TC_BLOCK_M, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * elem, (cuuint64_t)(splits > 1 ? split_stride : rows * ld) * elem};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / elem), (cuuint32_t)TC_BLOCK_M, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+  CUresult r = enc(map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(store) failed (%d)", (int)r); return LF_ERR_CUDA; }
@@ -293,18 +310,34 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   }
   TcGemmParams p;
   p.M = d.M; p.N = d.N; p.K = d.K;
+  p.elem = d.elem == 2 ? 2 : 4;
+  p.out_elem = d.out_elem == 2 ? 2 : 4;
+  p.kb_elems = 128 / p.elem; p.umma_k = 32 / p.elem; p.mn_box = 128 / p.elem;
+  p.mn_box_bytes = 128 * p.kb_elems;
+  if (p.elem == 4) { p.mn_step = 1024; p.mn_lbo = 4096; p.mn_sbo = 512; p.mn_lt = 1; }     // 128B swizzle, 32-byte atoms
+  else { p.mn_step = 2048; p.mn_lbo = 8192; p.mn_sbo = 1024; p.mn_lt = 2; }                // plain 128B swizzle
+  int mn_swz = 0;
+  if (p.elem == 2) {                                       // experiment overrides (tools/dbg_tc16.py)
+    if (getenv("LF_TC16_STEP")) p.mn_step = (unsigned)atoi(getenv("LF_TC16_STEP"));
+    if (getenv("LF_TC16_LBO")) p.mn_lbo = (unsigned)atoi(getenv("LF_TC16_LBO"));
+    if (getenv("LF_TC16_SBO")) p.mn_sbo = (unsigned)atoi(getenv("LF_TC16_SBO"));
+    if (getenv("LF_TC16_LT")) p.mn_lt = (unsigned)atoi(getenv("LF_TC16_LT"));
+    if (getenv("LF_TC16_SWZ")) mn_swz = atoi(getenv("LF_TC16_SWZ"));
+  }
+  if ((d.b_mn_major && d.block_n % p.mn_box) || (p.out_elem == 2 && d.block_n % 64)) { set_error("tc_gemm: block_n %d not a multiple of the box width", d.block_n); return LF_ERR_BAD_ARG; }
   p.block_n = d.block_n;
   p.nbatch = d.nbatch;
   p.splits = d.splits < 1 ? 1 : d.splits;
   int kps = div_up(d.K, p.splits);
-  kps = div_up(kps, TC_BLOCK_K) * TC_BLOCK_K;
+  kps = div_up(kps, p.kb_elems) * p.kb_elems;
   p.k_per_split = kps;
   p.a_mn_major = d.a_mn_major; p.b_mn_major = d.b_mn_major;
   for (int b = 0; b < 2; ++b) { p.out[b] = d.out[b < d.nbatch ? b : 0]; p.bias[b] = d.bias[b < d.nbatch ? b : 0]; }
   p.ld_out = d.ld_out; p.split_stride = d.split_stride;
-  bool aligned = (d.ld_out % 4 == 0) && (d.split_stride % 4 == 0) && (d.block_n % 32 == 0);
+  bool aligned = ((d.ld_out * p.out_elem) % 16 == 0) && ((d.split_stride * p.out_elem) % 16 == 0) && (d.block_n % (128 / p.out_elem) == 0);
   for (int b = 0; b < d.nbatch; ++b) aligned = aligned && (((uintptr_t)d.out[b] & 15) == 0) && d.bias[b] == nullptr;
   p.tma_store = aligned ? 1 : 0;
+  if (p.out_elem == 2 && !p.tma_store) { set_error("tc_gemm: bf16 output needs the TMA-store epilogue (16-byte pitch, no bias)"); return LF_ERR_BAD_ARG; }
   p.acc_cols = d.block_n <= 32 ? 32 : d.block_n <= 64 ? 64 : d.block_n <= 128 ? 128 : 256;
   p.tmem_cols = 2 * p.acc_cols;
   p.tile_m = TC_BLOCK_M;
@@ -326,14 +359,14 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   for (int b = 0; b < d.nbatch; ++b) {
     int rc;
     // K-major: inner = K, outer = MN rows, box [32 x rows].  MN-major: inner = MN, outer = K rows, box [32 x 32].
-    rc = d.a_mn_major ? make_map(&mA[b], d.A[b], d.M, d.K, d.lda, 32, TC_BLOCK_K, true)
-                      : make_map(&mA[b], d.A[b], d.K, d.M, d.lda, TC_BLOCK_K, p.tile_m, false);
+    rc = d.a_mn_major ? make_map(&mA[b], d.A[b], d.M, d.K, d.lda, p.mn_box, p.kb_elems, true, p.elem, mn_swz)
+                      : make_map(&mA[b], d.A[b], d.K, d.M, d.lda, p.kb_elems, p.tile_m, false, p.elem);
     if (rc) return rc;
-    rc = d.b_mn_major ? make_map(&mB[b], d.B[b], d.N, d.K, d.ldb, 32, TC_BLOCK_K, true)
-                      : make_map(&mB[b], d.B[b], d.K, d.N, d.ldb, TC_BLOCK_K, d.block_n, false);
+    rc = d.b_mn_major ? make_map(&mB[b], d.B[b], d.N, d.K, d.ldb, p.mn_box, p.kb_elems, true, p.elem, mn_swz)
+                      : make_map(&mB[b], d.B[b], d.K, d.N, d.ldb, p.kb_elems, d.block_n, false, p.elem);
     if (rc) return rc;
     if (p.tma_store) {
-      rc = make_store_map(&mO[b], d.out[b], d.N, d.M, d.ld_out, p.splits, d.split_stride);
+      rc = make_store_map(&mO[b], d.out[b], d.N, d.M, d.ld_out, p.splits, d.split_stride, p.out_elem);
       if (rc) return rc;
     } else {
       mO[b] = mA[b];
@@ -363,6 +396,19 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
 
 // Test hook (no reference counterpart): one tensor-pipe GEMM through the C ABI so the kernel can be
 // checked in isolation.  out(M,N) = A*B (+bias) with the operand orientations described in lf_tc.cuh.
+// Same hook for bf16 operands (A, B bf16; out fp32, or bf16 when out_bf16 != 0).
+extern "C" int lf_debug_tc_gemm16(const void* A, const void* B, void* out, int32_t M, int32_t N, int32_t K, int32_t lda,
+                                  int32_t ldb, int32_t ld_out, int32_t a_mn_major, int32_t b_mn_major, int32_t block_n,
+                                  int32_t splits, int64_t split_stride, int32_t out_bf16, void* stream) {
+  lf::TcGemmDesc d;
+  d.nbatch = 1;
+  d.A[0] = d.A[1] = A; d.B[0] = d.B[1] = B; d.bias[0] = d.bias[1] = nullptr; d.out[0] = d.out[1] = out;
+  d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ld_out = ld_out;
+  d.a_mn_major = a_mn_major; d.b_mn_major = b_mn_major; d.block_n = block_n;
+  d.splits = splits; d.split_stride = split_stride; d.elem = 2; d.out_elem = out_bf16 ? 2 : 4; d.name = "tc_gemm16_debug";
+  return lf::tc_gemm(d, (cudaStream_t)stream);
+}
+
 extern "C" int lf_debug_tc_gemm(const float* A, const float* B, const float* bias, float* out, int32_t M, int32_t N,
                                 int32_t K, int32_t lda, int32_t ldb, int32_t ld_out, int32_t a_mn_major,
                                 int32_t b_mn_major, int32_t block_n, int32_t splits, int64_t split_stride,
@@ -371,6 +417,7 @@ extern "C" int lf_debug_tc_gemm(const float* A, const float* B, const float* bia
   d.nbatch = 1;
   d.A[0] = A; d.B[0] = B; d.bias[0] = bias; d.out[0] = out;
   d.A[1] = A; d.B[1] = B; d.bias[1] = bias; d.out[1] = out;
+  d.elem = 4; d.out_elem = 4;
   d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ld_out = ld_out;
   d.a_mn_major = a_mn_major; d.b_mn_major = b_mn_major; d.block_n = block_n;
   d.splits = splits; d.split_stride = split_stride; d.balance_m = 0; d.name = "tc_gemm_debug";

@@ -16,9 +16,16 @@ struct TcGemmParams {
   int tmem_cols;           // 2 * acc_cols (double-buffered)
   int a_mn_major, b_mn_major;
   int tma_store;           // epilogue writes through cp.async.bulk.tensor (needs a 16-byte output pitch)
+  int elem;                // operand element size: 4 = fp32 consumed as TF32, 2 = bf16
+  int out_elem;            // output element size (TMA-store epilogue): 4 = fp32, 2 = bf16
+  int kb_elems;            // K elements per stage (128 B per operand row): 32 / 64
+  int umma_k;              // K elements per tcgen05.mma: 8 / 16
+  int mn_box;              // MN elements per MN-major TMA box (128 B): 32 / 64
+  int mn_box_bytes;        // bytes of one MN-major box: 128 B x kb_elems rows
+  unsigned mn_step, mn_lbo, mn_sbo, mn_lt;   // MN-major UMMA descriptor: bytes per instruction, LBO, SBO, layout type
   int tile_m;              // rows per M tile (<= 128): A box rows; smaller tiles balance the item count over the SMs
   int m_tiles, n_tiles, total_items;
-  float* out[2];
+  void* out[2];
   const float* bias[2];
   long long ld_out;        // output row pitch (elements)
   long long split_stride;  // elements between split partials
@@ -31,17 +38,19 @@ struct TcGemmParams {
 //   b_mn_major = 1: B is (K x N) row-major with pitch ldb (N contiguous)
 struct TcGemmDesc {
   int nbatch;
-  const float* A[2];
-  const float* B[2];
+  const void* A[2];        // fp32 or bf16 (elem)
+  const void* B[2];
   const float* bias[2];
-  float* out[2];
+  void* out[2];            // fp32, or bf16 when out_elem == 2
   int M, N, K;
   long long lda, ldb, ld_out;
   int a_mn_major, b_mn_major;
   int block_n;
   int splits;
   long long split_stride;
-  int balance_m;           // 1: pick tile_m so that the number of work items is a multiple of the SM count (K-major A, plain-store epilogue only)
+  int elem = 4;            // 4 = fp32 operands (TF32 MMA), 2 = bf16 operands
+  int out_elem = 4;        // 4 = fp32 output, 2 = bf16 output (TMA-store epilogue only)
+  int balance_m = 0;           // 1: pick tile_m so that the number of work items is a multiple of the SM count (K-major A, plain-store epilogue only)
   const char* name;
 };
 

@@ -98,6 +98,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// instruction descriptor for kind::f16 with bf16 operands, fp32 accumulate
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int a_mn, int b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;                         // c_format = F32
+  d |= 1u << 7;                         // a_format = BF16
+  d |= 1u << 10;                        // b_format = BF16
+  d |= (uint32_t)(a_mn & 1) << 15;
+  d |= (uint32_t)(b_mn & 1) << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(m >> 4) << 24;
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -125,8 +144,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// host: 2-D fp32 tensor map (lf_tc.cu)
-int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_inner,
-             int box_outer, bool mn_major);
+// host: 2-D tensor map (lf_tc.cu).  elem = 4 (fp32, consumed as TF32) or 2 (bf16); mn_swizzle: CUtensorMapSwizzle of
+// MN-major boxes (0 = default for the element type)
+int make_map(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_inner,
+             int box_outer, bool mn_major, int elem = 4, int mn_swizzle = 0);
 
 }  // namespace lf

@@ -57,3 +57,38 @@ def test_tc_gemm_dweight_orientation(M, N, K, bn, splits):
     got = run(dZ[:, :M], F, None, M, N, K, 1, 1, bn, splits)
     ref = dZ[:, :M].double().T @ F.double()
     assert relerr(got, ref) < 5e-3, relerr(got, ref)
+
+
+# ---------------------------------------------------------------- bf16 operands (kind::f16), fp32 accumulate
+def run16(A, B, M, N, K, a_mn, b_mn, block_n, splits=1, out_bf16=False):
+    """A: (M,K) values, B: (K,N) values, both already rounded to bf16; stored in the orientation under test."""
+    from multimodal_clinical_b200 import _lib
+    lib = _lib.load()
+    As = A.t().contiguous() if a_mn else A.contiguous()
+    Bs = B.contiguous() if b_mn else B.t().contiguous()
+    out = torch.full((splits, M, N), float("nan"), device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    rc = lib.lf_debug_tc_gemm16(As.data_ptr(), Bs.data_ptr(), out.data_ptr(), M, N, K, As.stride(0), Bs.stride(0), N, a_mn, b_mn,
+                                block_n, splits, M * N, int(out_bf16), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "lf_debug_tc_gemm16")
+    torch.cuda.synchronize()
+    return out.double().sum(0)
+
+
+@pytest.mark.parametrize("a_mn,b_mn,M,N,K,bn,splits,out16", [
+    (0, 0, 256, 112, 768, 112, 1, False),        # logits: both K-major
+    (0, 0, 1000, 304, 512, 160, 1, False),
+    (0, 1, 256, 768, 104, 256, 1, True),         # dfeat: A K-major (K = padded classes), B MN-major, bf16 out
+    (0, 1, 777, 512, 312, 256, 1, True),
+    (0, 1, 130, 128, 8, 64, 1, False),
+    (1, 1, 104, 768, 4096, 256, 4, False),       # dweight: both MN-major, split-K partials
+    (1, 1, 312, 512, 700, 256, 2, False),
+    (1, 1, 8, 64, 300, 64, 1, False),
+])
+def test_tc_gemm_bf16_orientations(a_mn, b_mn, M, N, K, bn, splits, out16):
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(K, N, device="cuda") / K ** 0.5).bfloat16()
+    got = run16(A, B, M, N, K, a_mn, b_mn, bn, splits, out16)
+    ref = A.double() @ B.double()
+    tol = 6e-3 if out16 else 1e-5                # bf16 output rounding vs exact fp32 accumulation of bf16 products
+    assert relerr(got, ref) < tol, relerr(got, ref)
