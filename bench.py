@@ -61,19 +61,19 @@ def resnet18_conv_shapes(in_ch):
     return s
 
 
-def step_alg_bytes_per_sample(w):
+def step_alg_bytes_per_sample(w, fe=4):
     """SURVEY.md §8(d) algorithmic bytes per sample (fp32): read f, write df, write the returned logits,
     label (+idx).  The QMF step is two-pass by construction (mid-step global dependency), so it adds one
     more read of f (§8d: 'a two-pass design must report +M*D*4')."""
     M, D, C = 2, w["D"], w["C"]
     n_out = 4 if w["mode"] == "qmf" else 3
-    b = M * D * 4 + (M * D * 4 if w["dfeat"] else 0) + n_out * C * 4 + 8
+    b = M * D * fe + (M * D * fe if w["dfeat"] else 0) + n_out * C * 4 + 8      # fe: bytes per feature element (2 in bf16 mode)
     if w["mode"] == "qmf":
-        b += 8 + M * D * 4
+        b += 8 + M * D * fe
     return b
 
 
-def kernel_alg_bytes(name, w, B):
+def kernel_alg_bytes(name, w, B, fe=4):
     """Algorithmic HBM bytes of ONE launch of kernel `name`: every input read once + every output written once
     (DESIGN.md §4).  k = number of dL/dlogits matrices (1 for mean fusion: dz1 == dz2; 2 for QMF)."""
     D, C = w["D"], w["C"]
@@ -81,15 +81,17 @@ def kernel_alg_bytes(name, w, B):
     ldz = (C + 3) // 4 * 4
     k = 2 if w["mode"] == "qmf" else 1
     n_out = 4 if w["mode"] == "qmf" else 3
-    logits = 2 * (B * D + C * D + C + B * C) * f
-    dfeat = (k * B * ldz + 2 * C * D + 2 * B * D) * f
-    dweight = (k * B * ldz + 2 * B * D + 2 * C * D) * f
+    if fe == 2:
+        ldz = (C + 7) // 8 * 8
+    logits = 2 * (B * D + C * D) * fe + 2 * (C + B * C) * f
+    dfeat = (k * B * ldz + 2 * C * D + 2 * B * D) * fe
+    dweight = (k * B * ldz + 2 * B * D) * fe + 2 * C * D * f
     table = {
         "sgemm_logits": logits, "tc_logits": logits,
         "tc_heads_forward": (2 * B * D + 2 * C * D + n_out * B * C) * f + 8 * B,
         "rows_forward_qmf": (2 * B * C + 2 * B * C + 2 * B + 4 * B) * f + 8 * B,
-        "rows_forward_jlogits": (2 * B * C + B * C + B * ldz) * f + 8 * B,
-        "rows_backward_qmf": (2 * B * C + 2 * B * ldz + 8 * B) * f + 8 * B,
+        "rows_forward_jlogits": (2 * B * C + B * C) * f + B * ldz * fe + 8 * B,
+        "rows_backward_qmf": (2 * B * C + 8 * B) * f + 2 * B * ldz * fe + 8 * B,
         "rows_calibrated": 2 * B * C * f + 8 * B,
         "sgemm_dfeat": dfeat, "tc_dfeat": dfeat,
         "sgemm_dweight": dweight, "tc_dweight": dweight,
@@ -229,7 +231,8 @@ def workload_config(w, args, world):
     return {"workload": f"{args.workload}: {w['desc']}", "head": w["mode"], "batch_per_gpu": w["B"],
             "global_batch": w["B"] * world, "feature_dim": w["D"], "classes": w["C"], "history_len": w["N"],
             "precision": args.precision, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
-            "l2": ("inputs rotate over buffer sets totalling > 2x the 126 MB L2" if 2 * w["B"] * w["D"] * 4 * 8 >= 2 * L2_BYTES
+            "l2": ("inputs rotate over buffer sets totalling > 2x the 126 MB L2"
+                   if 2 * w["B"] * w["D"] * (2 if args.precision == "bf16" else 4) * 8 >= 2 * L2_BYTES
                    else "256 MB L2 flush between steps, outside the per-step CUDA-event brackets")}
 
 
@@ -266,7 +269,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="k4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32"],
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "bf16"],
                     help="auto: tf32 tensor pipe for wide heads (C >= 32), exact fp32 FMA for narrow heads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying CUDA graphs")
@@ -301,7 +304,8 @@ def main():
     eng = LateFusionStep(w["C"], mode=w["mode"], n_data=w["N"], device=dev, precision=args.precision)
     W, b = head_params(w)
     W = [x.to(dev) for x in W]; b = [x.to(dev) for x in b]
-    in_bytes = 2 * w["B"] * w["D"] * 4
+    fe = 2 if args.precision == "bf16" else 4
+    in_bytes = 2 * w["B"] * w["D"] * fe
     need_sets = max(2, -(-2 * L2_BYTES // in_bytes))
     # few, large sets: rotating over them keeps every step's inputs out of L2.  Small workloads would need
     # hundreds of sets; they use 8 and an explicit L2 flush (256 MB fill) between steps, outside the per-step
@@ -310,6 +314,9 @@ def main():
     n_sets = min(need_sets, 8)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if flush_l2 else None
     host_sets = make_batches(w, n_sets, dev, seed=100 + rank)
+    if fe == 2:            # bf16 mode: the features exist in bf16 on the host too (encoder outputs under autocast)
+        for hs in host_sets:
+            hs["f1"] = hs["f1"].bfloat16(); hs["f2"] = hs["f2"].bfloat16()
     dev_sets = [{k: v.to(dev) for k, v in s.items()} for s in host_sets]
     enc_grads = None
     if w["modulate"]:
@@ -456,21 +463,21 @@ def main():
         dom = max(kern, key=lambda k: kern[k]["share"]) if kern else None
         roof = None
         if dom:
-            ab = kernel_alg_bytes(dom, w, w["B"])
+            ab = kernel_alg_bytes(dom, w, w["B"], fe)
             ach = ab / (kern[dom]["avg_us"] * 1e-6) / 1e9 if ab else None
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (ach / hbm_peak) if ach else None,
                     "traffic": measured_traffic(args.workload, args.precision, dom), "peak_source": peak_src,
                     "alg_bytes_per_launch": ab, "avg_launch_us": kern[dom]["avg_us"], "share_of_step": kern[dom]["share"]}
-        step_bytes = step_alg_bytes_per_sample(w) * w["B"]
+        step_bytes = step_alg_bytes_per_sample(w, fe) * w["B"]
         step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
         line = {"metric": "fusion_step_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
+                "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
                 "data": "synthetic", "config": workload_config(w, args, world),
                 "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
-                "step_roofline": {"alg_bytes_per_sample": step_alg_bytes_per_sample(w), "achieved": step_gbs,
+                "step_roofline": {"alg_bytes_per_sample": step_alg_bytes_per_sample(w, fe), "achieved": step_gbs,
                                   "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak},
                 "kernels": {k: {"launches": v["launches"], "avg_us": round(v["avg_us"], 2), "share": round(v["share"], 4)}
                             for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["share"])}}

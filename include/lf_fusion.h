@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 4
+#define LF_ABI_VERSION 5
 
 /* error codes */
 #define LF_OK 0
@@ -35,6 +35,10 @@ extern "C" {
 /* arithmetic of the three head GEMMs */
 #define LF_PREC_FP32 0 /* exact fp32 FMA; parity 1e-5 */
 #define LF_PREC_TF32 1 /* tcgen05 kind::tf32 tensor pipe (wide heads); parity 2e-2 like the reference's bf16-mixed */
+#define LF_PREC_BF16 2 /* the reference's own mode (Trainer precision "bf16-mixed", utils/run_trainer.py:47): features, dfeat
+                          and the dL/dlogits scratch are bf16 in HBM (half the bytes), heads are cast to bf16 per step like
+                          autocast does, tcgen05 kind::f16 with fp32 accumulation; logits, losses, statistics and head
+                          gradients stay fp32.  Wide heads only (C >= 32); dim and ld_dlogits multiples of 8.  Parity 2e-2 */
 
 /* OGM-GE modulation (existing_algos/OGM_GE.py:48-54) */
 #define LF_MOD_OGM_GE 0 /* g <- k g + N(0, std(g)+1e-8) */
@@ -69,7 +73,7 @@ typedef struct LfHeadsArgs {
   int32_t precision;    /* LF_PREC_* */
   int32_t need_dfeat;   /* 0: encoders frozen (enrico/joint_model.py:36-38), dfeat not produced */
   int32_t ld_dlogits;   /* row pitch (elements) of dlogits; 0 = classes.  LF_PREC_TF32 needs a multiple of 4 (TMA) */
-  const float* feat[2];   /* (B,D) pooled encoder features  cremad/joint_model_qmf.py:48-55 */
+  const float* feat[2];   /* (B,D) pooled encoder features  cremad/joint_model_qmf.py:48-55.  LF_PREC_BF16: bf16 data */
   const float* weight[2]; /* (C,D) x{1,2}_classifier.weight cremad/joint_model_qmf.py:26,28 */
   const float* bias[2];   /* (C)   x{1,2}_classifier.bias */
   const int64_t* label;   /* (B) */
@@ -77,8 +81,8 @@ typedef struct LfHeadsArgs {
   float* avg_logits;      /* out (B,C) (x1+x2)/2            cremad/joint_model_qmf.py:73 */
   float* logits_df;       /* out (B,C) QMF only             existing_algos/QMF.py:115-117 */
   float* conf;            /* out (2,B) QMF only: log(sum(exp z))/10  existing_algos/QMF.py:113-114 */
-  float* dlogits[2];      /* scratch (B,C) each: dL/dz_m.  JLOGITS uses dlogits[0] only (dz1 == dz2) */
-  float* dfeat[2];        /* out (B,D) dL/df_m, or NULL when need_dfeat == 0 */
+  float* dlogits[2];      /* scratch (B,ld_dlogits) each: dL/dz_m.  JLOGITS uses dlogits[0] only (dz1 == dz2).  LF_PREC_BF16: bf16 */
+  float* dfeat[2];        /* out (B,D) dL/df_m, or NULL when need_dfeat == 0.  LF_PREC_BF16: bf16 data */
   float* dweight[2];      /* out (C,D) LOCAL-shard dL/dW_m (host all-reduces across GPUs) */
   float* dbias[2];        /* out (C) */
   const float* qmf_g;     /* in  (2,B) dL_reg/dconf from lf_qmf_history_step (QMF backward only) */

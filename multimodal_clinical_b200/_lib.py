@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lf_fusion.so")
 
 LF_MODE_JLOGITS, LF_MODE_QMF = 0, 1
-LF_PREC_FP32, LF_PREC_TF32 = 0, 1
+LF_PREC_FP32, LF_PREC_TF32, LF_PREC_BF16 = 0, 1, 2
 LF_MOD_OGM_GE, LF_MOD_OGM, LF_MOD_NOISE = 0, 1, 2
 LF_STATS_HEADER = 16
 LF_MAX_TENSORS = 64

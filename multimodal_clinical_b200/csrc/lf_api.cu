@@ -17,6 +17,7 @@
 namespace lf {
 int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* dbpart, float* rowstat, cudaStream_t s);  // lf_tc_fwd.cu
 int tc_forward_parts(int B);
+int cast_weights_bf16(const float* w0, const float* w1, void* out, size_t n, cudaStream_t s);   // lf_gemm.cu
 // lf_narrow.cu
 int narrow_tile(int C, int D, bool fwd_only);
 size_t narrow_dw_floats(int C, int D);
@@ -89,6 +90,7 @@ HeadsWorkspace carve_heads_workspace(void* base, int B, int D, int C) {
   w.dw_partials = (float*)take((size_t)2 * kMaxSplits * C * D * sizeof(float));
   w.db_partials = (float*)take((size_t)part_rows * 2 * C * sizeof(float));
   w.cal_partials = (float*)take((size_t)kMaxRowBlocks * 2 * sizeof(float));
+  w.w16 = take((size_t)2 * C * D * 2);
   w.narrow_dw = narrow_tile(C, D, false) > 0 ? (float*)take(narrow_dw_floats(C, D) * sizeof(float)) : nullptr;
   w.total = off + (size_t)B * 4 * sizeof(float) + 256;  // + rowstat
   return w;
@@ -100,7 +102,8 @@ static float* rowstat_ptr(void* base, int B, int D, int C) {
 }
 
 // The tensor pipe only pays for wide heads (C = 6/20 is HBM-bound on FMA).
-static bool use_tensor_pipe(const LfHeadsArgs* a) { return a->precision == LF_PREC_TF32 && a->classes >= 32; }
+static bool use_tensor_pipe(const LfHeadsArgs* a) { return a->precision != LF_PREC_FP32 && a->classes >= 32; }
+static bool is_bf16(const LfHeadsArgs* a) { return a->precision == LF_PREC_BF16; }
 // Narrow heads (C <= 32, HBM-bound on FMA): one fused kernel per pass over the features (lf_narrow.cu).
 static bool use_narrow(const LfHeadsArgs* a) {
   return !use_tensor_pipe(a) && a->classes <= 32 && narrow_tile(a->classes, a->dim, false) > 0 && !getenv("LF_NO_NARROW");
@@ -126,7 +129,11 @@ static int check_heads(const LfHeadsArgs* a, bool backward) {
     return LF_ERR_BAD_ARG;
   }
   if (a->mode != LF_MODE_JLOGITS && a->mode != LF_MODE_QMF) { set_error("bad mode %d", a->mode); return LF_ERR_BAD_ARG; }
-  if (a->precision != LF_PREC_FP32 && a->precision != LF_PREC_TF32) { set_error("bad precision %d", a->precision); return LF_ERR_BAD_ARG; }
+  if (a->precision != LF_PREC_FP32 && a->precision != LF_PREC_TF32 && a->precision != LF_PREC_BF16) { set_error("bad precision %d", a->precision); return LF_ERR_BAD_ARG; }
+  if (a->precision == LF_PREC_BF16 && (a->classes < 32 || a->dim % 8 || a->ld_dlogits % 8 || a->ld_dlogits == 0)) {
+    set_error("LF_PREC_BF16 needs classes >= 32 and dim / ld_dlogits multiples of 8 (got C=%d D=%d ld=%d)", a->classes, a->dim, a->ld_dlogits);
+    return LF_ERR_UNSUPPORTED;
+  }
   for (int m = 0; m < 2; ++m)
     if (!a->feat[m] || !a->weight[m] || !a->bias[m] || !a->logits[m] || !a->dweight[m] || !a->dbias[m]) {
       set_error("null per-modality pointer (modality %d)", m);
@@ -160,6 +167,7 @@ static RowsArgs rows_args(const LfHeadsArgs* a, const HeadsWorkspace& w) {
   r.dbpart = w.db_partials; r.calpart = w.cal_partials;
   r.B = a->batch; r.B_global = a->batch_global; r.C = a->classes;
   r.ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
+  r.dz_bf16 = a->precision == LF_PREC_BF16;
   r.nb_total = row_blocks(a->batch);
   return r;
 }
@@ -231,14 +239,24 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
     finalize_forward_stats(w.row_partials, grid, a->classes, a->stats, s);
     return check_launch("finalize_stats");
   }
-  if (use_tensor_pipe(a) && a->classes <= 256 && getenv("LF_FUSED_FWD")) {
+  if (use_tensor_pipe(a) && !is_bf16(a) && a->classes <= 256 && getenv("LF_FUSED_FWD")) {
     // logits GEMMs + all per-sample forward math in one kernel (lf_tc_fwd.cu)
     return tc_heads_forward(a, w.row_partials, w.db_partials, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), s);
   }
   if (use_tensor_pipe(a)) {
     TcGemmDesc d;
     d.nbatch = 2;
-    for (int m = 0; m < 2; ++m) { d.A[m] = a->feat[m]; d.B[m] = a->weight[m]; d.bias[m] = a->bias[m]; d.out[m] = a->logits[m]; }
+    const size_t cd = (size_t)a->classes * a->dim;
+    if (is_bf16(a)) {
+      rc = cast_weights_bf16(a->weight[0], a->weight[1], w.w16, cd, s);       // what autocast does for nn.Linear every step
+      if (rc) return rc;
+      d.elem = 2;
+    }
+    for (int m = 0; m < 2; ++m) {
+      d.A[m] = a->feat[m];
+      d.B[m] = is_bf16(a) ? (const void*)((const char*)w.w16 + m * cd * 2) : (const void*)a->weight[m];
+      d.bias[m] = a->bias[m]; d.out[m] = a->logits[m];
+    }
     d.M = a->batch; d.N = a->classes; d.K = a->dim;
     d.lda = a->dim; d.ldb = a->dim; d.ld_out = a->classes;
     d.a_mn_major = 0; d.b_mn_major = 0; d.block_n = tc_block_n(a->classes);
@@ -294,10 +312,15 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     if (tc) {
       TcGemmDesc d;
       d.nbatch = 2;
-      for (int m = 0; m < 2; ++m) { d.A[m] = dz[m]; d.B[m] = a->weight[m]; d.bias[m] = nullptr; d.out[m] = a->dfeat[m]; }
+      if (is_bf16(a)) { d.elem = 2; d.out_elem = 2; }
+      for (int m = 0; m < 2; ++m) {
+        d.A[m] = dz[m];
+        d.B[m] = is_bf16(a) ? (const void*)((const char*)w.w16 + (size_t)m * a->classes * a->dim * 2) : (const void*)a->weight[m];
+        d.bias[m] = nullptr; d.out[m] = a->dfeat[m];
+      }
       d.M = a->batch; d.N = a->dim; d.K = a->classes;
       d.lda = ldz; d.ldb = a->dim; d.ld_out = a->dim;
-      d.a_mn_major = 0; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 32) * 32;
+      d.a_mn_major = 0; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 64) * 64;
       d.splits = 1; d.split_stride = 0; d.balance_m = 0; d.name = "tc_dfeat";
       rc = tc_gemm(d, s);
     } else {
@@ -316,10 +339,11 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   if (tc) {
     TcGemmDesc d;
     d.nbatch = 2;
+    if (is_bf16(a)) d.elem = 2;
     for (int m = 0; m < 2; ++m) { d.A[m] = dz[m]; d.B[m] = a->feat[m]; d.bias[m] = nullptr; d.out[m] = w.dw_partials + (size_t)m * kMaxSplits * cd; }
     d.M = a->classes; d.N = a->dim; d.K = a->batch;
     d.lda = ldz; d.ldb = a->dim; d.ld_out = a->dim;
-    d.a_mn_major = 1; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 32) * 32;
+    d.a_mn_major = 1; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 64) * 64;
     // split-K so that (C tiles x D tiles x 2 modalities x splits) covers the 148 SMs about once or twice
     const int tiles = div_up(a->classes, 128) * div_up(a->dim, d.block_n) * 2;
     splits = 148 / tiles;                    // floor: one full wave, no second-wave tail
@@ -337,7 +361,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   rc = reduce_splits2(w.dw_partials, a->dweight[0], a->dweight[1], splits, kMaxSplits, cd, s);
   if (rc) return rc;
   // db_m (column sums of dZ_m, accumulated by the kernel that produced dZ) and the calibrated counts
-  const bool fused_fwd = tc && a->classes <= 256 && getenv("LF_FUSED_FWD");
+  const bool fused_fwd = tc && !is_bf16(a) && a->classes <= 256 && getenv("LF_FUSED_FWD");
   const int nb_db = (a->mode == LF_MODE_JLOGITS && fused_fwd) ? tc_forward_parts(a->batch) : row_blocks(a->batch);
   return finalize_db_cal(w.db_partials, nb_db, a->classes, w.cal_partials, row_blocks(a->batch), a->dbias[0], a->dbias[1],
                          a->stats, s);

@@ -70,6 +70,7 @@ struct HeadsWorkspace {
   float* dw_partials;    // [2][splits][C][D]
   float* db_partials;    // [part_rows][2][C]  column sums of dz per producing CTA
   float* cal_partials;   // [kMaxRowBlocks][2]
+  void* w16;             // [2][C][D] bf16 copy of the head weights (LF_PREC_BF16: autocast's per-step cast)
   float* narrow_dw;      // [2][148][C*D] per-CTA dW partials of the fused narrow-head kernel (C <= 32), else null
   size_t total;
 };

@@ -5,6 +5,7 @@
 // This is the LF_PREC_FP32 path: plain FFMA, sequential k order inside a tile, deterministic.
 // The narrow-head fused kernels (lf_narrow.cu) and the tcgen05 path (lf_tc.cu) replace it where they
 // apply; this file stays as the generic, always-correct implementation.
+#include <cuda_bf16.h>
 #include "lf_common.cuh"
 #include "lf_gemm.cuh"
 
@@ -110,6 +111,17 @@ int gemm_dweight(GemmArgs g, int nbatch, cudaStream_t s) {
   g.name = "sgemm_dweight";
   if (g.M <= 16) return launch<false, false, 1, 4>(g, nbatch, s);
   return launch<false, false, 4, 4>(g, nbatch, s);
+}
+
+// fp32 head weights -> bf16 [2][n] (LF_PREC_BF16): the per-step cast autocast performs for nn.Linear
+__global__ void cast_weights_bf16_kernel(const float* __restrict__ w0, const float* __restrict__ w1, __nv_bfloat16* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[(size_t)blockIdx.y * n + i] = __float2bfloat16_rn((blockIdx.y == 0 ? w0 : w1)[i]);
+}
+int cast_weights_bf16(const float* w0, const float* w1, void* out, size_t n, cudaStream_t s) {
+  LF_LAUNCH("cast_weights_bf16", s, (cast_weights_bf16_kernel<<<dim3(div_up((long long)n, 256), 2), 256, 0, s>>>(w0, w1, (__nv_bfloat16*)out, n)));
+  return check_launch("cast_weights_bf16");
 }
 
 // dW[c][d] = sum_s part[s][c][d] in fixed order; db[c] = sum_s dbpart[s][c]

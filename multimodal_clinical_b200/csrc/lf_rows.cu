@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
         const float av = (z1[c] + z2[c]) / 2.f;
         const float p = __expf(av - lsea);
         const float d = (p - (c == y ? 1.f : 0.f)) * dz_scale;
-        a.dz[0][(size_t)b * a.ldz + c] = d;
+        store_dz(a, 0, (size_t)b * a.ldz + c, d);
         colsum[2 * C + c] += d;
       }
     }
@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(256) rows_backward_kernel(RowsArgs a) {
         const float pd = __expf((v1 * c1 + v2 * c2) - lsed) - oh;
         const float d1 = ((p1 - oh) + c1 * pd) * invB + g1 * p1;
         const float d2 = ((p2 - oh) + c2 * pd) * invB + g2 * p2;
-        a.dz[0][(size_t)b * a.ldz + c] = d1;
-        a.dz[1][(size_t)b * a.ldz + c] = d2;
+        store_dz(a, 0, (size_t)b * a.ldz + c, d1);
+        store_dz(a, 1, (size_t)b * a.ldz + c, d2);
         dsum[c] += d1;
         dsum[C + c] += d2;
       }

@@ -1,5 +1,6 @@
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include "../../include/lf_fusion.h"
 
@@ -21,8 +22,15 @@ struct RowsArgs {
   double* stats;
   int B, B_global, C;
   int ldz;               // row pitch of dz
+  int dz_bf16;           // 1: dz[] point at bf16 buffers (LF_PREC_BF16): dL/dz is stored rounded to bf16
   int nb_total;          // partial rows the finalize kernels will sum; CTAs zero the rows beyond the grid
 };
+
+// dL/dz store: fp32, or bf16 when the tensor pipe runs kind::f16 (the GEMMs then consume it directly)
+__device__ __forceinline__ void store_dz(const RowsArgs& a, int m, size_t pos, float d) {
+  if (a.dz_bf16) reinterpret_cast<__nv_bfloat16*>(a.dz[m])[pos] = __float2bfloat16_rn(d);
+  else a.dz[m][pos] = d;
+}
 
 __host__ __device__ inline int stat_len_dev(int C) { return LF_STATS_HEADER + 2 * C; }
 

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) rows_forward_reg_kernel(RowsArgs a) {
         const int c = lane + 32 * k;
         if (c < C) {
           const float d = (exp_sub(av[k], lsea * 1.4426950408889634f) - (c == y ? 1.f : 0.f)) * dz_scale;
-          a.dz[0][(size_t)b * a.ldz + c] = d;
+          store_dz(a, 0, (size_t)b * a.ldz + c, d);
           cs3[k] += d;
         }
       }
@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(256) rows_backward_reg_kernel(RowsArgs a) {
           const float pd = exp_sub(v1[k] * c1 + v2[k] * c2, ld) - oh;
           const float d1 = ((p1 - oh) + c1 * pd) * invB + g1 * p1;
           const float d2 = ((p2 - oh) + c2 * pd) * invB + g2 * p2;
-          a.dz[0][(size_t)b * a.ldz + c] = d1;
-          a.dz[1][(size_t)b * a.ldz + c] = d2;
+          store_dz(a, 0, (size_t)b * a.ldz + c, d1);
+          store_dz(a, 1, (size_t)b * a.ldz + c, d2);
           d1s[k] += d1; d2s[k] += d2;
         }
       }

@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, parallel
-from ._lib import (LF_MODE_JLOGITS, LF_MODE_QMF, LF_PREC_FP32, LF_PREC_TF32, LF_STATS_HEADER, STAT,
+from ._lib import (LF_MODE_JLOGITS, LF_MODE_QMF, LF_PREC_BF16, LF_PREC_FP32, LF_PREC_TF32, LF_STATS_HEADER, STAT,
                    LfHeadsArgs, LfMidArgs, LfQmfArgs, LfTensorList, check)
 
 _MOD = {"OGM_GE": _lib.LF_MOD_OGM_GE, "OGM": _lib.LF_MOD_OGM, "noise": _lib.LF_MOD_NOISE}
@@ -32,6 +32,12 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _devc(t: torch.Tensor, dtype, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.LfError(f"{what} must live on a CUDA device: the fused late-fusion step has no CPU path")
+    return (t if t.dtype == dtype else t.to(dtype)).contiguous()
 
 
 def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
@@ -85,7 +91,8 @@ class LateFusionStep:
             raise _lib.LfError("LateFusionStep needs a CUDA device (sm_100a); there is no CPU fallback")
         self.C = int(num_classes)
         self.mode = {"jlogits": LF_MODE_JLOGITS, "ogm_ge": LF_MODE_JLOGITS, "qmf": LF_MODE_QMF}[mode]
-        self.precision = {"fp32": LF_PREC_FP32, "tf32": LF_PREC_TF32}[precision]
+        self.precision = {"fp32": LF_PREC_FP32, "tf32": LF_PREC_TF32, "bf16": LF_PREC_BF16}[precision]
+        self.bf16 = self.precision == LF_PREC_BF16
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.pg = process_group
         self.rank, self.world = parallel.world(process_group)
@@ -147,9 +154,10 @@ class LateFusionStep:
             b["avg"] = torch.empty(B, Cn, device=dev)
             b["zdf"] = torch.empty(B, Cn, device=dev) if qmf else None
             b["conf"] = torch.empty(2, B, device=dev) if qmf else None
-            b["ldz"] = (Cn + 3) // 4 * 4            # dL/dlogits rows padded to 16 B (TMA row pitch, 128-bit access)
-            b["dz"] = torch.zeros(2 if qmf else 1, B, b["ldz"], device=dev)
-            b["dfeat"] = torch.empty(2, B, D, device=dev) if need_dfeat else None
+            fdt = torch.bfloat16 if self.bf16 else torch.float32
+            b["ldz"] = (Cn + 7) // 8 * 8 if self.bf16 else (Cn + 3) // 4 * 4     # dL/dlogits rows padded to 16 B (TMA pitch)
+            b["dz"] = torch.zeros(2 if qmf else 1, B, b["ldz"], device=dev, dtype=fdt)
+            b["dfeat"] = torch.empty(2, B, D, device=dev, dtype=fdt) if need_dfeat else None
             # one flat buffer [dW1 | db1 | dW2 | db2 | cal1 cal2] so the gradient exchange is ONE all-reduce
             n = Cn * D
             b["grad_flat"] = torch.empty((2 * (n + Cn) + 2 + 3) // 4 * 4, device=dev)[:2 * (n + Cn) + 2]   # 16-B padded slot
@@ -166,7 +174,7 @@ class LateFusionStep:
                 b["zdf"] = torch.empty(B, Cn, device=dev)
                 b["conf"] = torch.empty(2, B, device=dev)
             if need_dfeat:
-                b["dfeat"] = torch.empty(2, B, D, device=dev)
+                b["dfeat"] = torch.empty(2, B, D, device=dev, dtype=torch.bfloat16 if self.bf16 else torch.float32)
             b["grad_flat"] = torch.empty((2 * (Cn * D + Cn) + 2 + 3) // 4 * 4, device=dev)[:2 * (Cn * D + Cn) + 2]
             return b
         return self._bufs
@@ -218,7 +226,10 @@ class LateFusionStep:
         and -- QMF -- the History update with the batch's indices, utils/BaseModel.py:1023-1026), without
         gradients; ``update_ema=False`` leaves the calibration state alone like the reference's eval steps."""
         lib = self.lib
-        f = [_f32c(feats[0], "features"), _f32c(feats[1], "features")]
+        if self.bf16:            # features arrive in bf16 (what the encoders emit under autocast); fp32 inputs are rounded once
+            f = [_devc(feats[0], torch.bfloat16, "features"), _devc(feats[1], torch.bfloat16, "features")]
+        else:
+            f = [_f32c(feats[0], "features"), _f32c(feats[1], "features")]
         W = [_f32c(weights[0], "weight"), _f32c(weights[1], "weight")]
         bb = [_f32c(biases[0], "bias"), _f32c(biases[1], "bias")]
         B, D = f[0].shape

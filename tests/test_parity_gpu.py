@@ -297,3 +297,41 @@ def test_modulate_matches_reference_golden():
         eng.modulate(grads, which=which, modulation="OGM", seed=0, offset=0)
         for n, gr in zip(sel, grads):
             assert_close(gr, g["after_OGM/" + n], 1e-6, n)
+
+
+# ---------------------------------------------------------------- LF_PREC_BF16: the reference's bf16-mixed mode
+@pytest.mark.parametrize("mode,B,D,C,N", [("qmf", 1000, 768, 101, 5000), ("jlogits", 515, 512, 309, None), ("qmf", 130, 256, 40, 300)])
+def test_bf16_mode_matches_oracle_on_bf16_rounded_inputs(mode, B, D, C, N):
+    """bf16 features / heads (rounded once, like autocast), fp32 accumulation and fp32 row math.  Checked against the
+    oracle run in fp64 on the same rounded inputs; 2e-2 is BASELINE.json's bf16 tolerance (dz is stored in bf16)."""
+    inp = O.make_inputs(B, D, C, seed=B + C, n_data=N)
+    r16 = lambda x: x.bfloat16().float()
+    f = [r16(inp["f1"]), r16(inp["f2"])]; W = [r16(inp["W1"]), r16(inp["W2"])]; b = [inp["b1"], inp["b2"]]
+    eng = _step(num_classes=C, mode=mode, n_data=N, precision="bf16")
+    hist = O.HistoryState(N) if N else None
+    ema = torch.zeros(2, C, dtype=torch.float64)
+    for s in range(2):
+        if mode == "qmf":
+            ref = O.qmf_step(f, W, b, inp["y"], inp["idx"], hist, ema_x=ema, dtype=torch.float64)
+        else:
+            ref = O.jlogits_step(f, W, b, inp["y"], ema_x=ema, dtype=torch.float64)
+        ema = ref["ema_x"]
+        out = eng.step([x.cuda().bfloat16() for x in f], [inp["W1"].cuda(), inp["W2"].cuda()], [x.cuda() for x in b], inp["y"].cuda(),
+                       idx=inp["idx"].cuda() if N else None)
+        torch.cuda.synchronize()
+        assert out.dfeat[0].dtype == torch.bfloat16
+        assert_close(out.loss, ref["loss"], TOL_TENSOR, "loss")
+        assert_close(out.logits[0], ref["logits"][0], TOL_TENSOR, "z1")
+        for m in range(2):
+            assert_close(out.dweight[m], ref["dW"][m], TOL_TENSOR, f"dW{m+1}")
+            assert_close(out.dbias[m], ref["db"][m], TOL_TENSOR, f"db{m+1}")
+            assert_close(out.dfeat[m].float(), ref["dfeat"][m], TOL_TENSOR, f"df{m+1}")
+        assert_close(eng.ema_x, ref["ema_x"], TOL_TENSOR, "ema_x")
+
+
+def test_bf16_mode_rejects_narrow_heads():
+    from multimodal_clinical_b200 import _lib
+    inp = O.make_inputs(64, 512, 6, seed=1)
+    eng = _step(num_classes=6, mode="jlogits", precision="bf16")
+    with pytest.raises(_lib.LfError):
+        eng.step([inp["f1"].cuda(), inp["f2"].cuda()], [inp["W1"].cuda(), inp["W2"].cuda()], [inp["b1"].cuda(), inp["b2"].cuda()], inp["y"].cuda())
