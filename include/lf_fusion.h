@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 5
+#define LF_ABI_VERSION 6
 
 /* error codes */
 #define LF_OK 0
@@ -77,7 +77,7 @@ typedef struct LfHeadsArgs {
   const float* weight[2]; /* (C,D) x{1,2}_classifier.weight cremad/joint_model_qmf.py:26,28 */
   const float* bias[2];   /* (C)   x{1,2}_classifier.bias */
   const int64_t* label;   /* (B) */
-  float* logits[2];       /* out (B,C) x1_logits, x2_logits */
+  float* logits[2];       /* out (B,C) x1_logits, x2_logits, row pitch ld_logits */
   float* avg_logits;      /* out (B,C) (x1+x2)/2            cremad/joint_model_qmf.py:73 */
   float* logits_df;       /* out (B,C) QMF only             existing_algos/QMF.py:115-117 */
   float* conf;            /* out (2,B) QMF only: log(sum(exp z))/10  existing_algos/QMF.py:113-114 */
@@ -95,6 +95,9 @@ typedef struct LfHeadsArgs {
   int32_t bwd_phase;      /* lf_heads_backward: 0 = everything; 1 = dL/dz, dW, db, calibrated counts (all but dfeat);
                              2 = dfeat only (after a phase-1 call).  Lets the caller start the gradient exchange of
                              dW/db on a second stream while dfeat, which no other rank needs, is still being written. */
+  int32_t ld_logits;      /* row pitch (elements) of logits[0], logits[1]; 0 = classes (dense).  A multiple of 4 lets the
+                             tensor-pipe GEMM write them with TMA stores (1236-byte rows of a dense C = 309 cannot be). */
+  int32_t reserved2;
 } LfHeadsArgs;
 
 /* Bytes of caller-provided scratch the heads calls need. */

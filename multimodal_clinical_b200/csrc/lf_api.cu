@@ -144,6 +144,10 @@ static int check_heads(const LfHeadsArgs* a, bool backward) {
   if (a->need_dfeat && (!a->dfeat[0] || !a->dfeat[1])) { set_error("need_dfeat set but dfeat is null"); return LF_ERR_BAD_ARG; }
   if (backward && !a->ema_offset) { set_error("backward needs ema_offset"); return LF_ERR_BAD_ARG; }
   if (backward && a->mode == LF_MODE_QMF && !a->qmf_g) { set_error("QMF backward needs qmf_g"); return LF_ERR_BAD_ARG; }
+  if (a->ld_logits != 0 && (a->ld_logits < a->classes || (a->ld_logits != a->classes && (!use_tensor_pipe(a) )))) {
+    set_error("ld_logits %d: must be >= classes, and a padded pitch is only supported on the tensor-pipe path", a->ld_logits);
+    return LF_ERR_BAD_ARG;
+  }
   if (a->ld_dlogits != 0 && a->ld_dlogits < a->classes) { set_error("ld_dlogits %d < classes %d", a->ld_dlogits, a->classes); return LF_ERR_BAD_ARG; }
   if (use_tensor_pipe(a) && (a->ld_dlogits % 4 != 0 || a->ld_dlogits == 0)) {
     set_error("LF_PREC_TF32 needs ld_dlogits to be a non-zero multiple of 4 (TMA row pitch), got %d", a->ld_dlogits);
@@ -166,6 +170,7 @@ static RowsArgs rows_args(const LfHeadsArgs* a, const HeadsWorkspace& w) {
   r.partials = w.row_partials; r.stats = a->stats;
   r.dbpart = w.db_partials; r.calpart = w.cal_partials;
   r.B = a->batch; r.B_global = a->batch_global; r.C = a->classes;
+  r.ld_z = a->ld_logits > 0 ? a->ld_logits : a->classes;
   r.ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
   r.dz_bf16 = a->precision == LF_PREC_BF16;
   r.nb_total = row_blocks(a->batch);
@@ -258,8 +263,9 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
       d.bias[m] = a->bias[m]; d.out[m] = a->logits[m];
     }
     d.M = a->batch; d.N = a->classes; d.K = a->dim;
-    d.lda = a->dim; d.ldb = a->dim; d.ld_out = a->classes;
+    d.lda = a->dim; d.ldb = a->dim; d.ld_out = a->ld_logits > 0 ? a->ld_logits : a->classes;
     d.a_mn_major = 0; d.b_mn_major = 0; d.block_n = tc_block_n(a->classes);
+    if (a->classes > d.block_n) d.block_n = div_up(d.block_n, 32) * 32;     // several N tiles: whole 128-byte store chunks
     d.splits = 1; d.split_stride = 0; d.balance_m = 1; d.name = "tc_logits";
     rc = tc_gemm(d, s);
   } else {

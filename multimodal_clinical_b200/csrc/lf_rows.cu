@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
   const float dz_scale = 0.5f / (float)a.B_global;
 
   for (int b = blockIdx.x * nwarp + warp; b < B; b += gridDim.x * nwarp) {
-    const float* __restrict__ z1 = a.z[0] + (size_t)b * C;
-    const float* __restrict__ z2 = a.z[1] + (size_t)b * C;
+    const float* __restrict__ z1 = a.z[0] + (size_t)b * a.ld_z;
+    const float* __restrict__ z2 = a.z[1] + (size_t)b * a.ld_z;
     const int y = (int)a.label[b];
     Lse l1, l2, la;
     l1.init(); l2.init(); la.init();
@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(256) rows_backward_kernel(RowsArgs a) {
   const float invB = 1.f / (float)a.B_global;
   float cal1 = 0.f, cal2 = 0.f;
   for (int b = blockIdx.x * nwarp + warp; b < B; b += gridDim.x * nwarp) {
-    const float* __restrict__ z1 = a.z[0] + (size_t)b * C;
-    const float* __restrict__ z2 = a.z[1] + (size_t)b * C;
+    const float* __restrict__ z1 = a.z[0] + (size_t)b * a.ld_z;
+    const float* __restrict__ z2 = a.z[1] + (size_t)b * a.ld_z;
     const int y = (int)a.label[b];
     float c1 = 0.f, c2 = 0.f, lse1 = 0.f, lse2 = 0.f, lsed = 0.f, g1 = 0.f, g2 = 0.f;
     if (MODE == LF_MODE_QMF) {

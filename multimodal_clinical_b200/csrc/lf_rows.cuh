@@ -21,6 +21,7 @@ struct RowsArgs {
   float* calpart;        // [blocks][2] calibrated-accuracy counts
   double* stats;
   int B, B_global, C;
+  int ld_z;              // row pitch of the input logits z (>= C; padded to 16 B when the tensor pipe TMA-stores them)
   int ldz;               // row pitch of dz
   int dz_bf16;           // 1: dz[] point at bf16 buffers (LF_PREC_BF16): dL/dz is stored rounded to bf16
   int nb_total;          // partial rows the finalize kernels will sum; CTAs zero the rows beyond the grid

@@ -46,13 +46,13 @@ __global__ void __launch_bounds__(256) rows_forward_reg_kernel(RowsArgs a) {
   int b = blockIdx.x * nwarp + warp;
   float n1[NCH], n2[NCH];
   int ny = 0;
-  if (b < B) { load_row<NCH>(a.z[0], a.z[1], (size_t)b * C, C, lane, n1, n2); ny = (int)a.label[b]; }
+  if (b < B) { load_row<NCH>(a.z[0], a.z[1], (size_t)b * a.ld_z, C, lane, n1, n2); ny = (int)a.label[b]; }
   for (; b < B; b += stride) {
     float v1[NCH], v2[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) { v1[k] = n1[k]; v2[k] = n2[k]; }
     const int y = ny;
-    if (b + stride < B) { load_row<NCH>(a.z[0], a.z[1], (size_t)(b + stride) * C, C, lane, n1, n2); ny = (int)a.label[b + stride]; }
+    if (b + stride < B) { load_row<NCH>(a.z[0], a.z[1], (size_t)(b + stride) * a.ld_z, C, lane, n1, n2); ny = (int)a.label[b + stride]; }
 
     float av[NCH];
 #pragma unroll
@@ -189,12 +189,12 @@ __global__ void __launch_bounds__(256) rows_backward_reg_kernel(RowsArgs a) {
 
   int b = blockIdx.x * nwarp + warp;
   float n1[NCH], n2[NCH];
-  if (b < B) load_row<NCH>(a.z[0], a.z[1], (size_t)b * C, C, lane, n1, n2);
+  if (b < B) load_row<NCH>(a.z[0], a.z[1], (size_t)b * a.ld_z, C, lane, n1, n2);
   for (; b < B; b += stride) {
     float v1[NCH], v2[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) { v1[k] = n1[k]; v2[k] = n2[k]; }
-    if (b + stride < B) load_row<NCH>(a.z[0], a.z[1], (size_t)(b + stride) * C, C, lane, n1, n2);
+    if (b + stride < B) load_row<NCH>(a.z[0], a.z[1], (size_t)(b + stride) * a.ld_z, C, lane, n1, n2);
     const int y = (int)a.label[b];
     if (MODE == LF_MODE_QMF) {
       const float c1 = a.conf[b], c2 = a.conf[B + b];

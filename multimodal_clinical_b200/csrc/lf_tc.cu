@@ -59,6 +59,50 @@ __device__ __forceinline__ Item decode_item(const TcGemmParams& p, int item) {
   return it;
 }
 
+// The single MMA-issuing thread.  Everything that does not change per instruction is hoisted: the two
+// shared-memory descriptors are built once (address field = 0) and advanced with one 64-bit add per k-step
+// (the start-address field holds addr >> 4 and never carries out of its 14 bits for a 227 KB window), so the
+// issue loop stays far below the tensor pipe's time per instruction (56-128 cycles).
+//   K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); 32 B of K per instruction.
+//   MN-major: rows are k; fp32: 128B swizzle with 32-byte atoms, 4 k-rows per atom (SBO 512), 32-element MN
+//   chunks 4096 B apart (LBO), 1024 B per instruction; bf16: plain 128B swizzle, 8 k-rows per atom (SBO 1024),
+//   64-element MN chunks 8192 B apart, 2048 B per instruction.
+template <bool TF32>
+__device__ __forceinline__ void mma_issue_loop(const TcGemmParams& p, uint8_t* smem, uint32_t stage_bytes, uint32_t a_bytes,
+                                               uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tmem_full_bar,
+                                               uint64_t* tmem_empty_bar, uint32_t tmem_base) {
+  const int stages = p.stages;
+  const uint32_t idesc = TF32 ? make_idesc_tf32(TC_BLOCK_M, p.block_n, p.a_mn_major, p.b_mn_major)
+                              : make_idesc_bf16(TC_BLOCK_M, p.block_n, p.a_mn_major, p.b_mn_major);
+  const uint64_t descA0 = p.a_mn_major ? make_smem_desc(0, p.mn_lbo, p.mn_sbo, p.mn_lt) : make_smem_desc(0, 16, 1024, 2);
+  const uint64_t descB0 = p.b_mn_major ? make_smem_desc(0, p.mn_lbo, p.mn_sbo, p.mn_lt) : make_smem_desc(0, 16, 1024, 2);
+  const uint64_t stepA = (p.a_mn_major ? p.mn_step : 32u) >> 4, stepB = (p.b_mn_major ? p.mn_step : 32u) >> 4;
+  const uint32_t smem0 = smem_u32(smem);
+  uint32_t it = 0, li = 0, s = 0, ph = 0;
+  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++li) {
+    const Item w = decode_item(p, item);
+    const uint32_t buf = li & 1;
+    mbar_wait(&tmem_empty_bar[buf], ((li >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+    tc_fence_after();
+    const uint32_t acc = tmem_base + buf * (uint32_t)p.acc_cols;
+    int krem = w.k_end - w.k_begin;
+    for (int kb = 0; kb < w.num_kb; ++kb, ++it, krem -= p.kb_elems) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t sa = smem0 + s * stage_bytes;
+      uint64_t da = descA0 + (uint64_t)(sa >> 4), db = descB0 + (uint64_t)((sa + a_bytes) >> 4);
+      const int ksteps = krem >= p.kb_elems ? 4 : (krem + p.umma_k - 1) / p.umma_k;       // 32 B of K per instruction
+      for (int k = 0; k < ksteps; ++k, da += stepA, db += stepB) {
+        if (TF32) umma_tf32(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        else umma_f16(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&empty_bar[s]);               // frees the stage once the MMAs above have read it
+      if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
+    }
+    umma_commit(&tmem_full_bar[buf]);           // accumulator complete
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
@@ -94,14 +138,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;                                       // running k-block counter across items
+      uint32_t s = 0, ph = 0;                                // ring position / phase, carried across items
+      const int a_boxes = TC_BLOCK_M / p.mn_box, b_boxes = p.block_n / p.mn_box;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const Item w = decode_item(p, item);
         const CUtensorMap* mapA = w.batch == 0 ? &mapA0 : &mapA1;
         const CUtensorMap* mapB = w.batch == 0 ? &mapB0 : &mapB1;
-        for (int kb = 0; kb < w.num_kb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
+        for (int kb = 0; kb < w.num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
@@ -111,54 +154,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tma_load_2d(mapA, &full_bar[s], sa, k0, w.m0);                      // [32 k x 128 rows]
           } else {
 #pragma unroll
-            for (int i = 0; i < TC_BLOCK_M / p.mn_box; ++i)                     // [mn_box m x kb_elems k] boxes of 128-B rows
+            for (int i = 0; i < a_boxes; ++i)                                   // [mn_box m x kb_elems k] boxes of 128-B rows
               tma_load_2d(mapA, &full_bar[s], sa + i * p.mn_box_bytes, w.m0 + p.mn_box * i, k0);
           }
           if (!p.b_mn_major) {
             tma_load_2d(mapB, &full_bar[s], sb, k0, w.n0);                      // [32 k x block_n rows]
           } else {
-            for (int i = 0; i < p.block_n / p.mn_box; ++i)
+            for (int i = 0; i < b_boxes; ++i)
               tma_load_2d(mapB, &full_bar[s], sb + i * p.mn_box_bytes, w.n0 + p.mn_box * i, k0);
           }
+          if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = p.elem == 4 ? make_idesc_tf32(TC_BLOCK_M, p.block_n, p.a_mn_major, p.b_mn_major)
-                                         : make_idesc_bf16(TC_BLOCK_M, p.block_n, p.a_mn_major, p.b_mn_major);
-      uint32_t it = 0, li = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++li) {
-        const Item w = decode_item(p, item);
-        const uint32_t buf = li & 1;
-        mbar_wait(&tmem_empty_bar[buf], ((li >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t acc = tmem_base + buf * (uint32_t)p.acc_cols;
-        for (int kb = 0; kb < w.num_kb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
-          const int krem = w.k_end - (w.k_begin + kb * p.kb_elems);
-          const int ksteps = krem >= p.kb_elems ? 4 : (krem + p.umma_k - 1) / p.umma_k;       // 32 B of K per instruction
-          for (int k = 0; k < ksteps; ++k) {
-            // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); step 32 B inside the row.
-            // MN-major SW128/32B-base: rows are k, 128 B = 32 mn each; the atom is 4 k-rows (512 B, SBO),
-            //   32-element MN chunks are 4096 B apart (LBO); one instruction eats 8 k-rows -> step 1024 B.
-            const uint64_t da = p.a_mn_major ? make_smem_desc(sa + k * p.mn_step, p.mn_lbo, p.mn_sbo, p.mn_lt)
-                                             : make_smem_desc(sa + k * 32, 16, 1024, 2);
-            const uint64_t db = p.b_mn_major ? make_smem_desc(sb + k * p.mn_step, p.mn_lbo, p.mn_sbo, p.mn_lt)
-                                             : make_smem_desc(sb + k * 32, 16, 1024, 2);
-            if (p.elem == 4) umma_tf32(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else umma_f16(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[s]);               // frees the stage once the MMAs above have read it
-        }
-        umma_commit(&tmem_full_bar[buf]);           // accumulator complete
-      }
+      if (p.elem == 4) mma_issue_loop<true>(p, smem, stage_bytes, a_bytes, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+      else mma_issue_loop<false>(p, smem, stage_bytes, a_bytes, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
     }
   } else {
     // ===================== epilogue =====================
@@ -181,6 +194,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             float v[32];
             tmem_ld16(acc + c0, v);
             tmem_ld16(acc + c0 + 16, v + 16);
+            const float* bias = p.bias[w.batch];
+            if (bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { const int col = w.n0 + c0 + i; v[i] += col < p.N ? __ldg(bias + col) : 0.f; }
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) pk[i] = w.num_kb == 0 ? 0u : __float_as_uint(v[i]);
           } else {
@@ -334,8 +352,12 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   p.a_mn_major = d.a_mn_major; p.b_mn_major = d.b_mn_major;
   for (int b = 0; b < 2; ++b) { p.out[b] = d.out[b < d.nbatch ? b : 0]; p.bias[b] = d.bias[b < d.nbatch ? b : 0]; }
   p.ld_out = d.ld_out; p.split_stride = d.split_stride;
-  bool aligned = ((d.ld_out * p.out_elem) % 16 == 0) && ((d.split_stride * p.out_elem) % 16 == 0) && (d.block_n % (128 / p.out_elem) == 0);
-  for (int b = 0; b < d.nbatch; ++b) aligned = aligned && (((uintptr_t)d.out[b] & 15) == 0) && d.bias[b] == nullptr;
+  // TMA-store epilogue: 16-byte output pitch; the 128-byte store chunks must tile the N tile exactly unless it is
+  // the only N tile (then the tensor map clips the overhang); bias only for fp32 output
+  const int ccols = 128 / p.out_elem;
+  bool aligned = ((d.ld_out * p.out_elem) % 16 == 0) && ((d.split_stride * p.out_elem) % 16 == 0) &&
+                 (d.block_n % ccols == 0 || d.N <= d.block_n);
+  for (int b = 0; b < d.nbatch; ++b) aligned = aligned && (((uintptr_t)d.out[b] & 15) == 0) && (d.bias[b] == nullptr || p.out_elem == 4);
   p.tma_store = aligned ? 1 : 0;
   if (p.out_elem == 2 && !p.tma_store) { set_error("tc_gemm: bf16 output needs the TMA-store epilogue (16-byte pitch, no bias)"); return LF_ERR_BAD_ARG; }
   p.acc_cols = d.block_n <= 32 ? 32 : d.block_n <= 64 ? 64 : d.block_n <= 128 ? 128 : 256;

@@ -150,7 +150,10 @@ class LateFusionStep:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             qmf = self.mode == LF_MODE_QMF
             b = {}
-            b["logits"] = torch.empty(2, B, Cn, device=dev)
+            # tensor-pipe path: logits rows padded to 16 B so the GEMM epilogue can TMA-store them; callers get views
+            b["ldl"] = (Cn + 3) // 4 * 4 if (self.precision != LF_PREC_FP32 and Cn >= 32) else Cn
+            b["logits_store"] = torch.empty(2, B, b["ldl"], device=dev)
+            b["logits"] = b["logits_store"][:, :, :Cn]
             b["avg"] = torch.empty(B, Cn, device=dev)
             b["zdf"] = torch.empty(B, Cn, device=dev) if qmf else None
             b["conf"] = torch.empty(2, B, device=dev) if qmf else None
@@ -168,7 +171,8 @@ class LateFusionStep:
             # tensors that escape to the caller (autograd, metric lists) get fresh storage every step from
             # torch's caching allocator; scratch (dz, qmf_g, workspace) stays static
             dev, Cn, b = self.device, self.C, dict(self._bufs)
-            b["logits"] = torch.empty(2, B, Cn, device=dev)
+            b["logits_store"] = torch.empty(2, B, b["ldl"], device=dev)
+            b["logits"] = b["logits_store"][:, :, :Cn]
             b["avg"] = torch.empty(B, Cn, device=dev)
             if b["zdf"] is not None:
                 b["zdf"] = torch.empty(B, Cn, device=dev)
@@ -259,10 +263,11 @@ class LateFusionStep:
         a.batch, a.batch_global, a.dim, a.classes = B, Bg, D, Cn
         a.mode, a.precision, a.need_dfeat = self.mode, self.precision, int(need_dfeat)
         a.ld_dlogits = bufs["ldz"]
+        a.ld_logits = bufs["ldl"]
         a.fwd_only = int(not backward)
         for m in range(2):
             a.feat[m] = _ptr(f[m]); a.weight[m] = _ptr(W[m]); a.bias[m] = _ptr(bb[m])
-            a.logits[m] = _ptr(bufs["logits"][m])
+            a.logits[m] = _ptr(bufs["logits_store"][m])
             a.dfeat[m] = _ptr(bufs["dfeat"][m]) if need_dfeat else None
             a.dweight[m] = _ptr(dW[m]); a.dbias[m] = _ptr(db[m])
         a.label = _ptr(label)

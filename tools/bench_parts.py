@@ -32,8 +32,9 @@ def args_for(s):
     h = _lib.LfHeadsArgs()
     h.batch, h.batch_global, h.dim, h.classes = B, B, D, Cn
     h.mode, h.precision, h.need_dfeat, h.ld_dlogits = eng.mode, eng.precision, int(w["dfeat"]), bufs["ldz"]
+    h.ld_logits = bufs["ldl"]
     for m, f in enumerate((s["f1"], s["f2"])):
-        h.feat[m] = _ptr(f); h.weight[m] = _ptr(W[m]); h.bias[m] = _ptr(b[m]); h.logits[m] = _ptr(bufs["logits"][m])
+        h.feat[m] = _ptr(f); h.weight[m] = _ptr(W[m]); h.bias[m] = _ptr(b[m]); h.logits[m] = _ptr(bufs["logits_store"][m])
         h.dfeat[m] = _ptr(bufs["dfeat"][m]) if w["dfeat"] else None
     h.dweight[0] = _ptr(gf[0:n]); h.dbias[0] = _ptr(gf[n:n + Cn]); h.dweight[1] = _ptr(gf[n + Cn:2 * n + Cn]); h.dbias[1] = _ptr(gf[2 * n + Cn:])
     h.label = _ptr(s["y"]); h.avg_logits = _ptr(bufs["avg"]); h.logits_df = _ptr(bufs["zdf"]); h.conf = _ptr(bufs["conf"])
