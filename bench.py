@@ -270,7 +270,8 @@ def main():
     ap.add_argument("--workload", default="k4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "bf16"],
-                    help="auto: tf32 tensor pipe for wide heads (C >= 32), exact fp32 FMA for narrow heads")
+                    help="auto: bf16 (the reference's own bf16-mixed mode: bf16 features, fp32 accumulation) for wide heads "
+                         "(C >= 32), exact fp32 FMA for narrow heads; tf32 = fp32 features consumed as TF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--batch", type=int, default=None, help="override the workload's per-GPU batch (experiments)")
@@ -280,7 +281,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     w = dict(WORKLOADS[args.workload])
     if args.precision == "auto":
-        args.precision = "tf32" if (args.classes or w["C"]) >= 32 else "fp32"
+        args.precision = "bf16" if (args.classes or w["C"]) >= 32 else "fp32"
     if args.batch or args.dim or args.classes:
         w.update(B=args.batch or w["B"], D=args.dim or w["D"], C=args.classes or w["C"])
         w["desc"] += f" [overridden: B={w['B']} D={w['D']} C={w['C']}]"
