@@ -189,17 +189,28 @@ __global__ void __launch_bounds__(256) rows_backward_reg_kernel(RowsArgs a) {
 
   int b = blockIdx.x * nwarp + warp;
   float n1[NCH], n2[NCH];
-  if (b < B) load_row<NCH>(a.z[0], a.z[1], (size_t)b * a.ld_z, C, lane, n1, n2);
+  // the next sample's logits AND its per-row scalars are fetched while the current sample is processed
+  int ny = 0;
+  float nc1 = 0.f, nc2 = 0.f, ng1 = 0.f, ng2 = 0.f;
+  float4 nrs = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch_scalars = [&](int r) {
+    ny = (int)a.label[r];
+    if (MODE == LF_MODE_QMF) {
+      nc1 = a.conf[r]; nc2 = a.conf[B + r];
+      nrs = *reinterpret_cast<const float4*>(a.rowstat + (size_t)r * 4);               // lse1, lse2, lse(z_df)
+      ng1 = a.qmf_g[r]; ng2 = a.qmf_g[B + r];
+    }
+  };
+  if (b < B) { load_row<NCH>(a.z[0], a.z[1], (size_t)b * a.ld_z, C, lane, n1, n2); fetch_scalars(b); }
   for (; b < B; b += stride) {
     float v1[NCH], v2[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) { v1[k] = n1[k]; v2[k] = n2[k]; }
-    if (b + stride < B) load_row<NCH>(a.z[0], a.z[1], (size_t)(b + stride) * a.ld_z, C, lane, n1, n2);
-    const int y = (int)a.label[b];
+    const int y = ny;
+    const float c1 = nc1, c2 = nc2, g1 = ng1 / 10.f, g2 = ng2 / 10.f;
+    const float4 rs = nrs;
+    if (b + stride < B) { load_row<NCH>(a.z[0], a.z[1], (size_t)(b + stride) * a.ld_z, C, lane, n1, n2); fetch_scalars(b + stride); }
     if (MODE == LF_MODE_QMF) {
-      const float c1 = a.conf[b], c2 = a.conf[B + b];
-      const float4 rs = *reinterpret_cast<const float4*>(a.rowstat + (size_t)b * 4);   // lse1, lse2, lse(z_df)
-      const float g1 = a.qmf_g[b] / 10.f, g2 = a.qmf_g[B + b] / 10.f;
       const float l1 = rs.x * 1.4426950408889634f, l2 = rs.y * 1.4426950408889634f, ld = rs.z * 1.4426950408889634f;
 #pragma unroll
       for (int k = 0; k < NCH; ++k) {
