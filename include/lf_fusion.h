@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 6
+#define LF_ABI_VERSION 7
 
 /* error codes */
 #define LF_OK 0
@@ -319,6 +319,23 @@ int lf_ogm_scores(const float* z1, const float* z2, const int64_t* label, int32_
 int lf_debug_tc_gemm16(const void* A, const void* B, void* out, int32_t M, int32_t N, int32_t K, int32_t lda,
                        int32_t ldb, int32_t ld_out, int32_t a_mn_major, int32_t b_mn_major, int32_t block_n,
                        int32_t splits, int64_t split_stride, int32_t out_bf16, void* stream);
+
+/*
+ * SGD(momentum, weight decay) on the head parameters in one launch (utils/BaseModel.py:275-285:
+ * torch.optim.SGD(lr, momentum=0.9, weight_decay=1e-4), dampening 0, no nesterov):
+ *   d = g + wd*p;  buf = first_step ? d : momentum*buf + d;  p -= lr*buf.   Up to 8 tensors (W1,b1,W2,b2).
+ */
+typedef struct LfSgdArgs {
+  int32_t count;
+  int32_t first_step;      /* 1: momentum buffers are initialised with d (torch's first-step behaviour) */
+  float lr, momentum, weight_decay;
+  int32_t reserved;
+  float* param[8];
+  const float* grad[8];
+  float* momentum_buf[8];
+  int64_t numel[8];
+} LfSgdArgs;
+int lf_sgd_heads(const LfSgdArgs* args, void* stream);
 
 /* Last error message of the calling thread (host string). */
 const char* lf_last_error(void);

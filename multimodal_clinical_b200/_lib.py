@@ -74,6 +74,12 @@ class LfMidArgs(C.Structure):
     ]
 
 
+class LfSgdArgs(C.Structure):
+    _fields_ = [("count", C.c_int32), ("first_step", C.c_int32), ("lr", C.c_float), ("momentum", C.c_float),
+                ("weight_decay", C.c_float), ("reserved", C.c_int32), ("param", C.c_void_p * 8), ("grad", C.c_void_p * 8),
+                ("momentum_buf", C.c_void_p * 8), ("numel", C.c_int64 * 8)]
+
+
 LF_QMF_UPDATE_X1, LF_QMF_UPDATE_X2, LF_QMF_REG, LF_QMF_ALL = 1, 2, 4, 7
 
 
@@ -107,6 +113,7 @@ SIGNATURES = {
     "lf_ogm_scores_workspace_bytes": (C.c_size_t, []),
     "lf_ogm_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_size_t, C.c_void_p]),
+    "lf_sgd_heads": (C.c_int, [C.POINTER(LfSgdArgs), C.c_void_p]),
     "lf_launch_count": (C.c_int64, []),
     "lf_profile_enable": (None, [C.c_int32]),
     "lf_profile_report": (C.c_int32, [C.c_char_p, C.c_int32]),

@@ -91,3 +91,45 @@ extern "C" int lf_ogm_scores(const float* z1, const float* z2, const int64_t* la
                                   (float*)((char*)workspace + 256), (unsigned int*)workspace)));
   return check_launch("ogm_scores_kernel");
 }
+
+// ---- SGD(momentum, weight decay) for the head parameters (utils/BaseModel.py:275-285: torch.optim.SGD with
+// momentum 0.9, weight_decay 1e-4, dampening 0, no nesterov), all head tensors in one launch:
+//   d = g + wd * p ;  buf = first ? d : momentum * buf + d ;  p -= lr * buf
+namespace lf {
+struct SgdTable {
+  int count;
+  float* p[8];
+  const float* g[8];
+  float* buf[8];
+  long long n[8];
+};
+__global__ void __launch_bounds__(256) sgd_heads_kernel(SgdTable t, float lr, float momentum, float wd, int first) {
+  const int k = blockIdx.y;
+  if (k >= t.count) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.n[k]; i += (long long)gridDim.x * blockDim.x) {
+    const float pv = t.p[k][i];
+    const float d = fmaf(wd, pv, t.g[k][i]);
+    const float b = first ? d : fmaf(momentum, t.buf[k][i], d);
+    t.buf[k][i] = b;
+    t.p[k][i] = pv - lr * b;
+  }
+}
+}  // namespace lf
+
+extern "C" int lf_sgd_heads(const LfSgdArgs* a, void* stream) {
+  if (!a || a->count < 1 || a->count > 8) { set_error("lf_sgd_heads: bad tensor count"); return LF_ERR_BAD_ARG; }
+  lf::SgdTable t;
+  t.count = a->count;
+  long long maxn = 0;
+  for (int k = 0; k < a->count; ++k) {
+    if (!a->param[k] || !a->grad[k] || !a->momentum_buf[k] || a->numel[k] < 0) { set_error("lf_sgd_heads: bad tensor %d", k); return LF_ERR_BAD_ARG; }
+    t.p[k] = a->param[k]; t.g[k] = a->grad[k]; t.buf[k] = a->momentum_buf[k]; t.n[k] = a->numel[k];
+    if (a->numel[k] > maxn) maxn = a->numel[k];
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int gx = div_up(maxn, 256 * 4);
+  if (gx > 148) gx = 148;
+  if (gx < 1) gx = 1;
+  LF_LAUNCH("sgd_heads", s, (lf::sgd_heads_kernel<<<dim3(gx, a->count), 256, 0, s>>>(t, a->lr, a->momentum, a->weight_decay, a->first_step)));
+  return check_launch("sgd_heads_kernel");
+}

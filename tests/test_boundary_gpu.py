@@ -209,3 +209,24 @@ def test_main_entry_point_trains_food101_qmf_on_synthetic_embeddings(tmp_path, m
               "test_epoch/test_avg_x1_acc"):
         assert k in got and np.isfinite(got[k]), k
     assert 0.0 <= got["test_epoch/test_avg_acc"] <= 1.0
+
+
+def test_fused_head_sgd_matches_torch_sgd():
+    """one-launch SGD(momentum 0.9, wd 1e-4) + StepLR on the head tensors == torch.optim.SGD."""
+    from multimodal_clinical_b200.utils.fused_sgd import FusedHeadSGD
+    torch.manual_seed(0)
+    shapes = [(101, 768), (101,), (101, 768), (101,)]
+    ref = [torch.randn(s, device="cuda", requires_grad=True) for s in shapes]
+    mine = [p.detach().clone().requires_grad_(True) for p in ref]
+    o1 = torch.optim.SGD(ref, lr=0.02, momentum=0.9, weight_decay=1e-4)
+    o2 = FusedHeadSGD(mine, lr=0.02, momentum=0.9, weight_decay=1e-4)
+    s1 = torch.optim.lr_scheduler.StepLR(o1, step_size=2, gamma=0.5)
+    s2 = torch.optim.lr_scheduler.StepLR(o2, step_size=2, gamma=0.5)
+    for step in range(5):
+        for p, q in zip(ref, mine):
+            g = torch.randn_like(p)
+            p.grad = g.clone(); q.grad = g.clone()
+        o1.step(); o2.step(); s1.step(); s2.step()
+        for p, q in zip(ref, mine):
+            assert_close(q, p, 1e-6, f"param after step {step}")
+    assert_close(o2.state[mine[0]]["momentum_buffer"], o1.state[ref[0]]["momentum_buffer"], 1e-6, "momentum buffer")
