@@ -15,8 +15,6 @@
 #include "lf_tc.cuh"
 
 namespace lf {
-int tc_heads_forward(const LfHeadsArgs* a, float* partials, float* dbpart, float* rowstat, cudaStream_t s);  // lf_tc_fwd.cu
-int tc_forward_parts(int B);
 int cast_weights_bf16(const float* w0, const float* w1, void* out, size_t n, cudaStream_t s);   // lf_gemm.cu
 // lf_narrow.cu
 int narrow_tile(int C, int D, bool fwd_only);
@@ -85,7 +83,7 @@ HeadsWorkspace carve_heads_workspace(void* base, int B, int D, int C) {
   char* p = (char*)base;
   size_t off = 0;
   auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes, 256); return r; };
-  const int part_rows = div_up(B, 128) + 148 > kMaxRowBlocks ? div_up(B, 128) + 148 : kMaxRowBlocks;   // fused forward: one row per tile
+  const int part_rows = kMaxRowBlocks;
   w.row_partials = (float*)take((size_t)part_rows * stat_len(C) * sizeof(float));
   w.dw_partials = (float*)take((size_t)2 * kMaxSplits * C * D * sizeof(float));
   w.db_partials = (float*)take((size_t)part_rows * 2 * C * sizeof(float));
@@ -244,10 +242,6 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
     finalize_forward_stats(w.row_partials, grid, a->classes, a->stats, s);
     return check_launch("finalize_stats");
   }
-  if (use_tensor_pipe(a) && !is_bf16(a) && a->classes <= 256 && getenv("LF_FUSED_FWD")) {
-    // logits GEMMs + all per-sample forward math in one kernel (lf_tc_fwd.cu)
-    return tc_heads_forward(a, w.row_partials, w.db_partials, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), s);
-  }
   if (use_tensor_pipe(a)) {
     TcGemmDesc d;
     d.nbatch = 2;
@@ -367,8 +361,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   rc = reduce_splits2(w.dw_partials, a->dweight[0], a->dweight[1], splits, kMaxSplits, cd, s);
   if (rc) return rc;
   // db_m (column sums of dZ_m, accumulated by the kernel that produced dZ) and the calibrated counts
-  const bool fused_fwd = tc && !is_bf16(a) && a->classes <= 256 && getenv("LF_FUSED_FWD");
-  const int nb_db = (a->mode == LF_MODE_JLOGITS && fused_fwd) ? tc_forward_parts(a->batch) : row_blocks(a->batch);
+  const int nb_db = row_blocks(a->batch);
   return finalize_db_cal(w.db_partials, nb_db, a->classes, w.cal_partials, row_blocks(a->batch), a->dbias[0], a->dbias[1],
                          a->stats, s);
 }

@@ -1,0 +1,23 @@
+"""Small shapes through every kernel family, for compute-sanitizer memcheck:  compute-sanitizer --tool memcheck python tools/sanitize_step.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multimodal_clinical_b200.step import LateFusionStep
+from oracle import late_fusion as O
+
+cases = [("jlogits", 70, 512, 6, None, "fp32"), ("qmf", 70, 512, 6, 100, "fp32"), ("jlogits", 33, 36, 20, None, "fp32"),
+         ("qmf", 200, 768, 101, 500, "tf32"), ("jlogits", 150, 512, 309, None, "tf32"), ("qmf", 200, 768, 101, 500, "bf16"),
+         ("jlogits", 150, 512, 309, None, "bf16"), ("qmf", 90, 128, 40, 300, "fp32")]
+for mode, B, D, Cn, N, prec in cases:
+    inp = O.make_inputs(B, D, Cn, seed=1, n_data=N)
+    e = LateFusionStep(Cn, mode=mode, n_data=N, device="cuda:0", precision=prec)
+    for s in range(2):
+        o = e.step([inp["f1"].cuda(), inp["f2"].cuda()], [inp["W1"].cuda(), inp["W2"].cuda()], [inp["b1"].cuda(), inp["b2"].cuda()],
+                   inp["y"].cuda(), idx=inp["idx"].cuda() if N else None, ogm_alpha=0.5 if not N else None)
+    torch.cuda.synchronize()
+    print(mode, B, D, Cn, prec, "loss", float(o.loss), flush=True)
+g = [torch.randn(64, 3, 7, 7, device="cuda"), torch.randn(128, 64, 3, 3, device="cuda"), torch.randn(5, 5, 1, 1, device="cuda")]
+e = LateFusionStep(6, mode="jlogits", device="cuda:0")
+e.modulate(g, which=0, modulation="OGM_GE", seed=1, offset=0)
+torch.cuda.synchronize()
+print("modulate ok", flush=True)
