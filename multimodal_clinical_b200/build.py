@@ -18,9 +18,18 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+MANIFEST = OUT + ".sources"
+
+
+def _manifest() -> str:
+    return "\n".join(os.path.basename(x) for x in sources()) + "\n" + " ".join(NVCC_FLAGS)
+
+
 def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
+    if not os.path.exists(MANIFEST) or open(MANIFEST).read() != _manifest():
+        return True                       # a source was added / removed or the flags changed
     t = os.path.getmtime(OUT)
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
@@ -36,6 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building _lf_fusion.so")
+    with open(MANIFEST, "w") as f:
+        f.write(_manifest())
     return OUT
 
 
