@@ -97,7 +97,8 @@ typedef struct LfHeadsArgs {
                              dW/db on a second stream while dfeat, which no other rank needs, is still being written. */
   int32_t ld_logits;      /* row pitch (elements) of logits[0], logits[1]; 0 = classes (dense).  A multiple of 4 lets the
                              tensor-pipe GEMM write them with TMA stores (1236-byte rows of a dense C = 309 cannot be). */
-  int32_t reserved2;
+  int32_t ld_fused;       /* row pitch (elements) of avg_logits and logits_df; 0 = classes (dense).  A multiple of 4 (with 16-byte
+                             aligned bases) lets the row kernels write them with 128-bit stores. */
 } LfHeadsArgs;
 
 /* Bytes of caller-provided scratch the heads calls need. */

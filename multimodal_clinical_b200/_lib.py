@@ -31,7 +31,7 @@ class LfHeadsArgs(C.Structure):
         ("logits", _P2), ("avg_logits", C.c_void_p), ("logits_df", C.c_void_p), ("conf", C.c_void_p),
         ("dlogits", _P2), ("dfeat", _P2), ("dweight", _P2), ("dbias", _P2),
         ("qmf_g", C.c_void_p), ("ema_offset", C.c_void_p), ("stats", C.c_void_p),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("fwd_only", C.c_int32), ("bwd_phase", C.c_int32), ("ld_logits", C.c_int32), ("reserved2", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("fwd_only", C.c_int32), ("bwd_phase", C.c_int32), ("ld_logits", C.c_int32), ("ld_fused", C.c_int32),
     ]
 
 

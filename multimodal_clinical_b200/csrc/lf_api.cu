@@ -146,6 +146,8 @@ static int check_heads(const LfHeadsArgs* a, bool backward) {
     set_error("ld_logits %d: must be >= classes, and a padded pitch is only supported on the tensor-pipe path", a->ld_logits);
     return LF_ERR_BAD_ARG;
   }
+  if (a->ld_fused != 0 && a->ld_fused != a->classes && !use_tensor_pipe(a)) { set_error("ld_fused: a padded pitch is only supported on the tensor-pipe path"); return LF_ERR_BAD_ARG; }
+  if (a->ld_fused != 0 && a->ld_fused < a->classes) { set_error("ld_fused %d < classes %d", a->ld_fused, a->classes); return LF_ERR_BAD_ARG; }
   if (a->ld_dlogits != 0 && a->ld_dlogits < a->classes) { set_error("ld_dlogits %d < classes %d", a->ld_dlogits, a->classes); return LF_ERR_BAD_ARG; }
   if (use_tensor_pipe(a) && (a->ld_dlogits % 4 != 0 || a->ld_dlogits == 0)) {
     set_error("LF_PREC_TF32 needs ld_dlogits to be a non-zero multiple of 4 (TMA row pitch), got %d", a->ld_dlogits);
@@ -170,6 +172,7 @@ static RowsArgs rows_args(const LfHeadsArgs* a, const HeadsWorkspace& w) {
   r.B = a->batch; r.B_global = a->batch_global; r.C = a->classes;
   r.ld_z = a->ld_logits > 0 ? a->ld_logits : a->classes;
   r.ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
+  r.ld_f = a->ld_fused > 0 ? a->ld_fused : a->classes;
   r.dz_bf16 = a->precision == LF_PREC_BF16;
   r.nb_total = row_blocks(a->batch);
   return r;
@@ -358,10 +361,13 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     rc = gemm_dweight(g, 2, s);
   }
   if (rc) return rc;
-  rc = reduce_splits2(w.dw_partials, a->dweight[0], a->dweight[1], splits, kMaxSplits, cd, s);
-  if (rc) return rc;
   // db_m (column sums of dZ_m, accumulated by the kernel that produced dZ) and the calibrated counts
   const int nb_db = row_blocks(a->batch);
+  if (finalize_grads_supported(w.dw_partials, a->dweight[0], a->dweight[1], splits, cd) && (kMaxSplits * cd) % 4 == 0)
+    return finalize_grads(w.dw_partials, a->dweight[0], a->dweight[1], splits, kMaxSplits, cd, w.db_partials, nb_db, a->classes,
+                          w.cal_partials, row_blocks(a->batch), a->dbias[0], a->dbias[1], a->stats, s);
+  rc = reduce_splits2(w.dw_partials, a->dweight[0], a->dweight[1], splits, kMaxSplits, cd, s);
+  if (rc) return rc;
   return finalize_db_cal(w.db_partials, nb_db, a->classes, w.cal_partials, row_blocks(a->batch), a->dbias[0], a->dbias[1],
                          a->stats, s);
 }

@@ -13,8 +13,10 @@
 // buffer ([rank][stats | idx | conf]: a single all-gather, or the peer-memory push fused in below) and one
 // cooperatively launched grid (up to 128 CTAs x 1024 threads, ~2 samples per thread however large the
 // GLOBAL batch is) walks the dependent phases with grid-wide barriers in between:
-//   P0 sum statistics, EMA, coefficients   P1 ticket = last writer per index   P2 History update
-//   P3 min/max over all N                  P4 ranking terms, dL/dconf          P5 loss
+//   [P1 ticket = last writer per index | P0 sum statistics, EMA, coefficients]  -- barrier --
+//   [P2+P3 one owner-computes sweep over the History: update + min/max]         -- barrier --
+//   [P4 ranking terms, dL/dconf]  -- barrier --  P5 loss
+// (three grid barriers; an earlier version used five and a staging array of normalised correctness)
 #include <cooperative_groups.h>
 #include "lf_common.cuh"
 #include "lf_peer.cuh"
@@ -49,30 +51,36 @@ struct MidShared {
   int nan;
 };
 
-// After P3 the normalised correctness of every sample of the batch sits in two contiguous fp64 rows
-// A[m][j] = (corr_m[idx_j] - min_m) / (max_m - min_m)  (QMF.py:37-42, 51-52), so the pair terms below only
-// touch contiguous memory; the random History accesses happen once per sample, in the phase that fills A.
-__device__ __forceinline__ float a_pair_target(const double* __restrict__ A, int Bg, int j, float* margin) {
-  const int j2 = (j + 1 == Bg) ? 0 : j + 1;
-  const double a = A[j], b = A[j2];
-  if (margin) *margin = (float)fabs(a - b);
-  return (a > b ? 1.f : 0.f) - (a < b ? 1.f : 0.f);
-}
-__device__ __forceinline__ void g_pair_terms(const MidShared& sh, const double* __restrict__ A, const Gathered& g,
-                                             int j, float* x0, float* x1, float* t0, float* t1) {
-  *t0 = a_pair_target(A, g.Bg, j, nullptr);
-  *t1 = a_pair_target(A + g.Bg, g.Bg, j, nullptr);
-  const float r = (j + 1 < g.Bg) ? g.conf_at(0, j + 1) : g.conf_at(1, 0);   // flattened roll wraps into modality 1
-  *x0 = *t0 * (g.conf_at(0, j) - (r + sh.s0));                               // MarginRankingLoss(x1, x2, -t)
-  *x1 = *t1 * (g.conf_at(1, j) - ((r + sh.q0) + sh.q1));
-}
-
 struct MidParams {
   LfMidArgs a;
   double* minmax;     // [kMidMaxCtas][2][2]
   float* regpart;     // [kMidMaxCtas]
-  double* A;          // [2][Bg] normalised correctness of the batch
 };
+
+// Normalised correctness of batch position j, both modalities (QMF.py:37-42, 51-52): one index load and two
+// History gathers (the History is L2-resident: 16 N bytes).  Out-of-range index -> NaN, like a failed lookup.
+struct NormPair { double a0, a1; };
+__device__ __forceinline__ NormPair norm_at(const LfMidArgs& a, const MidShared& sh, const Gathered& g, int j) {
+  const int64_t i = g.idx_at(j);
+  const bool ok = (unsigned long long)i < (unsigned long long)a.n_data;
+  const double c0 = ok ? a.correctness[i] : (double)NAN;
+  const double c1 = ok ? a.correctness[(size_t)a.n_data + i] : (double)NAN;
+  NormPair r;
+  r.a0 = (c0 - sh.lo[0]) / (sh.hi[0] - sh.lo[0]);
+  r.a1 = (c1 - sh.lo[1]) / (sh.hi[1] - sh.lo[1]);
+  return r;
+}
+__device__ __forceinline__ float pair_target(double a, double b) { return (a > b ? 1.f : 0.f) - (a < b ? 1.f : 0.f); }
+
+// ranking terms of the pair (j, j+1) given the normalised correctness of both ends (QMF.py:124-139)
+__device__ __forceinline__ void pair_terms(const MidShared& sh, const Gathered& g, int j, const NormPair& cur,
+                                           const NormPair& nxt, float* x0, float* x1, float* t0, float* t1) {
+  *t0 = pair_target(cur.a0, nxt.a0);
+  *t1 = pair_target(cur.a1, nxt.a1);
+  const float r = (j + 1 < g.Bg) ? g.conf_at(0, j + 1) : g.conf_at(1, 0);   // flattened roll wraps into modality 1
+  *x0 = *t0 * (g.conf_at(0, j) - (r + sh.s0));                               // MarginRankingLoss(x1, x2, -t)
+  *x1 = *t1 * (g.conf_at(1, j) - ((r + sh.q0) + sh.q1));
+}
 
 __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
   const LfMidArgs& a = p.a;
@@ -82,6 +90,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
   const int C = a.classes, len = LF_STATS_HEADER + 2 * C, Bg = a.batch_global, N = a.n_data;
   extern __shared__ double s_stats[];                 // [len] global statistics (each CTA keeps a copy)
   __shared__ MidShared sh;
+  __shared__ double slo[2][32], shi[2][32];
 
   // ---- exchange (sharded runs): push this rank's [stats | idx | conf] to every peer, wait for all peers,
   // then read the local receive area, which has the same rank-major layout an all-gather would produce
@@ -100,6 +109,23 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     idx_parts = (const int64_t*)(base + a.off_idx); idx_stride = a.payload_bytes / 8;
     conf_parts = (const float*)(base + a.off_conf); conf_stride = a.payload_bytes / 4;
   }
+
+  Gathered g;
+  g.idx = idx_parts; g.idx_stride = idx_stride; g.conf = conf_parts; g.conf_stride = conf_stride;
+  g.Bl = a.batch_local; g.Bg = Bg;
+  const bool qmf = a.mode == LF_MODE_QMF;
+  long long* lw = (long long*)a.last_writer;
+  // tickets: host-provided base, or (step_base == 0) the device-resident counter at last_writer[N], which
+  // makes the launch replayable from a CUDA graph
+  const long long base = qmf ? (a.step_base ? a.step_base : lw[N] + 1) : 0;
+
+  // ---- P1 (issued first: its atomics fly while the statistics are summed): the last duplicate of an index
+  // wins (numpy fancy assignment); ticket = position in the batch
+  if (qmf)
+    for (int j = tid; j < Bg; j += nthr) {
+      const int64_t i = g.idx_at(j);
+      if ((unsigned long long)i < (unsigned long long)N) atomicMax(&lw[i], base + j);
+    }
 
   // ---- P0: global statistics in rank order
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
@@ -138,7 +164,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
   }
   __syncthreads();
 
-  if (a.mode != LF_MODE_QMF) {
+  if (!qmf) {
     if (cta == 0 && threadIdx.x == 0) {
       if (a.loss_out) a.loss_out[0] = (float)(s_stats[LF_STAT_CE_JOINT] / (double)Bg);
       if (a.use_peer) a.comm.epoch[0] = epoch;
@@ -146,64 +172,49 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     return;
   }
 
-  Gathered g;
-  g.idx = idx_parts; g.idx_stride = idx_stride; g.conf = conf_parts; g.conf_stride = conf_stride;
-  g.Bl = a.batch_local; g.Bg = Bg;
-  long long* lw = (long long*)a.last_writer;
-  // tickets: host-provided base, or (step_base == 0) the device-resident counter at last_writer[N], which
-  // makes the launch replayable from a CUDA graph
-  const long long base = a.step_base ? a.step_base : lw[N] + 1;
-
-  // ---- P1: the last duplicate of an index wins (numpy fancy assignment): ticket = position in the batch
-  for (int j = tid; j < Bg; j += nthr) {
-    const int64_t i = g.idx_at(j);
-    if ((unsigned long long)i < (unsigned long long)N) atomicMax(&lw[i], base + j);
-  }
-  grid.sync();
-  // ---- P2: History.correctness_update (QMF.py:20-29), alpha = 0.1.  Four samples per thread per round so
-  // the dependent random accesses (idx -> ticket -> History entry) of different samples overlap.
-  for (int j0 = tid; j0 < Bg; j0 += 4 * nthr) {
-    int64_t ii[4]; long long w[4]; double c0[4], c1[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int j = j0 + u * nthr; ii[u] = j < Bg ? g.idx_at(j) : -1; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = ((unsigned long long)ii[u] < (unsigned long long)N) ? lw[ii[u]] : -1;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool mine = w[u] == base + (j0 + u * nthr);
-      c0[u] = mine ? a.correctness[ii[u]] : 0.0; c1[u] = mine ? a.correctness[(size_t)N + ii[u]] : 0.0;
+  grid.sync();                                             // every ticket of this step is in place
+  // ---- P2 + P3 in ONE sweep over the History, owner-computes: the thread that scans entry i applies this
+  // step's update to it (History.correctness_update, QMF.py:20-29, alpha = 0.1; the winning sample is
+  // ticket - base) and folds the resulting value into the min / max over ALL N entries (QMF.py:38-40,
+  // NaN-propagating like numpy).  No random access, no second pass, no barrier between update and scan.
+  {
+    double lo0 = INFINITY, hi0 = -INFINITY, lo1 = INFINITY, hi1 = -INFINITY;
+    bool nan0 = false, nan1 = false;
+    const double u0 = 0.1 * (double)sh.l0, u1 = 0.1 * (double)sh.l1;
+    for (int i = tid; i < N; i += nthr) {
+      const long long t = lw[i];
+      double c0 = a.correctness[i], c1 = a.correctness[(size_t)N + i];
+      if (t >= base) {
+        const int j = (int)(t - base);
+        c0 = 0.9 * c0 + u0; c1 = 0.9 * c1 + u1;
+        a.correctness[i] = c0; a.correctness[(size_t)N + i] = c1;
+        a.confidence[i] = (double)g.conf_at(0, j);
+        a.confidence[(size_t)N + i] = (double)g.conf_at(1, j);
+      }
+      nan0 |= (c0 != c0); nan1 |= (c1 != c1);
+      lo0 = fmin(lo0, c0); hi0 = fmax(hi0, c0); lo1 = fmin(lo1, c1); hi1 = fmax(hi1, c1);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * nthr;
-      if (w[u] != base + j) continue;
-      a.correctness[ii[u]] = 0.9 * c0[u] + 0.1 * (double)sh.l0;
-      a.correctness[(size_t)N + ii[u]] = 0.9 * c1[u] + 0.1 * (double)sh.l1;
-      a.confidence[ii[u]] = (double)g.conf_at(0, j);
-      a.confidence[(size_t)N + ii[u]] = (double)g.conf_at(1, j);
+    for (int o = 16; o > 0; o >>= 1) {
+      lo0 = fmin(lo0, __shfl_xor_sync(kFull, lo0, o)); hi0 = fmax(hi0, __shfl_xor_sync(kFull, hi0, o));
+      lo1 = fmin(lo1, __shfl_xor_sync(kFull, lo1, o)); hi1 = fmax(hi1, __shfl_xor_sync(kFull, hi1, o));
     }
-  }
-  grid.sync();
-  // ---- P3: min / max over ALL N entries of both modalities (QMF.py:38-40), NaN-propagating like numpy
-  for (int m = 0; m < 2; ++m) {
-    const double* c = a.correctness + (size_t)m * N;
-    double lo = INFINITY, hi = -INFINITY;
-    bool nan = false;
-    for (int i = tid; i < N; i += nthr) { const double v = c[i]; nan |= (v != v); lo = fmin(lo, v); hi = fmax(hi, v); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(kFull, lo, o)); hi = fmax(hi, __shfl_xor_sync(kFull, hi, o)); }
-    if (nan) atomicOr(&sh.nan, 1 << m);
-    __shared__ double slo[32], shi[32];
-    if (threadIdx.x % 32 == 0) { slo[threadIdx.x / 32] = lo; shi[threadIdx.x / 32] = hi; }
+    if (nan0) atomicOr(&sh.nan, 1);
+    if (nan1) atomicOr(&sh.nan, 2);
+    if (threadIdx.x % 32 == 0) {
+      const int w = threadIdx.x / 32;
+      slo[0][w] = lo0; shi[0][w] = hi0; slo[1][w] = lo1; shi[1][w] = hi1;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < (int)blockDim.x / 32; ++w) { lo = fmin(lo, slo[w]); hi = fmax(hi, shi[w]); }
+    if (threadIdx.x < 2) {
+      const int m = threadIdx.x;
+      double lo = slo[m][0], hi = shi[m][0];
+      for (int w = 1; w < (int)blockDim.x / 32; ++w) { lo = fmin(lo, slo[m][w]); hi = fmax(hi, shi[m][w]); }
       if (sh.nan & (1 << m)) { lo = NAN; hi = NAN; }
       p.minmax[(cta * 2 + m) * 2 + 0] = lo; p.minmax[(cta * 2 + m) * 2 + 1] = hi;
     }
-    __syncthreads();
   }
-  grid.sync();
+  grid.sync();                                             // History updated, per-CTA min / max published
   if (threadIdx.x < 2) {
     const int m = threadIdx.x;
     double lo = p.minmax[m * 2], hi = p.minmax[m * 2 + 1];
@@ -217,48 +228,35 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     sh.lo[m] = lo; sh.hi[m] = hi;
   }
   __syncthreads();
-  // normalised correctness of the batch, four samples per thread per round (random History reads overlap)
-  for (int j0 = tid; j0 < Bg; j0 += 4 * nthr) {
-    int64_t ii[4]; double c0[4], c1[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int j = j0 + u * nthr; ii[u] = j < Bg ? g.idx_at(j) : -1; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool ok = (unsigned long long)ii[u] < (unsigned long long)N;      // out-of-range index -> NaN
-      c0[u] = ok ? a.correctness[ii[u]] : (double)NAN; c1[u] = ok ? a.correctness[(size_t)N + ii[u]] : (double)NAN;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * nthr;
-      if (j < Bg) { p.A[j] = (c0[u] - sh.lo[0]) / (sh.hi[0] - sh.lo[0]); p.A[Bg + j] = (c1[u] - sh.lo[1]) / (sh.hi[1] - sh.lo[1]); }
-    }
-  }
-  grid.sync();
   if (threadIdx.x == 0) {
-    float m00, m11;
-    const float t00 = a_pair_target(p.A, Bg, 0, &m00);
-    const float t01 = a_pair_target(p.A, Bg, 1, nullptr);
-    const float t11 = a_pair_target(p.A + Bg, Bg, 1, &m11);
+    const NormPair n0 = norm_at(a, sh, g, 0), n1 = norm_at(a, sh, g, 1), n2 = norm_at(a, sh, g, 2 == Bg ? 0 : 2);
+    const float m00 = (float)fabs(n0.a0 - n1.a0), m11 = (float)fabs(n1.a1 - n2.a1);
+    const float t00 = pair_target(n0.a0, n1.a0), t01 = pair_target(n1.a0, n2.a0), t11 = pair_target(n1.a1, n2.a1);
     const float z00 = t00 == 0.f ? 1.f : t00, z01 = t01 == 0.f ? 1.f : t01, z11 = t11 == 0.f ? 1.f : t11;
     sh.s0 = m00 / z00;     // rank_margin[0] / rank_target_nonzero, row 0   (QMF.py:134, n = 0)
     sh.q0 = m00 / z01;     // same matrix, row 1 (picked up by n = 1)
     sh.q1 = m11 / z11;     // n = 1: rank_margin[1] / rank_target_nonzero, row 1
   }
   __syncthreads();
-  // ---- P4: ranking terms and dL_reg/dconf for this rank's slice
+  // ---- P4: ranking terms and dL_reg/dconf for this rank's slice.  Each thread
+  // normalises the correctness of positions j-1, j, j+1 itself (neighbours hit L1 / L2), so no staging array and
+  // no barrier separate the History sweep from the pair terms.
   float reg = 0.f;
   const float invB = 1.f / (float)Bg;
   const int g_begin = a.rank * a.batch_local, g_end = g_begin + a.batch_local;
   for (int j = tid; j < Bg; j += nthr) {
+    const int jn = (j + 1 == Bg) ? 0 : j + 1;
+    const NormPair cur = norm_at(a, sh, g, j), nxt = norm_at(a, sh, g, jn);
     float x0, x1, t0, t1;
-    g_pair_terms(sh, p.A, g, j, &x0, &x1, &t0, &t1);
+    pair_terms(sh, g, j, cur, nxt, &x0, &x1, &t0, &t1);
     reg += relu_nan(x0) + relu_nan(x1);
     if (j >= g_begin && j < g_end && a.qmf_g) {
       const float u0 = (x0 >= 0.f) ? t0 * invB : 0.f;       // clamp_min backward mask is (x >= 0)
       const float u1 = (x1 >= 0.f) ? t1 * invB : 0.f;
       const int jp = (j == 0) ? Bg - 1 : j - 1;
+      const NormPair prv = norm_at(a, sh, g, jp);
       float px0, px1, pt0, pt1;
-      g_pair_terms(sh, p.A, g, jp, &px0, &px1, &pt0, &pt1);
+      pair_terms(sh, g, jp, prv, cur, &px0, &px1, &pt0, &pt1);
       const float v = -(((px0 >= 0.f) ? pt0 * invB : 0.f) + ((px1 >= 0.f) ? pt1 * invB : 0.f));
       a.qmf_g[j - g_begin] = u0 + (j >= 1 ? v : 0.f);       // pair jp's rolled operand is conf0[j] for j >= 1
       a.qmf_g[a.batch_local + (j - g_begin)] = u1 + (j == 0 ? v : 0.f);   // ... and conf1[0] for j == 0
@@ -294,7 +292,8 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
 using namespace lf;
 
 extern "C" size_t lf_mid_workspace_bytes(int32_t batch_global) {
-  return 8192 + sizeof(double) * 2 * (size_t)(batch_global > 0 ? batch_global : 0);
+  (void)batch_global;        // per-CTA min/max and ranking-loss partials only (the staging array of an earlier version is gone)
+  return 8192;
 }
 
 extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
@@ -324,7 +323,6 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
   p.a = *a;
   p.minmax = qmf ? (double*)a->workspace : nullptr;
   p.regpart = qmf ? (float*)((char*)a->workspace + 4096) : nullptr;        // minmax: 128 x 4 doubles = 4096 B
-  p.A = qmf ? (double*)((char*)a->workspace + 8192) : nullptr;
   const size_t smem = sizeof(double) * (LF_STATS_HEADER + 2 * (size_t)a->classes);
   cudaLaunchConfig_t cfg = {};
   // QMF: ~2 samples (and ~2 History entries) per thread, so the dependent random accesses of the phases are

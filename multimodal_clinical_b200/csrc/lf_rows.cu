@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
     for (int c = lane; c < C; c += 32) {
       const float v1 = z1[c], v2 = z2[c];
       const float av = (v1 + v2) / 2.f;
-      a.avg[(size_t)b * C + c] = av;
+      a.avg[(size_t)b * a.ld_f + c] = av;
       l1.add(v1); l2.add(v2); la.add(av);
       if (MODE == LF_MODE_QMF) { e1 += expf(v1); e2 += expf(v2); }
       if (v1 > m1) { m1 = v1; i1 = c; }
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
       float md = -INFINITY; int idf = 0x7fffffff; float zyd = 0.f;
       for (int c = lane; c < C; c += 32) {
         const float vd = z1[c] * c1 + z2[c] * c2;
-        a.zdf[(size_t)b * C + c] = vd;
+        a.zdf[(size_t)b * a.ld_f + c] = vd;
         ld.add(vd);
         if (vd > md) { md = vd; idf = c; }
         if (c == y) zyd = vd;
@@ -291,6 +291,70 @@ int finalize_db_cal(const float* dbpart, int nb_db, int C, const float* calpart,
   return check_launch("finalize_db_cal");
 }
 
+// The tail of the backward pass in ONE launch: dW_m = fixed-order sum of the split-K partials (CTAs [0, 2 nblk))
+// and db_m / calibrated counts = column sums of the per-CTA partials (remaining CTAs; 32 columns x 8 row groups).
+__global__ void __launch_bounds__(256) finalize_grads_kernel(const float* __restrict__ part, float* __restrict__ dw0,
+                                                             float* __restrict__ dw1, int splits, int max_splits, size_t n,
+                                                             int nblk, const float* __restrict__ dbpart, int nb_db, int C,
+                                                             const float* __restrict__ calpart, int nb_cal,
+                                                             float* __restrict__ db0, float* __restrict__ db1,
+                                                             double* __restrict__ stats) {
+  if ((int)blockIdx.x < 2 * nblk) {
+    const int m = (int)blockIdx.x / nblk, blk = (int)blockIdx.x - m * nblk;
+    const size_t i = ((size_t)blk * 256 + threadIdx.x) * 4;           // n is a multiple of 4 (D % 4 == 0)
+    if (i >= n) return;
+    const float* p = part + (size_t)m * max_splits * n + i;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < splits; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(p + (size_t)k * n);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* o = (m == 0 ? dw0 : dw1) + i;           // the flat gradient buffer packs dW2 after db1: not always 16-byte aligned
+    if (((uintptr_t)o & 15) == 0) *reinterpret_cast<float4*>(o) = s;
+    else { o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; }
+    return;
+  }
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int i = ((int)blockIdx.x - 2 * nblk) * 32 + tx;             // [0, 2C): db columns; [2C, 2C+2): calibrated counts
+  const bool is_db = i < 2 * C;
+  const float* __restrict__ src = is_db ? dbpart + i : calpart + (i - 2 * C);
+  const size_t pitch = is_db ? (size_t)2 * C : 2;
+  const int nb = is_db ? nb_db : nb_cal;
+  double s = 0.0;
+  if (i < 2 * C + 2) {
+    int b = ty;
+    for (; b + 24 < nb; b += 32) {
+      const float v0 = src[(size_t)b * pitch], v1 = src[(size_t)(b + 8) * pitch];
+      const float v2 = src[(size_t)(b + 16) * pitch], v3 = src[(size_t)(b + 24) * pitch];
+      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    }
+    for (; b < nb; b += 8) s += (double)src[(size_t)b * pitch];
+  }
+  __shared__ double sm[8][33];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || i >= 2 * C + 2) return;
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += sm[w][tx];
+  if (i < C) db0[i] = (float)t;
+  else if (i < 2 * C) db1[i - C] = (float)t;
+  else stats[LF_STAT_CNT_X1_CAL + (i - 2 * C)] = t;
+}
+
+bool finalize_grads_supported(const float* part, const float* dw0, const float* dw1, int splits, size_t n) {
+  (void)dw0; (void)dw1;
+  return splits <= 32 && n % 4 == 0 && (((uintptr_t)part) & 15) == 0;
+}
+int finalize_grads(const float* part, float* dw0, float* dw1, int splits, int max_splits, size_t n, const float* dbpart,
+                   int nb_db, int C, const float* calpart, int nb_cal, float* db0, float* db1, double* stats, cudaStream_t s) {
+  const int nblk = div_up((long long)(n / 4), 256);
+  LF_LAUNCH("finalize_grads", s, (finalize_grads_kernel<<<2 * nblk + div_up(2 * C + 2, 32), 256, 0, s>>>(
+      part, dw0, dw1, splits, max_splits, n, nblk, dbpart, nb_db, C, calpart, nb_cal, db0, db1, stats)));
+  return check_launch("finalize_grads");
+}
+
 int row_blocks(int B) {
   int nb = div_up(B, 8);
   return nb < kMaxRowBlocks ? (nb < 1 ? 1 : nb) : kMaxRowBlocks;
@@ -299,11 +363,15 @@ int row_blocks(int B) {
 bool rows_reg_supported(int C);                                                   // lf_rows_reg.cu
 int rows_forward_reg(const RowsArgs& a, int mode, int nb, cudaStream_t s);
 int rows_backward_reg(const RowsArgs& a, int mode, int nb, cudaStream_t s);
+bool rows_vec_supported(const RowsArgs& a, bool writes_dz);                       // lf_rows_vec.cu
+int rows_forward_vec(const RowsArgs& a, int mode, int nb, cudaStream_t s);
+int rows_backward_vec(const RowsArgs& a, int mode, int nb, cudaStream_t s);
 
 int rows_forward(const RowsArgs& a, int mode, cudaStream_t s) {
   const int nb = row_blocks(a.B);
   if (rows_reg_supported(a.C)) {
-    int rc = rows_forward_reg(a, mode, nb, s);
+    // 16-byte pitched logits (tensor-pipe path): G lanes per sample, 128-bit accesses; else one warp per sample
+    int rc = rows_vec_supported(a, mode == LF_MODE_JLOGITS) ? rows_forward_vec(a, mode, nb, s) : rows_forward_reg(a, mode, nb, s);
     if (rc) return rc;
     LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(a.C), 32), 1024, 0, s>>>(a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats)));
     return check_launch("finalize_stats_kernel");
@@ -329,7 +397,8 @@ void finalize_forward_stats(const float* partials, int nblocks, int C, double* s
 
 int rows_backward(const RowsArgs& a, int mode, cudaStream_t s) {
   const int nb = row_blocks(a.B);
-  if (rows_reg_supported(a.C)) return rows_backward_reg(a, mode, nb, s);
+  if (rows_reg_supported(a.C))
+    return rows_vec_supported(a, mode == LF_MODE_QMF) ? rows_backward_vec(a, mode, nb, s) : rows_backward_reg(a, mode, nb, s);
   const size_t sm = (size_t)8 * 2 * a.C * sizeof(float);
   if (mode == LF_MODE_QMF) {
     if (sm > 48 * 1024) cudaFuncSetAttribute(rows_backward_kernel<LF_MODE_QMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

@@ -23,6 +23,7 @@ struct RowsArgs {
   int B, B_global, C;
   int ld_z;              // row pitch of the input logits z (>= C; padded to 16 B when the tensor pipe TMA-stores them)
   int ldz;               // row pitch of dz
+  int ld_f;              // row pitch of avg / zdf (>= C)
   int dz_bf16;           // 1: dz[] point at bf16 buffers (LF_PREC_BF16): dL/dz is stored rounded to bf16
   int nb_total;          // partial rows the finalize kernels will sum; CTAs zero the rows beyond the grid
 };
@@ -41,6 +42,10 @@ int row_blocks(int B);
 // dbias[m][c] = sum over blocks of dbpart; stats[CNT_X*_CAL] = sum over blocks of calpart
 int finalize_db_cal(const float* dbpart, int nb_db, int C, const float* calpart, int nb_cal, float* db0, float* db1,
                     double* stats, cudaStream_t s);
+// dW (sum of split-K partials) + db + calibrated counts in one launch (splits <= 32, 16-byte aligned buffers)
+bool finalize_grads_supported(const float* part, const float* dw0, const float* dw1, int splits, size_t n);
+int finalize_grads(const float* part, float* dw0, float* dw1, int splits, int max_splits, size_t n, const float* dbpart,
+                   int nb_db, int C, const float* calpart, int nb_cal, float* db0, float* db1, double* stats, cudaStream_t s);
 int loss_finalize(const double* stats, int mode, int Bg, float* out, cudaStream_t s);
 int ema_update(float* x, float* off, const double* stats, int C, int Bg, float beta, cudaStream_t s);
 int ogm_coeff(const double* stats, float alpha, float* coeff, cudaStream_t s);

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) rows_forward_reg_kernel(RowsArgs a) {
     for (int k = 0; k < NCH; ++k) {
       av[k] = (v1[k] + v2[k]) / 2.f;
       const int c = lane + 32 * k;
-      if (c < C) { a.avg[(size_t)b * C + c] = av[k]; cs1[k] += v1[k]; cs2[k] += v2[k]; }
+      if (c < C) { a.avg[(size_t)b * a.ld_f + c] = av[k]; cs1[k] += v1[k]; cs2[k] += v2[k]; }
     }
     float m1, m2, ma; int i1, i2, ia;
     warp_max_arg<NCH>(v1, lane, m1, i1);
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) rows_forward_reg_kernel(RowsArgs a) {
       for (int k = 0; k < NCH; ++k) {
         const int c = lane + 32 * k;
         vd[k] = c < C ? v1[k] * c1 + v2[k] * c2 : -INFINITY;
-        if (c < C) a.zdf[(size_t)b * C + c] = vd[k];
+        if (c < C) a.zdf[(size_t)b * a.ld_f + c] = vd[k];
       }
       float md; int idf;
       warp_max_arg<NCH>(vd, lane, md, idf);

@@ -154,8 +154,11 @@ class LateFusionStep:
             b["ldl"] = (Cn + 3) // 4 * 4 if (self.precision != LF_PREC_FP32 and Cn >= 32) else Cn
             b["logits_store"] = torch.empty(2, B, b["ldl"], device=dev)
             b["logits"] = b["logits_store"][:, :, :Cn]
-            b["avg"] = torch.empty(B, Cn, device=dev)
-            b["zdf"] = torch.empty(B, Cn, device=dev) if qmf else None
+            # avg / z_df share the padded pitch, so the row kernels write them with 128-bit stores
+            b["avg_store"] = torch.empty(B, b["ldl"], device=dev)
+            b["avg"] = b["avg_store"][:, :Cn]
+            b["zdf_store"] = torch.empty(B, b["ldl"], device=dev) if qmf else None
+            b["zdf"] = b["zdf_store"][:, :Cn] if qmf else None
             b["conf"] = torch.empty(2, B, device=dev) if qmf else None
             fdt = torch.bfloat16 if self.bf16 else torch.float32
             b["ldz"] = (Cn + 7) // 8 * 8 if self.bf16 else (Cn + 3) // 4 * 4     # dL/dlogits rows padded to 16 B (TMA pitch)
@@ -173,9 +176,11 @@ class LateFusionStep:
             dev, Cn, b = self.device, self.C, dict(self._bufs)
             b["logits_store"] = torch.empty(2, B, b["ldl"], device=dev)
             b["logits"] = b["logits_store"][:, :, :Cn]
-            b["avg"] = torch.empty(B, Cn, device=dev)
+            b["avg_store"] = torch.empty(B, b["ldl"], device=dev)
+            b["avg"] = b["avg_store"][:, :Cn]
             if b["zdf"] is not None:
-                b["zdf"] = torch.empty(B, Cn, device=dev)
+                b["zdf_store"] = torch.empty(B, b["ldl"], device=dev)
+                b["zdf"] = b["zdf_store"][:, :Cn]
                 b["conf"] = torch.empty(2, B, device=dev)
             if need_dfeat:
                 b["dfeat"] = torch.empty(2, B, D, device=dev, dtype=torch.bfloat16 if self.bf16 else torch.float32)
@@ -264,6 +269,7 @@ class LateFusionStep:
         a.mode, a.precision, a.need_dfeat = self.mode, self.precision, int(need_dfeat)
         a.ld_dlogits = bufs["ldz"]
         a.ld_logits = bufs["ldl"]
+        a.ld_fused = bufs["ldl"]
         a.fwd_only = int(not backward)
         for m in range(2):
             a.feat[m] = _ptr(f[m]); a.weight[m] = _ptr(W[m]); a.bias[m] = _ptr(bb[m])
@@ -271,8 +277,8 @@ class LateFusionStep:
             a.dfeat[m] = _ptr(bufs["dfeat"][m]) if need_dfeat else None
             a.dweight[m] = _ptr(dW[m]); a.dbias[m] = _ptr(db[m])
         a.label = _ptr(label)
-        a.avg_logits = _ptr(bufs["avg"])
-        a.logits_df = _ptr(bufs["zdf"]); a.conf = _ptr(p_conf)
+        a.avg_logits = _ptr(bufs["avg_store"])
+        a.logits_df = _ptr(bufs["zdf_store"]); a.conf = _ptr(p_conf)
         a.dlogits[0] = _ptr(bufs["dz"][0]); a.dlogits[1] = _ptr(bufs["dz"][1]) if qmf else None
         a.qmf_g = _ptr(bufs["qmf_g"]); a.ema_offset = _ptr(self.ema_offset)
         a.stats = _ptr(p_stats)                                   # forward writes the LOCAL partial sums
