@@ -35,6 +35,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static const bool on = getenv("LF_PDL") != nullptr;     // opt-in: measured no gain under CUDA-graph replay
+  return on;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -58,6 +58,26 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl may become resident while its
+// predecessor on the stream is still draining, so its prologue (barrier init, TMEM allocation, descriptor prefetch,
+// shared-memory setup) overlaps the predecessor's tail.  pdl_wait() blocks until the predecessor has completed and
+// its writes are visible: it must precede the first access to global memory.  pdl_trigger() lets the successor start
+// its own prologue.  Both are no-ops for a kernel launched the ordinary way.  The attribute is only set when LF_PDL=1 (measured: no
+// gain under CUDA-graph replay, where kernel-to-kernel gaps are already ~1 us).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // relu that lets NaN through (torch.clamp_min semantics; fmaxf would swallow it)
 __device__ __forceinline__ float relu_nan(float x) { return (x > 0.f || x != x) ? x : 0.f; }
 

@@ -116,11 +116,13 @@ int gemm_dweight(GemmArgs g, int nbatch, cudaStream_t s) {
 // fp32 head weights -> bf16 [2][n] (LF_PREC_BF16): the per-step cast autocast performs for nn.Linear
 __global__ void cast_weights_bf16_kernel(const float* __restrict__ w0, const float* __restrict__ w1, __nv_bfloat16* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   if (i >= n) return;
   out[(size_t)blockIdx.y * n + i] = __float2bfloat16_rn((blockIdx.y == 0 ? w0 : w1)[i]);
 }
 int cast_weights_bf16(const float* w0, const float* w1, void* out, size_t n, cudaStream_t s) {
-  LF_LAUNCH("cast_weights_bf16", s, (cast_weights_bf16_kernel<<<dim3(div_up((long long)n, 256), 2), 256, 0, s>>>(w0, w1, (__nv_bfloat16*)out, n)));
+  LF_LAUNCH("cast_weights_bf16", s, launch_pdl(cast_weights_bf16_kernel, dim3(div_up((long long)n, 256), 2), dim3(256), 0, s, w0, w1, (__nv_bfloat16*)out, n));
   return check_launch("cast_weights_bf16");
 }
 

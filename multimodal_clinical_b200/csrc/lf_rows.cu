@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(1024) finalize_stats_kernel(const float* __res
                                                               int hi, int with_cols, double* __restrict__ stats) {
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;      // 32 columns x 32 row groups
   const int i = blockIdx.x * 32 + tx;
+  pdl_wait();
+  pdl_trigger();
   double s = 0.0;
   if (i < len) {
     int b = ty;
@@ -299,6 +301,8 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const float* __rest
                                                              const float* __restrict__ calpart, int nb_cal,
                                                              float* __restrict__ db0, float* __restrict__ db1,
                                                              double* __restrict__ stats) {
+  pdl_wait();
+  pdl_trigger();
   if ((int)blockIdx.x < 2 * nblk) {
     const int m = (int)blockIdx.x / nblk, blk = (int)blockIdx.x - m * nblk;
     const size_t i = ((size_t)blk * 256 + threadIdx.x) * 4;           // n is a multiple of 4 (D % 4 == 0)
@@ -350,8 +354,8 @@ bool finalize_grads_supported(const float* part, const float* dw0, const float* 
 int finalize_grads(const float* part, float* dw0, float* dw1, int splits, int max_splits, size_t n, const float* dbpart,
                    int nb_db, int C, const float* calpart, int nb_cal, float* db0, float* db1, double* stats, cudaStream_t s) {
   const int nblk = div_up((long long)(n / 4), 256);
-  LF_LAUNCH("finalize_grads", s, (finalize_grads_kernel<<<2 * nblk + div_up(2 * C + 2, 32), 256, 0, s>>>(
-      part, dw0, dw1, splits, max_splits, n, nblk, dbpart, nb_db, C, calpart, nb_cal, db0, db1, stats)));
+  LF_LAUNCH("finalize_grads", s, launch_pdl(finalize_grads_kernel, dim3(2 * nblk + div_up(2 * C + 2, 32)), dim3(256), 0, s,
+      part, dw0, dw1, splits, max_splits, n, nblk, dbpart, nb_db, C, calpart, nb_cal, db0, db1, stats));
   return check_launch("finalize_grads");
 }
 
@@ -373,7 +377,7 @@ int rows_forward(const RowsArgs& a, int mode, cudaStream_t s) {
     // 16-byte pitched logits (tensor-pipe path): G lanes per sample, 128-bit accesses; else one warp per sample
     int rc = rows_vec_supported(a, mode == LF_MODE_JLOGITS) ? rows_forward_vec(a, mode, nb, s) : rows_forward_reg(a, mode, nb, s);
     if (rc) return rc;
-    LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(a.C), 32), 1024, 0, s>>>(a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats)));
+    LF_LAUNCH("finalize_stats", s, launch_pdl(finalize_stats_kernel, dim3(div_up(stat_len(a.C), 32)), dim3(1024), 0, s, (const float*)a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats));
     return check_launch("finalize_stats_kernel");
   }
   const size_t sm = (size_t)8 * 3 * a.C * sizeof(float);
@@ -387,12 +391,12 @@ int rows_forward(const RowsArgs& a, int mode, cudaStream_t s) {
   }
   int rc = check_launch("rows_forward_kernel");
   if (rc) return rc;
-  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(a.C), 32), 1024, 0, s>>>(a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats)));
+  LF_LAUNCH("finalize_stats", s, launch_pdl(finalize_stats_kernel, dim3(div_up(stat_len(a.C), 32)), dim3(1024), 0, s, (const float*)a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats));
   return check_launch("finalize_stats_kernel");
 }
 
 void finalize_forward_stats(const float* partials, int nblocks, int C, double* stats, cudaStream_t s) {
-  LF_LAUNCH("finalize_stats", s, (finalize_stats_kernel<<<div_up(stat_len(C), 32), 1024, 0, s>>>(partials, nblocks, stat_len(C), 0, LF_STATS_HEADER, 1, stats)));
+  LF_LAUNCH("finalize_stats", s, launch_pdl(finalize_stats_kernel, dim3(div_up(stat_len(C), 32)), dim3(1024), 0, s, partials, nblocks, stat_len(C), 0, LF_STATS_HEADER, 1, stats));
 }
 
 int rows_backward(const RowsArgs& a, int mode, cudaStream_t s) {

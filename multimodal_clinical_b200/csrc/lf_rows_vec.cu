@@ -10,7 +10,8 @@
 //     warp instructions per sample at C = 101; this mapping needs ~160.)
 //   * every access is a 128-bit load or store: z1/z2 in, avg / z_df (when their pitch is padded too) and
 //     dz (fp32 x4 or bf16 x4) out.
-//   * no software prefetch: 16-24 resident warps x 8 independent 512-byte loads cover the HBM latency.
+//   * no software prefetch: 16 resident warps x 8 independent 512-byte loads cover the latency (tried:
+//     prefetch.global.L1 of the next iteration's rows made both kernels ~30 % slower).
 //
 // Reference arithmetic: see lf_rows.cu (formulas and reference line numbers).
 #include "lf_common.cuh"
@@ -143,6 +144,8 @@ __global__ void __launch_bounds__(256, 2) rows_forward_vec_kernel(RowsArgs a) {
   const float dz_scale = 0.5f / (float)a.B_global;
   const bool vec_out = a.ld_f % 4 == 0;
 
+  pdl_wait();
+  pdl_trigger();
   float cs1[NE], cs2[NE], cs3[NE];
 #pragma unroll
   for (int i = 0; i < NE; ++i) { cs1[i] = 0.f; cs2[i] = 0.f; cs3[i] = 0.f; }
@@ -304,6 +307,8 @@ __global__ void __launch_bounds__(256, 2) rows_backward_vec_kernel(RowsArgs a) {
 
   // EMA offsets of this step, padded with -inf (keeps padded columns out of the calibrated argmax), in
   // shared memory after the column-sum area: registers are the scarce resource here
+  pdl_wait();
+  pdl_trigger();
   constexpr int LDP = 4 * G * NK;
   float* soff = smem + (MODE == LF_MODE_QMF ? (size_t)8 * 2 * C : 0);
   for (int c = threadIdx.x; c < 2 * LDP; c += blockDim.x) {
@@ -416,7 +421,7 @@ static int launch_fwd_vec(const RowsArgs& a, int nb, cudaStream_t s) {
   if (sm > 48 * 1024) cudaFuncSetAttribute(rows_forward_vec_kernel<MODE, G, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   nb = one_wave_vec(rows_forward_vec_kernel<MODE, G, NK>, sm, nb);
   LF_LAUNCH(MODE == LF_MODE_QMF ? "rows_forward_qmf" : "rows_forward_jlogits", s,
-            (rows_forward_vec_kernel<MODE, G, NK><<<nb, 256, sm, s>>>(a)));
+            launch_pdl(rows_forward_vec_kernel<MODE, G, NK>, dim3(nb), dim3(256), sm, s, a));
   return check_launch("rows_forward_vec_kernel");
 }
 template <int MODE, int G, int NK>
@@ -425,7 +430,7 @@ static int launch_bwd_vec(const RowsArgs& a, int nb, cudaStream_t s) {
   if (sm > 48 * 1024) cudaFuncSetAttribute(rows_backward_vec_kernel<MODE, G, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   nb = one_wave_vec(rows_backward_vec_kernel<MODE, G, NK>, sm, nb);
   LF_LAUNCH(MODE == LF_MODE_QMF ? "rows_backward_qmf" : "rows_calibrated", s,
-            (rows_backward_vec_kernel<MODE, G, NK><<<nb, 256, sm, s>>>(a)));
+            launch_pdl(rows_backward_vec_kernel<MODE, G, NK>, dim3(nb), dim3(256), sm, s, a));
   return check_launch("rows_backward_vec_kernel");
 }
 

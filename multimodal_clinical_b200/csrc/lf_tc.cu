@@ -134,6 +134,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything above overlapped the previous kernel's tail; global memory is touched from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -307,12 +309,12 @@ int make_map(CUtensorMap* map, const void* base, long long inner, long long oute
 
 // 3-D output map for the TMA-store epilogue: (cols, rows, splits), box [32 x 128 x 1], SWIZZLE_128B.
 static int make_store_map(CUtensorMap* map, void* base, long long cols, long long rows, long long ld,
-                          long long splits, long long split_stride, int elem) {
+                          long long splits, long long split_stride, int elem, int tile_m) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return LF_ERR_CUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)splits};
   cuuint64_t strides[2] = {(cuuint64_t)ld * elem, (cuuint64_t)(splits > 1 ? split_stride : rows * ld) * elem};
-  cuuint32_t box[3] = {(cuuint32_t)(128 / elem), (cuuint32_t)TC_BLOCK_M, 1};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / elem), (cuuint32_t)tile_m, 1};      // balanced M tiles store only their own rows
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -364,7 +366,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   p.tmem_cols = 2 * p.acc_cols;
   p.tile_m = TC_BLOCK_M;
   p.n_tiles = div_up(d.N, d.block_n);
-  if (d.balance_m && !d.a_mn_major && !p.tma_store) {
+  if (d.balance_m && !d.a_mn_major) {
     // smallest number of M tiles >= ceil(M/128) that makes items a multiple of 148, if it costs < 15% extra tiles
     const int per_m = p.n_tiles * p.splits * d.nbatch;
     const int base = div_up(d.M, TC_BLOCK_M);
@@ -388,7 +390,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
                       : make_map(&mB[b], d.B[b], d.K, d.N, d.ldb, p.kb_elems, d.block_n, false, p.elem);
     if (rc) return rc;
     if (p.tma_store) {
-      rc = make_store_map(&mO[b], d.out[b], d.N, d.M, d.ld_out, p.splits, d.split_stride, p.out_elem);
+      rc = make_store_map(&mO[b], d.out[b], d.N, d.M, d.ld_out, p.splits, d.split_stride, p.out_elem, p.tile_m);
       if (rc) return rc;
     } else {
       mO[b] = mA[b];
@@ -410,7 +412,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = p.total_items < 148 ? p.total_items : 148;
-  LF_LAUNCH(d.name, s, (tc_gemm_kernel<<<grid, TC_THREADS, smem, s>>>(mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p)));
+  LF_LAUNCH(d.name, s, launch_pdl(tc_gemm_kernel, dim3(grid), dim3(TC_THREADS), smem, s, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p));
   return check_launch(d.name);
 }
 
