@@ -161,22 +161,34 @@ __global__ void __launch_bounds__(256) rows_forward_kernel(RowsArgs a) {
 // One CTA per 32 statistics: 32 columns x 8 row groups, coalesced 128-byte reads, fixed summation order.
 __global__ void __launch_bounds__(1024) finalize_stats_kernel(const float* __restrict__ partials, int nblocks, int len, int lo,
                                                               int hi, int with_cols, double* __restrict__ stats) {
-  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;      // 32 columns x 32 row groups
-  const int i = blockIdx.x * 32 + tx;
+  // 8 columns x 128 row groups: with <= 640 partial rows every thread's loads are issued at once (one memory round
+  // trip for the whole kernel); fixed-order two-level sum over the groups
+  const int tx = threadIdx.x % 8, ty = threadIdx.x / 8;
+  const int i = blockIdx.x * 8 + tx;
   pdl_wait();
   pdl_trigger();
   double s = 0.0;
   if (i < len) {
     int b = ty;
-    for (; b + 96 < nblocks; b += 128) {                          // four independent loads in flight
-      const float v0 = partials[(size_t)b * len + i], v1 = partials[(size_t)(b + 32) * len + i];
-      const float v2 = partials[(size_t)(b + 64) * len + i], v3 = partials[(size_t)(b + 96) * len + i];
-      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    for (; b + 512 < nblocks; b += 640) {
+      float v[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) v[u] = partials[(size_t)(b + 128 * u) * len + i];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) s += (double)v[u];
     }
-    for (; b < nblocks; b += 32) s += (double)partials[(size_t)b * len + i];
+    for (; b < nblocks; b += 128) s += (double)partials[(size_t)b * len + i];
   }
-  __shared__ double sm[32][33];
+  __shared__ double sm[128][9];
+  __shared__ double sm2[8][9];
   sm[ty][tx] = s;
+  __syncthreads();
+  if (ty < 8) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) t += sm[ty * 16 + w][tx];
+    sm2[ty][tx] = t;
+  }
   __syncthreads();
   if (ty != 0 || i >= len) return;
   const bool header = i < LF_STATS_HEADER;
@@ -184,7 +196,7 @@ __global__ void __launch_bounds__(1024) finalize_stats_kernel(const float* __res
   if (!header && !with_cols) return;
   double t = 0.0;
 #pragma unroll
-  for (int w = 0; w < 32; ++w) t += sm[w][tx];
+  for (int w = 0; w < 8; ++w) t += sm2[w][tx];
   stats[i] = t;
 }
 
@@ -294,7 +306,7 @@ int finalize_db_cal(const float* dbpart, int nb_db, int C, const float* calpart,
 }
 
 // The tail of the backward pass in ONE launch: dW_m = fixed-order sum of the split-K partials (CTAs [0, 2 nblk))
-// and db_m / calibrated counts = column sums of the per-CTA partials (remaining CTAs; 32 columns x 8 row groups).
+// and db_m / calibrated counts = column sums of the per-CTA partials (remaining CTAs; 8 columns x 32 row groups).
 __global__ void __launch_bounds__(256) finalize_grads_kernel(const float* __restrict__ part, float* __restrict__ dw0,
                                                              float* __restrict__ dw1, int splits, int max_splits, size_t n,
                                                              int nblk, const float* __restrict__ dbpart, int nb_db, int C,
@@ -303,45 +315,59 @@ __global__ void __launch_bounds__(256) finalize_grads_kernel(const float* __rest
                                                              double* __restrict__ stats) {
   pdl_wait();
   pdl_trigger();
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   if ((int)blockIdx.x < 2 * nblk) {
+    // 32 float4 columns x 8 split groups: every thread's loads are independent (one DRAM round trip instead of a
+    // chain of `splits`), then a fixed-order sum over the groups
     const int m = (int)blockIdx.x / nblk, blk = (int)blockIdx.x - m * nblk;
-    const size_t i = ((size_t)blk * 256 + threadIdx.x) * 4;           // n is a multiple of 4 (D % 4 == 0)
-    if (i >= n) return;
-    const float* p = part + (size_t)m * max_splits * n + i;
+    const size_t i = ((size_t)blk * 32 + tx) * 4;                     // n is a multiple of 4 (D % 4 == 0)
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) {
+      const float* p = part + (size_t)m * max_splits * n + i;
 #pragma unroll 4
-    for (int k = 0; k < splits; ++k) {
-      const float4 v = *reinterpret_cast<const float4*>(p + (size_t)k * n);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      for (int k = ty; k < splits; k += 8) {
+        const float4 v = *reinterpret_cast<const float4*>(p + (size_t)k * n);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
     }
+    __shared__ float4 sm4[8][33];
+    sm4[ty][tx] = s;
+    __syncthreads();
+    if (ty != 0 || i >= n) return;
+    float4 t = sm4[0][tx];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) { const float4 v = sm4[g][tx]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
     float* o = (m == 0 ? dw0 : dw1) + i;           // the flat gradient buffer packs dW2 after db1: not always 16-byte aligned
-    if (((uintptr_t)o & 15) == 0) *reinterpret_cast<float4*>(o) = s;
-    else { o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; }
+    if (((uintptr_t)o & 15) == 0) *reinterpret_cast<float4*>(o) = t;
+    else { o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
     return;
   }
-  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-  const int i = ((int)blockIdx.x - 2 * nblk) * 32 + tx;             // [0, 2C): db columns; [2C, 2C+2): calibrated counts
+  // db / calibrated counts: 8 columns x 32 row groups per CTA, eight independent loads in flight per thread
+  const int cx = threadIdx.x % 8, ry = threadIdx.x / 8;
+  const int i = ((int)blockIdx.x - 2 * nblk) * 8 + cx;              // [0, 2C): db columns; [2C, 2C+2): calibrated counts
   const bool is_db = i < 2 * C;
   const float* __restrict__ src = is_db ? dbpart + i : calpart + (i - 2 * C);
   const size_t pitch = is_db ? (size_t)2 * C : 2;
   const int nb = is_db ? nb_db : nb_cal;
   double s = 0.0;
   if (i < 2 * C + 2) {
-    int b = ty;
-    for (; b + 24 < nb; b += 32) {
-      const float v0 = src[(size_t)b * pitch], v1 = src[(size_t)(b + 8) * pitch];
-      const float v2 = src[(size_t)(b + 16) * pitch], v3 = src[(size_t)(b + 24) * pitch];
-      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    int b = ry;
+    for (; b + 224 < nb; b += 256) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(b + 32 * u) * pitch];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += (double)v[u];
     }
-    for (; b < nb; b += 8) s += (double)src[(size_t)b * pitch];
+    for (; b < nb; b += 32) s += (double)src[(size_t)b * pitch];
   }
-  __shared__ double sm[8][33];
-  sm[ty][tx] = s;
+  __shared__ double sm[32][9];
+  sm[ry][cx] = s;
   __syncthreads();
-  if (ty != 0 || i >= 2 * C + 2) return;
+  if (ry != 0 || i >= 2 * C + 2) return;
   double t = 0.0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) t += sm[w][tx];
+  for (int w = 0; w < 32; ++w) t += sm[w][cx];
   if (i < C) db0[i] = (float)t;
   else if (i < 2 * C) db1[i - C] = (float)t;
   else stats[LF_STAT_CNT_X1_CAL + (i - 2 * C)] = t;
@@ -353,8 +379,8 @@ bool finalize_grads_supported(const float* part, const float* dw0, const float* 
 }
 int finalize_grads(const float* part, float* dw0, float* dw1, int splits, int max_splits, size_t n, const float* dbpart,
                    int nb_db, int C, const float* calpart, int nb_cal, float* db0, float* db1, double* stats, cudaStream_t s) {
-  const int nblk = div_up((long long)(n / 4), 256);
-  LF_LAUNCH("finalize_grads", s, launch_pdl(finalize_grads_kernel, dim3(2 * nblk + div_up(2 * C + 2, 32)), dim3(256), 0, s,
+  const int nblk = div_up((long long)(n / 4), 32);
+  LF_LAUNCH("finalize_grads", s, launch_pdl(finalize_grads_kernel, dim3(2 * nblk + div_up(2 * C + 2, 8)), dim3(256), 0, s,
       part, dw0, dw1, splits, max_splits, n, nblk, dbpart, nb_db, C, calpart, nb_cal, db0, db1, stats));
   return check_launch("finalize_grads");
 }
@@ -377,7 +403,7 @@ int rows_forward(const RowsArgs& a, int mode, cudaStream_t s) {
     // 16-byte pitched logits (tensor-pipe path): G lanes per sample, 128-bit accesses; else one warp per sample
     int rc = rows_vec_supported(a, mode == LF_MODE_JLOGITS) ? rows_forward_vec(a, mode, nb, s) : rows_forward_reg(a, mode, nb, s);
     if (rc) return rc;
-    LF_LAUNCH("finalize_stats", s, launch_pdl(finalize_stats_kernel, dim3(div_up(stat_len(a.C), 32)), dim3(1024), 0, s, (const float*)a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats));
+    LF_LAUNCH("finalize_stats", s, launch_pdl(finalize_stats_kernel, dim3(div_up(stat_len(a.C), 8)), dim3(1024), 0, s, (const float*)a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats));
     return check_launch("finalize_stats_kernel");
   }
   const size_t sm = (size_t)8 * 3 * a.C * sizeof(float);
@@ -391,12 +417,12 @@ int rows_forward(const RowsArgs& a, int mode, cudaStream_t s) {
   }
   int rc = check_launch("rows_forward_kernel");
   if (rc) return rc;
-  LF_LAUNCH("finalize_stats", s, launch_pdl(finalize_stats_kernel, dim3(div_up(stat_len(a.C), 32)), dim3(1024), 0, s, (const float*)a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats));
+  LF_LAUNCH("finalize_stats", s, launch_pdl(finalize_stats_kernel, dim3(div_up(stat_len(a.C), 8)), dim3(1024), 0, s, (const float*)a.partials, nb, stat_len(a.C), 0, LF_STATS_HEADER, 1, a.stats));
   return check_launch("finalize_stats_kernel");
 }
 
 void finalize_forward_stats(const float* partials, int nblocks, int C, double* stats, cudaStream_t s) {
-  LF_LAUNCH("finalize_stats", s, launch_pdl(finalize_stats_kernel, dim3(div_up(stat_len(C), 32)), dim3(1024), 0, s, partials, nblocks, stat_len(C), 0, LF_STATS_HEADER, 1, stats));
+  LF_LAUNCH("finalize_stats", s, launch_pdl(finalize_stats_kernel, dim3(div_up(stat_len(C), 8)), dim3(1024), 0, s, partials, nblocks, stat_len(C), 0, LF_STATS_HEADER, 1, stats));
 }
 
 int rows_backward(const RowsArgs& a, int mode, cudaStream_t s) {
