@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 7
+#define LF_ABI_VERSION 8
 
 /* error codes */
 #define LF_OK 0
@@ -64,6 +64,13 @@ extern "C" {
 #define LF_STAT_REG_SUM 11  /* sum of the two ranking-loss relu sums (written by lf_qmf_history_step) */
 #define LF_STATS_HEADER 16  /* [16, 16+C): sum_b z1[b,:]   [16+C, 16+2C): sum_b z2[b,:]  (utils/BaseModel.py:82-83) */
 
+/* QMF loss-term ablations (cremad/joint_model_qmf_ablate_Ljoint.py:68, cremad/joint_model_qmf_ablate_Lunimodal.py:70):
+   bits of LfHeadsArgs.loss_terms / LfMidArgs.loss_terms.  0 = the full loss CE(z_df) + sum CE(z_m) + L_reg.
+   Dropped terms leave the forward quantities (logits, History update with the unimodal losses, statistics)
+   untouched; they vanish from the reported loss and from dL/dz. */
+#define LF_LOSS_NO_JOINT 1 /* loss_joint = 0 */
+#define LF_LOSS_NO_UNI 2   /* the sum of the unimodal CE terms is dropped */
+
 typedef struct LfHeadsArgs {
   int32_t batch;        /* B: samples in this shard */
   int32_t batch_global; /* denominator of every batch mean (== batch on one GPU) */
@@ -99,6 +106,8 @@ typedef struct LfHeadsArgs {
                              tensor-pipe GEMM write them with TMA stores (1236-byte rows of a dense C = 309 cannot be). */
   int32_t ld_fused;       /* row pitch (elements) of avg_logits and logits_df; 0 = classes (dense).  A multiple of 4 (with 16-byte
                              aligned bases) lets the row kernels write them with 128-bit stores. */
+  int32_t loss_terms;     /* QMF: LF_LOSS_* bits */
+  int32_t reserved3;
 } LfHeadsArgs;
 
 /* Bytes of caller-provided scratch the heads calls need. */
@@ -250,7 +259,7 @@ typedef struct LfMidArgs {
      waits for all peers, then consumes the LOCAL receive area; stats_parts / idx_parts / conf_parts are
      ignored (their byte offsets inside the payload are off_idx / off_conf). */
   int32_t use_peer;
-  int32_t reserved;
+  int32_t loss_terms;      /* QMF: LF_LOSS_* bits, applied to loss_out */
   const void* payload_local;
   int64_t payload_bytes;
   int64_t off_idx;

@@ -31,7 +31,7 @@ class LfHeadsArgs(C.Structure):
         ("logits", _P2), ("avg_logits", C.c_void_p), ("logits_df", C.c_void_p), ("conf", C.c_void_p),
         ("dlogits", _P2), ("dfeat", _P2), ("dweight", _P2), ("dbias", _P2),
         ("qmf_g", C.c_void_p), ("ema_offset", C.c_void_p), ("stats", C.c_void_p),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("fwd_only", C.c_int32), ("bwd_phase", C.c_int32), ("ld_logits", C.c_int32), ("ld_fused", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("fwd_only", C.c_int32), ("bwd_phase", C.c_int32), ("ld_logits", C.c_int32), ("ld_fused", C.c_int32), ("loss_terms", C.c_int32), ("reserved3", C.c_int32),
     ]
 
 
@@ -69,7 +69,7 @@ class LfMidArgs(C.Structure):
         ("ema_offset", C.c_void_p), ("smoothing", C.c_float), ("alpha", C.c_float), ("coeff_out", C.c_void_p),
         ("correctness", C.c_void_p), ("confidence", C.c_void_p), ("last_writer", C.c_void_p), ("step_base", C.c_int64),
         ("qmf_g", C.c_void_p), ("loss_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-        ("use_peer", C.c_int32), ("reserved", C.c_int32), ("payload_local", C.c_void_p), ("payload_bytes", C.c_int64),
+        ("use_peer", C.c_int32), ("loss_terms", C.c_int32), ("payload_local", C.c_void_p), ("payload_bytes", C.c_int64),
         ("off_idx", C.c_int64), ("off_conf", C.c_int64), ("comm", LfPeerComm),
     ]
 

@@ -7,6 +7,14 @@ def get_model(args):
         from .joint_model_ogm_ge import MultimodalCremadModel
     elif args.model_type == "qmf":
         from .joint_model_qmf import MultimodalCremadModel
+    elif args.model_type == "qmf_ablate":
+        from .joint_model_qmf_ablate import MultimodalCremadModel
+    elif args.model_type == "qmf_ablate_Ljoint":
+        from .joint_model_qmf_ablate_Ljoint import MultimodalCremadModel
+    elif args.model_type == "qmf_ablate_Lunimodal":
+        from .joint_model_qmf_ablate_Lunimodal import MultimodalCremadModel
+    elif args.model_type == "ogm_ge_lreg":
+        from .joint_model_ogm_ge_lreg import MultimodalCremadModel
     else:
         raise NotImplementedError("Model type not implemented")
     return MultimodalCremadModel(args)

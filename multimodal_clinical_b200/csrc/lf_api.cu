@@ -151,6 +151,7 @@ static int check_heads(const LfHeadsArgs* a, bool backward) {
     set_error("ld_logits %d: must be >= classes, and a padded pitch is only supported on the tensor-pipe path", a->ld_logits);
     return LF_ERR_BAD_ARG;
   }
+  if (a->loss_terms & ~(LF_LOSS_NO_JOINT | LF_LOSS_NO_UNI)) { set_error("bad loss_terms %d", a->loss_terms); return LF_ERR_BAD_ARG; }
   if (a->ld_fused != 0 && a->ld_fused != a->classes && !use_tensor_pipe(a)) { set_error("ld_fused: a padded pitch is only supported on the tensor-pipe path"); return LF_ERR_BAD_ARG; }
   if (a->ld_fused != 0 && a->ld_fused < a->classes) { set_error("ld_fused %d < classes %d", a->ld_fused, a->classes); return LF_ERR_BAD_ARG; }
   if (a->ld_dlogits != 0 && a->ld_dlogits < a->classes) { set_error("ld_dlogits %d < classes %d", a->ld_dlogits, a->classes); return LF_ERR_BAD_ARG; }
@@ -178,6 +179,8 @@ static RowsArgs rows_args(const LfHeadsArgs* a, const HeadsWorkspace& w) {
   r.ld_z = a->ld_logits > 0 ? a->ld_logits : a->classes;
   r.ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
   r.ld_f = a->ld_fused > 0 ? a->ld_fused : a->classes;
+  r.w_joint = (a->loss_terms & LF_LOSS_NO_JOINT) ? 0.f : 1.f;
+  r.w_uni = (a->loss_terms & LF_LOSS_NO_UNI) ? 0.f : 1.f;
   r.dz_bf16 = a->precision == LF_PREC_BF16;
   r.nb_total = row_blocks(a->batch);
   return r;

@@ -281,8 +281,10 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     if (a.use_peer) a.comm.epoch[0] = epoch;
     if (a.loss_out) {
       const double inv = 1.0 / (double)Bg;
-      const float uni = (float)(s_stats[LF_STAT_CE_X1] * inv) + (float)(s_stats[LF_STAT_CE_X2] * inv);
-      a.loss_out[0] = ((float)(s_stats[LF_STAT_CE_JOINT] * inv) + uni) + (float)(rs * inv);
+      // loss-term ablations drop a term the way the reference does (cremad/joint_model_qmf_ablate_Ljoint.py:68-70)
+      const float uni = (a.loss_terms & LF_LOSS_NO_UNI) ? 0.f : (float)(s_stats[LF_STAT_CE_X1] * inv) + (float)(s_stats[LF_STAT_CE_X2] * inv);
+      const float joint = (a.loss_terms & LF_LOSS_NO_JOINT) ? 0.f : (float)(s_stats[LF_STAT_CE_JOINT] * inv);
+      a.loss_out[0] = (joint + uni) + (float)(rs * inv);
     }
   }
 }

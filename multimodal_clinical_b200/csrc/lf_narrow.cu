@@ -51,6 +51,7 @@ struct NarrowParams {
   float* calpart;                // [grid][2]
   float* dwpart;                 // [2][kNarrowMaxCtas][C*D]
   int nb_total;                  // partial rows the finalize kernels will read
+  float w_joint, w_uni;          // 1 or 0: QMF loss-term ablations (LF_LOSS_* bits)
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -250,8 +251,8 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) narrow_kernel(NarrowParams 
           const float oh = (lane == y) ? 1.f : 0.f;
           const float p1 = exp_sub(v1[0], rs.x * 1.4426950408889634f), p2 = exp_sub(v2[0], rs.y * 1.4426950408889634f);
           const float pd = exp_sub(v1[0] * c1 + v2[0] * c2, rs.z * 1.4426950408889634f) - oh;
-          d1 = ((p1 - oh) + c1 * pd) * invB + g1 * p1;
-          d2 = ((p2 - oh) + c2 * pd) * invB + g2 * p2;
+          d1 = (p.w_uni * (p1 - oh) + (p.w_joint * c1) * pd) * invB + g1 * p1;
+          d2 = (p.w_uni * (p2 - oh) + (p.w_joint * c2) * pd) * invB + g2 * p2;
           p.dz[0][(size_t)b * p.ldz + lane] = d1;
           p.dz[1][(size_t)b * p.ldz + lane] = d2;
           cd1 += d1; cd2 += d2;
@@ -422,6 +423,8 @@ int narrow_run(const LfHeadsArgs* a, int pass, float* partials, float* dbpart, f
   }
   p.label = a->label; p.avg = a->avg_logits; p.zdf = a->logits_df; p.conf = a->conf; p.rowstat = rowstat;
   p.qmf_g = a->qmf_g; p.ema_off = a->ema_offset;
+  p.w_joint = (a->loss_terms & LF_LOSS_NO_JOINT) ? 0.f : 1.f;
+  p.w_uni = (a->loss_terms & LF_LOSS_NO_UNI) ? 0.f : 1.f;
   p.partials = partials; p.dbpart = dbpart; p.calpart = calpart; p.dwpart = dwpart; p.nb_total = nb_total;
   const int cmax = p.C <= 8 ? 8 : p.C <= 16 ? 16 : 32;
   const size_t smem = narrow_smem(p.C, p.D, p.S, cmax, fwd_only);

@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(256) rows_backward_kernel(RowsArgs a) {
         const float oh = (c == y) ? 1.f : 0.f;
         const float p1 = __expf(v1 - lse1), p2 = __expf(v2 - lse2);
         const float pd = __expf((v1 * c1 + v2 * c2) - lsed) - oh;
-        const float d1 = ((p1 - oh) + c1 * pd) * invB + g1 * p1;
-        const float d2 = ((p2 - oh) + c2 * pd) * invB + g2 * p2;
+        const float d1 = (a.w_uni * (p1 - oh) + (a.w_joint * c1) * pd) * invB + g1 * p1;
+        const float d2 = (a.w_uni * (p2 - oh) + (a.w_joint * c2) * pd) * invB + g2 * p2;
         store_dz(a, 0, (size_t)b * a.ldz + c, d1);
         store_dz(a, 1, (size_t)b * a.ldz + c, d2);
         dsum[c] += d1;

@@ -24,6 +24,7 @@ struct RowsArgs {
   int ld_z;              // row pitch of the input logits z (>= C; padded to 16 B when the tensor pipe TMA-stores them)
   int ldz;               // row pitch of dz
   int ld_f;              // row pitch of avg / zdf (>= C)
+  float w_joint, w_uni;  // 1 or 0: weight of CE(z_df) / of the unimodal CE terms in dL/dz (QMF loss ablations)
   int dz_bf16;           // 1: dz[] point at bf16 buffers (LF_PREC_BF16): dL/dz is stored rounded to bf16
   int nb_total;          // partial rows the finalize kernels will sum; CTAs zero the rows beyond the grid
 };

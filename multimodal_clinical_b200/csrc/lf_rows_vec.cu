@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(256, 2) rows_backward_vec_kernel(RowsArgs a) {
       const float4 rs = *reinterpret_cast<const float4*>(a.rowstat + (size_t)b * 4);          // lse1, lse2, lse(z_df)
       const float g1 = a.qmf_g[b] / 10.f, g2 = a.qmf_g[B + b] / 10.f;
       const float l1 = rs.x * kLog2e, l2 = rs.y * kLog2e, ldf = rs.z * kLog2e;
+      const float wu = a.w_uni, cj1 = a.w_joint * c1, cj2 = a.w_joint * c2;      // loss-term ablations (1 or 0)
       float d1[NE], d2[NE];
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
@@ -345,8 +346,8 @@ __global__ void __launch_bounds__(256, 2) rows_backward_vec_kernel(RowsArgs a) {
         const float oh = (c == y) ? 1.f : 0.f;
         const float p1 = exp_sub(r1.v[i], l1), p2 = exp_sub(r2.v[i], l2);
         const float pd = exp_sub(r1.v[i] * c1 + r2.v[i] * c2, ldf) - oh;
-        d1[i] = ((p1 - oh) + c1 * pd) * invB + g1 * p1;
-        d2[i] = ((p2 - oh) + c2 * pd) * invB + g2 * p2;
+        d1[i] = (wu * (p1 - oh) + cj1 * pd) * invB + g1 * p1;
+        d2[i] = (wu * (p2 - oh) + cj2 * pd) * invB + g2 * p2;
       }
       mask_cols<G, NK>(d1, l, C, 0.f);                   // padded columns hold z = 0: their dz is not a gradient of anything
       mask_cols<G, NK>(d2, l, C, 0.f);

@@ -70,7 +70,7 @@ class FusedLateFusionHead(nn.Module):
     """
 
     def __init__(self, num_classes: int, mode: str = "jlogits", n_data: Optional[int] = None,
-                 precision: str = "fp32", ema_smoothing: float = 0.05):
+                 precision: str = "fp32", ema_smoothing: float = 0.05, loss_terms: int = 0):
         super().__init__()
         if mode not in ("jlogits", "ogm_ge", "qmf"):
             raise NotImplementedError(f"fused head mode {mode!r}")
@@ -79,6 +79,7 @@ class FusedLateFusionHead(nn.Module):
         self.n_data = n_data
         self.precision = precision
         self.ema_smoothing = ema_smoothing
+        self.loss_terms = int(loss_terms)            # QMF loss ablations (LF_LOSS_* bits of include/lf_fusion.h)
         self.ogm_alpha: Optional[float] = None       # set by OGMGEBaseModel: coefficients come out of the same pass
         self.update_ema = True
         self.last_step: Optional[StepOutput] = None
@@ -102,7 +103,7 @@ class FusedLateFusionHead(nn.Module):
         if self._engine is None or self._engine.device != device:
             self._engine = LateFusionStep(self.num_classes, mode=self.mode, n_data=self.n_data, device=device,
                                           precision=self.precision, ema_smoothing=self.ema_smoothing,
-                                          qmf_state=self._qmf_state, ema=self._ema)
+                                          qmf_state=self._qmf_state, ema=self._ema, loss_terms=self.loss_terms)
             self._engine.fresh_outputs = True
         return self._engine
 

@@ -85,7 +85,7 @@ class LateFusionStep:
 
     def __init__(self, num_classes: int, mode: str = "jlogits", n_data: Optional[int] = None,
                  device: Optional[torch.device] = None, precision: str = "fp32", ema_smoothing: float = 0.05,
-                 process_group=None, qmf_state=None, ema=None, comm: str = "auto"):
+                 process_group=None, qmf_state=None, ema=None, comm: str = "auto", loss_terms: int = 0):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.LfError("LateFusionStep needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -95,6 +95,8 @@ class LateFusionStep:
         self.bf16 = self.precision == LF_PREC_BF16
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.pg = process_group
+        # QMF loss-term ablations (LF_LOSS_NO_JOINT = 1, LF_LOSS_NO_UNI = 2; include/lf_fusion.h)
+        self.loss_terms = int(loss_terms)
         self.rank, self.world = parallel.world(process_group)
         self.smoothing = float(ema_smoothing)
         dev = self.device
@@ -270,6 +272,7 @@ class LateFusionStep:
         a.ld_dlogits = bufs["ldz"]
         a.ld_logits = bufs["ldl"]
         a.ld_fused = bufs["ldl"]
+        a.loss_terms = self.loss_terms
         a.fwd_only = int(not backward)
         for m in range(2):
             a.feat[m] = _ptr(f[m]); a.weight[m] = _ptr(W[m]); a.bias[m] = _ptr(bb[m])
@@ -315,6 +318,7 @@ class LateFusionStep:
         if ogm_alpha is not None:
             mid.alpha, mid.coeff_out = float(ogm_alpha), _ptr(self.coeff)
         mid.loss_out = _ptr(self.loss)
+        mid.loss_terms = self.loss_terms
         check(lib.lf_step_mid(C.byref(mid), st), "lf_step_mid")
         if update_ema:
             self.ema_counter += 1

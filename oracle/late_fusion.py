@@ -288,10 +288,15 @@ def jlogits_step(feats, weights, biases, y, ema_x=None, dtype=torch.float32, fea
     return _finish(out, fs, ws, bs, zs, y, ema_x, feat_grad)
 
 
+LOSS_NO_JOINT, LOSS_NO_UNI = 1, 2     # the LF_LOSS_* bits of include/lf_fusion.h
+
+
 def qmf_step(feats, weights, biases, y, idx, hist: HistoryState, ema_x=None, dtype=torch.float32,
-             feat_grad=True, literal_reg=False) -> Dict:
+             feat_grad=True, literal_reg=False, loss_terms=0) -> Dict:
     """QMF head step (cremad/joint_model_qmf.py:57-75).  Mutates ``hist`` like the reference does:
-    the History update precedes the regulariser inside the same forward (:63-67)."""
+    the History update precedes the regulariser inside the same forward (:63-67).
+    ``loss_terms``: LOSS_NO_JOINT = ``loss_joint = 0`` (cremad/joint_model_qmf_ablate_Ljoint.py:68),
+    LOSS_NO_UNI = unimodal sum dropped from the loss (cremad/joint_model_qmf_ablate_Lunimodal.py:70)."""
     fs, ws, bs = _leafs(feats, weights, biases, dtype, feat_grad)
     zs = heads_forward(fs, ws, bs)
     z = torch.stack(zs)
@@ -306,7 +311,8 @@ def qmf_step(feats, weights, biases, y, idx, hist: HistoryState, ema_x=None, dty
                        conf[m].detach().to(torch.float32).numpy())
     reg = (qmf_reg_loss_literal if literal_reg else qmf_reg_loss_closed)(conf, idx_np, hist)
     loss_joint = cross_entropy_mean(z_df, y)
-    loss = loss_joint + torch.stack(loss_uni).sum() + reg
+    loss = (0 if loss_terms & LOSS_NO_JOINT else loss_joint) + \
+           (0 if loss_terms & LOSS_NO_UNI else torch.stack(loss_uni).sum()) + reg
     avg = (zs[0] + zs[1]) / 2
     out = {"loss": loss, "avg_logits": avg}
     out["logits_df"] = z_df.detach()

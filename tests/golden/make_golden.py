@@ -79,10 +79,13 @@ def accs(z1, z2, avg, y, off, zdf=None):
     return out
 
 
-def golden_qmf(name, B, D, C, N, steps, seed, idx_mode="replacement", dtype=torch.float32):
-    """cremad/joint_model_qmf.FusionNet (identity encoders) + utils/EMA.EMA for ``steps`` steps with
-    fresh features each step, fixed weights; records every step's outputs and the History arrays."""
-    import cremad.joint_model_qmf as mq
+def golden_qmf(name, B, D, C, N, steps, seed, idx_mode="replacement", dtype=torch.float32,
+               module="cremad.joint_model_qmf"):
+    """``module``.FusionNet (identity encoders; cremad/joint_model_qmf.py or one of its loss ablations
+    cremad/joint_model_qmf_ablate_L{joint,unimodal}.py / cremad/joint_model_ogm_ge_lreg.py) + utils/EMA.EMA for
+    ``steps`` steps with fresh features each step, fixed weights; records every step's outputs and the History."""
+    import importlib
+    mq = importlib.import_module(module)
     from utils.EMA import EMA
     mq.resnet18 = lambda modality: nn.Identity()
     g = torch.Generator().manual_seed(seed)
@@ -241,6 +244,11 @@ if __name__ == "__main__":
     golden_qmf("qmf_d768_c7", B=8, D=768, C=7, N=64, steps=2, seed=29)
     # minimum legal batch for reg_loss
     golden_qmf("qmf_b2", B=2, D=32, C=3, N=5, steps=3, seed=13)
+    # loss-term ablations and the QMF + OGM-GE model: same FusionNet, one line differs
+    golden_qmf("qmf_ablate_ljoint_b48", B=48, D=512, C=6, N=211, steps=3, seed=31, module="cremad.joint_model_qmf_ablate_Ljoint")
+    golden_qmf("qmf_ablate_lunimodal_b48", B=48, D=512, C=6, N=211, steps=3, seed=37, module="cremad.joint_model_qmf_ablate_Lunimodal")
+    golden_qmf("qmf_ablate_ljoint_c101", B=36, D=128, C=101, N=300, steps=2, seed=41, module="cremad.joint_model_qmf_ablate_Ljoint")
+    golden_qmf("qmf_ogm_ge_lreg_b48", B=48, D=512, C=6, N=211, steps=2, seed=43, module="cremad.joint_model_ogm_ge_lreg")
     # K3-shaped OGM-GE heads (small batch: the reference score loop is O(B^2 C))
     golden_ogm("ogm_cremad_b48", B=48, D=512, C=6, steps=3, seed=5, alpha=0.8)
     golden_ogm("ogm_wide_c309", B=40, D=128, C=309, steps=2, seed=17, alpha=0.8)

@@ -120,6 +120,98 @@ def test_cremad_ogm_ge_manual_optimisation_matches_reference_golden():
         assert abs(float(m.train_metrics["train_x1_acc"][-1]) - float(g[p + "acc_x1_cal"])) < 1e-6
 
 
+@pytest.mark.parametrize("model_type,fixture", [("qmf_ablate_Ljoint", "qmf_ablate_ljoint_b48"),
+                                                ("qmf_ablate_Lunimodal", "qmf_ablate_lunimodal_b48")])
+def test_cremad_qmf_loss_ablations_match_reference_golden(model_type, fixture):
+    """`get_model` types whose FusionNet drops one loss term (cremad/joint_model_qmf_ablate_L*.py)."""
+    from multimodal_clinical_b200 import cremad
+    g = load_golden(fixture)
+    B, D, C, N, steps = [int(v) for v in g["meta"]]
+    m = cremad.get_model(_args(num_classes=C, num_samples=N, model_type=model_type))
+    m.model.x1_model = nn.Identity(); m.model.x2_model = nn.Identity()
+    m = m.cuda().train()
+    _set_heads(m.model.x1_classifier, m.model.x2_classifier, g)
+    for s in range(steps):
+        p = f"s{s}_"
+        a = cu(g[p + "f1"]).view(B, D, 1, 1).requires_grad_(True)
+        v = cu(g[p + "f2"]).view(B, D, 1, 1).requires_grad_(True)
+        m.zero_grad()
+        loss = m.training_step((a, v, cu(g[p + "y"]), cu(g[p + "idx"])), s)
+        loss.backward()
+        assert_close(loss, g[p + "loss"], TOL_FP32, f"loss step {s}")
+        assert_close(m.model.x1_classifier.weight.grad, g[p + "dW1"], TOL_FP32, "dW1")
+        assert_close(m.model.x2_classifier.weight.grad, g[p + "dW2"], TOL_FP32, "dW2")
+        assert_close(m.model.x1_classifier.bias.grad, g[p + "db1"], TOL_FP32, "db1")
+        assert_close(a.grad.view(B, D), g[p + "df1"], TOL_FP32, "df1")
+        assert_close(v.grad.view(B, D), g[p + "df2"], TOL_FP32, "df2")
+        assert_close(m.model.qmf.history[0].correctness, g[p + "corr"][0], 1e-6, "history[0].correctness")
+        assert abs(float(m.train_metrics["train_df_acc"][-1]) - float(g[p + "acc_df"])) < 1e-6
+
+
+def test_cremad_ogm_ge_lreg_qmf_loss_with_modulated_encoder_gradients():
+    """cremad/joint_model_ogm_ge_lreg.py: QMF loss, manual optimisation, `ogm_ge` on the encoders' conv gradients.
+    Loss / head gradients against the reference fixture; the Dirac 1x1-conv encoder gradient must come out scaled
+    by the OGM coefficient of the step's logits."""
+    from multimodal_clinical_b200 import cremad
+    from multimodal_clinical_b200.utils import lightning_compat as lc
+    g = load_golden("qmf_ogm_ge_lreg_b48")
+    B, D, C, N, steps = [int(v) for v in g["meta"]]
+    torch.backends.cudnn.allow_tf32 = False
+    m = cremad.get_model(_args(num_classes=C, num_samples=N, model_type="ogm_ge_lreg", alpha=0.8, learning_rate=0.0))
+
+    def stub():
+        conv = nn.Conv2d(D, D, 1, bias=False)
+        with torch.no_grad():
+            nn.init.dirac_(conv.weight)
+        return nn.Sequential(conv)
+    m.model.x1_model = stub(); m.model.x2_model = stub()
+    m = m.cuda().train()
+    _set_heads(m.model.x1_classifier, m.model.x2_classifier, g)
+    if not lc.HAVE_LIGHTNING:
+        tr = lc.Trainer(); m.trainer = tr; tr._configure(m)
+    assert m.automatic_optimization is False
+    for s in range(steps):
+        p = f"s{s}_"
+        a = cu(g[p + "f1"]).view(B, D, 1, 1); v = cu(g[p + "f2"]).view(B, D, 1, 1)
+        loss = m.training_step((a, v, cu(g[p + "y"]), cu(g[p + "idx"])), s)
+        assert_close(loss, g[p + "loss"], TOL_FP32, "loss")
+        assert_close(m.model.x1_classifier.weight.grad, g[p + "dW1"], TOL_FP32, "dW1")
+        assert_close(m.model.x2_classifier.bias.grad, g[p + "db2"], TOL_FP32, "db2")
+        z1, z2, y = torch.from_numpy(g[p + "z1"]), torch.from_numpy(g[p + "z2"]), torch.from_numpy(g[p + "y"])
+        k = O.ogm_coeffs(*[float(x) for x in O.ogm_scores(z1, z2, y)], 0.8)
+        for which, (enc, f, df) in enumerate(((m.model.x1_model, g[p + "f1"], g[p + "df1"]),
+                                               (m.model.x2_model, g[p + "f2"], g[p + "df2"]))):
+            g_raw = torch.from_numpy(df).double().t() @ torch.from_numpy(f).double()       # dL/dW of the 1x1 conv
+            assert_close(enc[0].weight.grad.view(D, D), g_raw * k[which], 5e-5, f"modulated encoder grad {which} step {s}")
+
+
+def test_cremad_qmf_ablate_trains_on_mean_fusion_and_evaluates_with_qmf():
+    """cremad/joint_model_qmf_ablate.py: CE((z1+z2)/2) while training, the full QMF block (History included) in eval."""
+    from multimodal_clinical_b200 import cremad
+    g = load_golden("qmf_cremad_b64")
+    B, D, C, N, steps = [int(v) for v in g["meta"]]
+    m = cremad.get_model(_args(num_classes=C, num_samples=N, model_type="qmf_ablate"))
+    m.model.x1_model = nn.Identity(); m.model.x2_model = nn.Identity()
+    m = m.cuda().train()
+    _set_heads(m.model.x1_classifier, m.model.x2_classifier, g)
+    p = "s0_"
+    f1, f2, y, idx = cu(g[p + "f1"]).view(B, D, 1, 1), cu(g[p + "f2"]).view(B, D, 1, 1), cu(g[p + "y"]), cu(g[p + "idx"])
+    ref = O.jlogits_step([torch.from_numpy(g[p + "f1"]), torch.from_numpy(g[p + "f2"])],
+                         [torch.from_numpy(g["W1"]), torch.from_numpy(g["W2"])],
+                         [torch.from_numpy(g["b1"]), torch.from_numpy(g["b2"])], torch.from_numpy(g[p + "y"]))
+    m.zero_grad()
+    loss = m.training_step((f1, f2, y, idx), 0)
+    loss.backward()
+    assert_close(loss, ref["loss"], TOL_FP32, "training loss = CE(avg)")
+    assert_close(m.model.x1_classifier.weight.grad, ref["dW"][0], TOL_FP32, "dW1")
+    assert float(np.abs(np.asarray(m.model.qmf.history[0].correctness)).sum()) == 0.0          # training never touches the History
+    m.eval()
+    with torch.no_grad():
+        vloss = m.validation_step((f1, f2, y, idx), 0)
+    assert_close(vloss, g[p + "loss"], TOL_FP32, "eval loss = full QMF loss")
+    assert_close(m.model.qmf.history[0].correctness, g[p + "corr"][0], 1e-6, "History updated by the eval branch")
+
+
 def test_enrico_joint_logits_matches_reference_golden():
     from multimodal_clinical_b200.enrico.joint_model import MultimodalEnricoModel
     g = load_golden("jlogits_enrico_b32")

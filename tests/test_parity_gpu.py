@@ -6,11 +6,12 @@ import pytest
 import torch
 
 from oracle import late_fusion as O
-from tests.util import load_golden, assert_close, relerr, t, TOL_FP32, TOL_TENSOR
+from tests.util import load_golden, assert_close, relerr, t, TOL_FP32, TOL_TENSOR, loss_terms_of
 
 pytestmark = pytest.mark.gpu
 
-QMF_CASES = ["qmf_cremad_b64", "qmf_small_c11", "qmf_food_c101", "qmf_d768_c7", "qmf_b2"]
+QMF_CASES = ["qmf_cremad_b64", "qmf_small_c11", "qmf_food_c101", "qmf_d768_c7", "qmf_b2",
+             "qmf_ablate_ljoint_b48", "qmf_ablate_lunimodal_b48", "qmf_ablate_ljoint_c101", "qmf_ogm_ge_lreg_b48"]
 OGM_CASES = ["ogm_cremad_b48", "ogm_wide_c309", "jlogits_enrico_b32"]
 
 
@@ -27,7 +28,7 @@ def cu(x):
 def test_qmf_cuda_matches_reference_golden(name):
     g = load_golden(name)
     B, D, C, N, steps = [int(v) for v in g["meta"]]
-    eng = _step(num_classes=C, mode="qmf", n_data=N)
+    eng = _step(num_classes=C, mode="qmf", n_data=N, loss_terms=loss_terms_of(name))
     W = [cu(g["W1"]), cu(g["W2"])]
     b = [cu(g["b1"]), cu(g["b2"])]
     for s in range(steps):

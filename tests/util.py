@@ -37,3 +37,8 @@ def t(x):
 
 def cu(x):
     return t(x).cuda()
+
+
+def loss_terms_of(name: str) -> int:
+    """LF_LOSS_* bits of a golden fixture generated from one of the reference's QMF loss ablations."""
+    return 1 if "ljoint" in name else 2 if "lunimodal" in name else 0
