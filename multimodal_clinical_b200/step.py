@@ -156,10 +156,12 @@ class LateFusionStep:
             b["ldl"] = (Cn + 3) // 4 * 4 if (self.precision != LF_PREC_FP32 and Cn >= 32) else Cn
             b["logits_store"] = torch.empty(2, B, b["ldl"], device=dev)
             b["logits"] = b["logits_store"][:, :, :Cn]
-            # avg / z_df share the padded pitch, so the row kernels write them with 128-bit stores
-            b["avg_store"] = torch.empty(B, b["ldl"], device=dev)
+            # avg / z_df share the padded pitch up to 256 classes, where the vector row kernels write them with 128-bit
+            # stores; wider heads use the one-warp-per-sample kernels, which measured faster on dense rows
+            b["ldf"] = b["ldl"] if Cn <= 256 else Cn
+            b["avg_store"] = torch.empty(B, b["ldf"], device=dev)
             b["avg"] = b["avg_store"][:, :Cn]
-            b["zdf_store"] = torch.empty(B, b["ldl"], device=dev) if qmf else None
+            b["zdf_store"] = torch.empty(B, b["ldf"], device=dev) if qmf else None
             b["zdf"] = b["zdf_store"][:, :Cn] if qmf else None
             b["conf"] = torch.empty(2, B, device=dev) if qmf else None
             fdt = torch.bfloat16 if self.bf16 else torch.float32
@@ -178,10 +180,10 @@ class LateFusionStep:
             dev, Cn, b = self.device, self.C, dict(self._bufs)
             b["logits_store"] = torch.empty(2, B, b["ldl"], device=dev)
             b["logits"] = b["logits_store"][:, :, :Cn]
-            b["avg_store"] = torch.empty(B, b["ldl"], device=dev)
+            b["avg_store"] = torch.empty(B, b["ldf"], device=dev)
             b["avg"] = b["avg_store"][:, :Cn]
             if b["zdf"] is not None:
-                b["zdf_store"] = torch.empty(B, b["ldl"], device=dev)
+                b["zdf_store"] = torch.empty(B, b["ldf"], device=dev)
                 b["zdf"] = b["zdf_store"][:, :Cn]
                 b["conf"] = torch.empty(2, B, device=dev)
             if need_dfeat:
@@ -271,7 +273,7 @@ class LateFusionStep:
         a.mode, a.precision, a.need_dfeat = self.mode, self.precision, int(need_dfeat)
         a.ld_dlogits = bufs["ldz"]
         a.ld_logits = bufs["ldl"]
-        a.ld_fused = bufs["ldl"]
+        a.ld_fused = bufs["ldf"]
         a.loss_terms = self.loss_terms
         a.fwd_only = int(not backward)
         for m in range(2):

@@ -32,12 +32,12 @@ def args_for(s):
     h = _lib.LfHeadsArgs()
     h.batch, h.batch_global, h.dim, h.classes = B, B, D, Cn
     h.mode, h.precision, h.need_dfeat, h.ld_dlogits = eng.mode, eng.precision, int(w["dfeat"]), bufs["ldz"]
-    h.ld_logits = bufs["ldl"]
+    h.ld_logits = bufs["ldl"]; h.ld_fused = bufs["ldf"]
     for m, f in enumerate((s["f1"], s["f2"])):
         h.feat[m] = _ptr(f); h.weight[m] = _ptr(W[m]); h.bias[m] = _ptr(b[m]); h.logits[m] = _ptr(bufs["logits_store"][m])
         h.dfeat[m] = _ptr(bufs["dfeat"][m]) if w["dfeat"] else None
     h.dweight[0] = _ptr(gf[0:n]); h.dbias[0] = _ptr(gf[n:n + Cn]); h.dweight[1] = _ptr(gf[n + Cn:2 * n + Cn]); h.dbias[1] = _ptr(gf[2 * n + Cn:])
-    h.label = _ptr(s["y"]); h.avg_logits = _ptr(bufs["avg"]); h.logits_df = _ptr(bufs["zdf"]); h.conf = _ptr(bufs["conf"])
+    h.label = _ptr(s["y"]); h.avg_logits = _ptr(bufs["avg_store"]); h.logits_df = _ptr(bufs["zdf_store"]); h.conf = _ptr(bufs["conf"])
     h.dlogits[0] = _ptr(bufs["dz"][0]); h.dlogits[1] = _ptr(bufs["dz"][1]) if eng.mode == 1 else None
     h.qmf_g = _ptr(bufs["qmf_g"]); h.ema_offset = _ptr(eng.ema_offset); h.stats = _ptr(eng.stats)
     h.workspace = _ptr(eng._ws); h.workspace_bytes = eng._ws.numel()
