@@ -22,6 +22,11 @@ size_t narrow_dw_floats(int C, int D);
 int narrow_run(const LfHeadsArgs* a, int pass, float* partials, float* dbpart, float* calpart, float* dwpart,
                float* rowstat, int nb_total, int* grid_out, cudaStream_t s);
 void finalize_forward_stats(const float* partials, int nblocks, int C, double* stats, cudaStream_t s);  // lf_rows.cu
+// lf_tc_fwd.cu: logits of both modalities + the QMF row math in one tcgen05 kernel (32 <= C <= 128)
+bool tc_fwd_supported(int mode, int B, int D, int C, int ld_z, int ld_f, int elem);
+int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2], const float* const bias[2], int elem, int B, int D,
+                         int C, float* const z[2], int ld_z, float* avg, float* zdf, int ld_f, float* conf, float* rowstat,
+                         const int64_t* label, float* partials, int nb_total, int* grid_out, cudaStream_t s);
 }
 
 namespace lf {
@@ -266,6 +271,21 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
       d.A[m] = a->feat[m];
       d.B[m] = is_bf16(a) ? (const void*)((const char*)w.w16 + m * cd * 2) : (const void*)a->weight[m];
       d.bias[m] = a->bias[m]; d.out[m] = a->logits[m];
+    }
+    {
+      const int ldz = a->ld_logits > 0 ? a->ld_logits : a->classes, ldf = a->ld_fused > 0 ? a->ld_fused : a->classes;
+      if (tc_fwd_supported(a->mode, a->batch, a->dim, a->classes, ldz, ldf, d.elem)) {
+        // QMF, 32 <= C <= 128: the row math runs in the GEMM's epilogue (one thread per sample straight from TMEM)
+        int grid = 0;
+        const void* fp[2] = {a->feat[0], a->feat[1]};
+        float* zp[2] = {a->logits[0], a->logits[1]};
+        rc = tc_heads_forward_qmf(fp, d.B, a->bias, d.elem, a->batch, a->dim, a->classes, zp, ldz, a->avg_logits, a->logits_df, ldf,
+                                  a->conf, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), a->label, w.row_partials, 0,
+                                  &grid, s);
+        if (rc) return rc;
+        finalize_forward_stats(w.row_partials, grid, a->classes, a->stats, s);
+        return check_launch("finalize_stats");
+      }
     }
     d.M = a->batch; d.N = a->classes; d.K = a->dim;
     d.lda = a->dim; d.ldb = a->dim; d.ld_out = a->ld_logits > 0 ? a->ld_logits : a->classes;

@@ -59,31 +59,6 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// Sum v[i] over the warp for all i < CMAX with ~CMAX shuffles: at every step a lane keeps one half of its
-// values and hands the other half to its partner.  Afterwards every lane holds the total of class
-// lane / (32 / CMAX).
-template <int CMAX>
-__device__ __forceinline__ float transpose_reduce(float (&v)[CMAX], int lane) {
-  int n = CMAX;
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    if (n > 1) {
-      n >>= 1;
-      const bool up = (lane & s) != 0;
-#pragma unroll
-      for (int i = 0; i < CMAX / 2; ++i)
-        if (i < n) {
-          const float keep = up ? v[i + n] : v[i];
-          const float send = up ? v[i] : v[i + n];
-          v[i] = keep + __shfl_xor_sync(kFull, send, s);
-        }
-    } else {
-      v[0] += __shfl_xor_sync(kFull, v[0], s);
-    }
-  }
-  return v[0];
-}
-
 // NARROW_THREADS: 512 for the small-class variants (one sample per warp and one dW column per thread per tile
 // at D = 512; twice the warps to hide latency), 256 where the register budget of the wide variants needs it.
 template <int MODE, int PASS, int CMAX, int KV, int NARROW_THREADS>

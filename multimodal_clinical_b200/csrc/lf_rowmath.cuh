@@ -44,5 +44,29 @@ __device__ __forceinline__ void warp_sum3(float& a, float& b, float& c) {
   }
 }
 
+// Sum v[i] over the warp for all i < CMAX with ~CMAX shuffles: at every step a lane keeps one half of its
+// values and hands the other half to its partner.  Afterwards every lane holds the total of class
+// lane / (32 / CMAX).
+template <int CMAX>
+__device__ __forceinline__ float transpose_reduce(float (&v)[CMAX], int lane) {
+  int n = CMAX;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    if (n > 1) {
+      n >>= 1;
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < CMAX / 2; ++i)
+        if (i < n) {
+          const float keep = up ? v[i + n] : v[i];
+          const float send = up ? v[i] : v[i + n];
+          v[i] = keep + __shfl_xor_sync(kFull, send, s);
+        }
+    } else {
+      v[0] += __shfl_xor_sync(kFull, v[0], s);
+    }
+  }
+  return v[0];
+}
 
 }  // namespace lf
