@@ -41,7 +41,9 @@ struct TcFwdParams {
   int ld_z, ld_f;          // row pitches of z1/z2 and of avg/z_df (multiples of 4)
   int block_n;             // 16 * NCH
   int stages, elem, kb_elems, num_kb, m_tiles;
+  int tile_m;              // samples per M tile (<= 128, multiple of 8): chosen so that the tiles fill whole waves of CTAs
   int nb_total;            // partial rows the finalize kernel sums; rows beyond the grid are zeroed here
+  unsigned long long* trace;   // LF_FWD_TRACE=1: [grid][8] %globaltimer stamps of the roles (printed once, see tc_heads_forward_qmf)
   const float* bias[2];
   float* z[2];
   float* avg;
@@ -52,6 +54,11 @@ struct TcFwdParams {
   float* partials;         // [nb_total][stat_len]
 };
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void fw_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -108,10 +115,23 @@ __device__ __forceinline__ void store16_coalesced(float* stg, float* __restrict_
   }
   __syncwarp();
 }
+// running max / first argmax over one chunk: trees instead of a 16-deep compare-select chain (the epilogue is
+// latency-bound: four warps per scheduler, each a chain of dependent steps)
 __device__ __forceinline__ void max_arg16(const float (&v)[16], int c0, float& mx, int& arg) {
+  float t[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (v[i] > mx) { mx = v[i]; arg = c0 + i; }         // strict: the first index wins ties (torch.argmax)
+  for (int i = 0; i < 8; ++i) t[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+  const float cm = fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), fmaxf(fmaxf(t[4], t[5]), fmaxf(t[6], t[7])));
+  int e[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) e[i] = (v[i] == cm) ? i : 16;
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) e[i] = min(e[i], e[i + w]);
+  const bool up = cm > mx;                                  // strict: an earlier chunk keeps a tie (torch.argmax: first index)
+  mx = up ? cm : mx;
+  arg = up ? c0 + e[0] : arg;
 }
 
 template <int NCH, int H>
@@ -138,6 +158,8 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int C = p.C, B = p.B;
+  unsigned long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 8 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = gtimer();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapW0); tma_prefetch_desc(&mapW1);
@@ -159,25 +181,31 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   for (int i = threadIdx.x; i < EW * 256; i += FW_THREADS) sred[i] = 0.f;
   __syncthreads();
 
+  if (tr && threadIdx.x == 0) tr[1] = gtimer();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
+      bool first = true;
+      // (tried: cp.async.bulk.prefetch.tensor of the feature boxes one / two tiles ahead into L2 -- the main loop got
+      // 10 % slower, 29 vs 26 us to the last load)
       for (int item = blockIdx.x; item < p.m_tiles; item += gridDim.x) {
-        const int m0 = item * TC_BLOCK_M;
+        const int m0 = item * p.tile_m;
         for (int m = 0; m < 2; ++m) {
           const CUtensorMap* mapA = m == 0 ? &mapA0 : &mapA1;
           const CUtensorMap* mapW = m == 0 ? &mapW0 : &mapW1;
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + (size_t)s * stage_bytes;
-            mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
-            tma_load_2d(mapA, &full_bar[s], sa, kb * p.kb_elems, m0);            // [128 B of K x 128 samples]
+            mbar_expect_tx(&full_bar[s], (uint32_t)p.tile_m * 128u + b_bytes);
+            tma_load_2d(mapA, &full_bar[s], sa, kb * p.kb_elems, m0);            // [128 B of K x tile_m samples]
             tma_load_2d(mapW, &full_bar[s], sa + a_bytes, kb * p.kb_elems, 0);   // [128 B of K x block_n classes]
+            if (tr && first) { tr[2] = gtimer(); first = false; }
             if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
           }
         }
       }
+      if (tr) tr[3] = gtimer();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
@@ -194,6 +222,7 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const uint32_t acc = tmem_base + (buf * 2 + m) * 128;
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(&full_bar[s], ph);
+            if (tr && li == 0 && m == 0 && kb == 0) tr[4] = gtimer();
             tc_fence_after();
             const uint32_t sa = smem0 + s * stage_bytes;
             uint64_t da = desc0 + (uint64_t)(sa >> 4), db = desc0 + (uint64_t)((sa + a_bytes) >> 4);
@@ -208,6 +237,7 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
         umma_commit(&tmem_full_bar[buf]);                           // both accumulators of the tile complete
       }
+      if (tr) tr[5] = gtimer();
     }
   } else {
     // ===================== epilogue: 4 quarters x H column shares =====================
@@ -236,9 +266,10 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     uint32_t li = 0;
     for (int item = blockIdx.x; item < p.m_tiles; item += gridDim.x, ++li) {
       const uint32_t buf = li & 1;
-      const int row0 = item * TC_BLOCK_M + q * 32;
+      const int row0 = item * p.tile_m + q * 32;
       const int row = row0 + lane;
-      const bool valid = row < B;
+      const int row_end = min(B, (item + 1) * p.tile_m);      // TMEM lanes past the tile hold stale rows: never stored
+      const bool valid = row < row_end;
       const int y = (int)p.label[valid ? row : B - 1];
       const bool yok = (unsigned)y < (unsigned)C;
       mbar_wait_warp(&tmem_full_bar[buf], (li >> 1) & 1);
@@ -255,8 +286,8 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         float v1[16], v2[16];
         tmem_ld16x2(acc0 + c0, acc1 + c0, v1, v2);
         add_bias16(v1, sbias + c0); add_bias16(v2, sbias + 128 + c0);
-        store16_coalesced(stg, p.z[0], p.ld_z, row0, B, c0, v1, lane);
-        store16_coalesced(stg, p.z[1], p.ld_z, row0, B, c0, v2, lane);
+        store16_coalesced(stg, p.z[0], p.ld_z, row0, row_end, c0, v1, lane);
+        store16_coalesced(stg, p.z[1], p.ld_z, row0, row_end, c0, v2, lane);
         {
           float t1[16], t2[16];
 #pragma unroll
@@ -269,7 +300,7 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           float av[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) av[i] = (v1[i] + v2[i]) / 2.f;
-          store16_coalesced(stg, p.avg, p.ld_f, row0, B, c0, av, lane);
+          store16_coalesced(stg, p.avg, p.ld_f, row0, row_end, c0, av, lane);
           mask16(av, c0, C);
           max_arg16(av, c0, ma, ia);
         }
@@ -323,7 +354,7 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         add_bias16(v1, sbias + c0); add_bias16(v2, sbias + 128 + c0);
 #pragma unroll
         for (int i = 0; i < 16; ++i) vd[i] = v1[i] * c1 + v2[i] * c2;
-        store16_coalesced(stg, p.zdf, p.ld_f, row0, B, c0, vd, lane);
+        store16_coalesced(stg, p.zdf, p.ld_f, row0, row_end, c0, vd, lane);
         mask16(vd, c0, C);
         const float od = md;
         max_arg16(vd, c0, md, idf);
@@ -374,6 +405,7 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
     }
 
+    if (tr && ew == 0 && lane == 0) tr[6] = gtimer();
     // ---- CTA reduction in fixed order -> one partial row per CTA (layout of rows_forward)
 #pragma unroll
     for (int i = 0; i < 9; ++i) st[i] = warp_sum(st[i]);
@@ -405,6 +437,7 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (tr && threadIdx.x == 0) tr[7] = gtimer();
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -443,8 +476,25 @@ int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2],
   p.elem = elem == 2 ? 2 : 4;
   p.kb_elems = 128 / p.elem;
   p.num_kb = div_up(D, p.kb_elems);
-  p.m_tiles = div_up(B, TC_BLOCK_M);
+  // M tiles of <= 128 samples sized so that they fill whole waves of the 148 persistent CTAs (B = 32768: 293 tiles of
+  // 112 samples = 1.98 per CTA instead of 256 tiles = 2 for 108 CTAs and 1 for 40: the kernel is a bandwidth-bound
+  // stream and the CTAs that finish early cannot lend their share of the in-flight bytes to the others)
+  {
+    const int base = div_up(B, TC_BLOCK_M), waves = div_up(base, 148);
+    int tm = div_up(div_up(B, waves * 148), 8) * 8;
+    if (tm < 64) tm = 64;
+    if (tm > TC_BLOCK_M || base <= 148 / 2) tm = TC_BLOCK_M;
+    p.tile_m = tm;
+  }
+  p.m_tiles = div_up(B, p.tile_m);
   p.nb_total = nb_total;
+  static unsigned long long* trace_buf = nullptr;
+  static int trace_calls = 0;
+  p.trace = nullptr;
+  if (getenv("LF_FWD_TRACE")) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 148 * 8 * sizeof(unsigned long long));
+    p.trace = trace_buf;
+  }
   for (int m = 0; m < 2; ++m) { p.bias[m] = bias[m]; p.z[m] = z[m]; }
   p.avg = avg; p.zdf = zdf; p.conf = conf; p.rowstat = rowstat; p.label = label; p.partials = partials;
   for (int m = 0; m < 2; ++m)
@@ -454,7 +504,7 @@ int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2],
     }
   CUtensorMap mA[2], mW[2];
   for (int m = 0; m < 2; ++m) {
-    int rc = make_map(&mA[m], feat[m], D, B, D, p.kb_elems, TC_BLOCK_M, false, p.elem);
+    int rc = make_map(&mA[m], feat[m], D, B, D, p.kb_elems, p.tile_m, false, p.elem);
     if (rc) return rc;
     rc = make_map(&mW[m], weight[m], D, C, D, p.kb_elems, p.block_n, false, p.elem);
     if (rc) return rc;
@@ -468,6 +518,21 @@ int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2],
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   const int grid = p.m_tiles < 148 ? p.m_tiles : 148;
   if (grid_out) *grid_out = grid;
+  if (p.trace && ++trace_calls == 12) {
+    int rc = launch_fwd<7>(mA, mW, p, grid, smem, s);
+    cudaStreamSynchronize(s);
+    static unsigned long long h[148 * 8];
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < grid; ++c) if (h[c * 8] < t0) t0 = h[c * 8];
+    const char* nm[8] = {"entry", "setup", "first_load", "last_load", "first_full", "last_commit", "epi_done", "exit"};
+    for (int k = 0; k < 8; ++k) {
+      double mn = 1e30, mx = 0, sum = 0;
+      for (int c = 0; c < grid; ++c) { const double v = (double)(h[c * 8 + k] - t0) / 1000.0; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; }
+      fprintf(stderr, "[fwd trace] %-12s min %7.2f  avg %7.2f  max %7.2f us\n", nm[k], mn, sum / grid, mx);
+    }
+    return rc;
+  }
   switch (p.block_n / 16) {
     case 2: return launch_fwd<2>(mA, mW, p, grid, smem, s);
     case 3: return launch_fwd<3>(mA, mW, p, grid, smem, s);
