@@ -15,7 +15,10 @@
 // Persistent: one CTA per SM walks a static list of (batch, split, m tile, n tile) items.  Roles:
 //   warp 0    TMA producer, runs ahead across item boundaries through a multi-stage full/empty mbarrier ring
 //   warp 1    TMEM allocator + single-thread MMA issuer; accumulators are DOUBLE-BUFFERED in TMEM
-//   warps 2-5 epilogue: tcgen05.ld -> registers -> swizzled smem box -> TMA store (cp.async.bulk.tensor
+//   warps 2-9 epilogue, two halves of four warps (one warp per TMEM lane quarter in each half): the halves take
+//             alternate 128-byte column chunks of the accumulator, each with its own pair of staging boxes, named
+//             barrier and TMA-store issuing thread (with one half the epilogue, not HBM, bounded tc_dfeat: 10 items
+//             per CTA x ~2.5 us).  tcgen05.ld -> registers -> swizzled smem box -> TMA store (cp.async.bulk.tensor
 //             shared->global), so the store of tile i overlaps the loads and MMAs of tile i+1.
 //             Outputs whose row pitch is not a multiple of 16 B (logits, C = 309) take a transposing path
 //             with 128-byte coalesced stores instead.
@@ -30,8 +33,8 @@
 
 namespace lf {
 
-constexpr int TC_THREADS = 192;
-constexpr int TC_STAGING_BYTES = 2 * TC_BLOCK_M * 128;   // two [128 rows x 128 B] store boxes
+constexpr int TC_THREADS = 320;                          // producer warp, MMA warp, 2 x 4 epilogue warps
+// staging: two [128 rows x 128 B] store boxes per epilogue half (TcGemmParams::epi_halves = 1 or 2)
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -113,7 +116,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t b_bytes = (uint32_t)p.block_n * TC_BLOCK_K * 4;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
   uint8_t* staging = smem + (size_t)stages * stage_bytes;            // 1024-aligned (stage_bytes is)
-  uint64_t* full_bar = (uint64_t*)(staging + TC_STAGING_BYTES);
+  uint64_t* full_bar = (uint64_t*)(staging + (size_t)2 * p.epi_halves * TC_BLOCK_M * 128);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;                      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                      // [2]
@@ -126,7 +129,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (p.nbatch > 1) { tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB1); }
     if (p.tma_store) { tma_prefetch_desc(&mapO0); if (p.nbatch > 1) tma_prefetch_desc(&mapO1); }
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4 * p.epi_halves); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -175,12 +178,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (p.elem == 4) mma_issue_loop<true>(p, smem, stage_bytes, a_bytes, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
       else mma_issue_loop<false>(p, smem, stage_bytes, a_bytes, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
     }
-  } else {
+  } else if (warp < 2 + 4 * p.epi_halves) {
     // ===================== epilogue =====================
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;                // 0..127
+    const int half = (warp - 2) >> 2;               // which of the two epilogue halves
+    const int et = (threadIdx.x - 64) & 127;        // 0..127 within the half
     const int row_in_tile = q * 32 + lane;
-    uint32_t li = 0, cc = 0;                        // local item counter, running store-chunk counter
+    uint32_t li = 0, cc = 0;                        // local item counter, this half's running store-chunk counter
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++li) {
       const Item w = decode_item(p, item);
       const uint32_t buf = li & 1;
@@ -190,7 +194,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const CUtensorMap* mapO = w.batch == 0 ? &mapO0 : &mapO1;
       if (p.tma_store) {
         const int ccols = 128 / p.out_elem;                 // output columns per 128-byte staging row: 32 fp32 / 64 bf16
-        for (int c0 = 0; c0 < p.block_n; c0 += ccols, ++cc) {
+        for (int c0 = half * ccols; c0 < p.block_n; c0 += p.epi_halves * ccols, ++cc) {
           uint32_t pk[32];                                   // 128 bytes of this thread's output row
           if (p.out_elem == 4) {
             float v[32];
@@ -215,21 +219,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               }
             }
           }
-          uint8_t* box = staging + (cc & 1) * (TC_BLOCK_M * 128);
+          uint8_t* box = staging + (half * 2 + (cc & 1)) * (TC_BLOCK_M * 128);
           if (et == 0) tma_store_wait_read<1>();     // the store that last used this box has read it
-          named_bar_sync(1, 128);
+          named_bar_sync(1 + half, 128);
           uint8_t* rowp = box + row_in_tile * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)                 // SWIZZLE_128B: 16-byte chunk j of row r lives at j ^ (r & 7)
             *reinterpret_cast<uint4*>(rowp + ((j ^ (row_in_tile & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           fence_proxy_async();
-          named_bar_sync(1, 128);
+          named_bar_sync(1 + half, 128);
           if (et == 0) {
             tma_store_3d(mapO, box, w.n0 + c0, w.m0, w.split);
             tma_store_commit();
           }
         }
-      } else {
+      } else if (half == 0) {
         // transposing path: 32x32 blocks through a padded per-warp tile, 128 contiguous bytes per store
         float* tile = reinterpret_cast<float*>(staging) + q * (32 * 33);
         const int row0 = w.m0 + q * 32;
@@ -401,7 +405,11 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4;
   const uint32_t b_bytes = (uint32_t)d.block_n * TC_BLOCK_K * 4;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
-  const size_t fixed = TC_STAGING_BYTES + 256;
+  // the second epilogue half pays when the epilogue bounds the kernel: short K (tc_dfeat of a <= 128-way head: ten
+  // 128 x 256 output tiles per CTA, two k-blocks each); with long K its two extra staging boxes cost a pipeline stage
+  p.epi_halves = (p.tma_store && d.K <= 128) ? 2 : 1;
+  const size_t staging_bytes = (size_t)2 * p.epi_halves * TC_BLOCK_M * 128;
+  const size_t fixed = staging_bytes + 256;
   int stages = 8;
   while (stages > 2 && (size_t)stages * stage_bytes + fixed > 226 * 1024) --stages;
   p.stages = stages;

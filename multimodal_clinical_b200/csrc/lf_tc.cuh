@@ -16,6 +16,7 @@ struct TcGemmParams {
   int tmem_cols;           // 2 * acc_cols (double-buffered)
   int a_mn_major, b_mn_major;
   int tma_store;           // epilogue writes through cp.async.bulk.tensor (needs a 16-byte output pitch)
+  int epi_halves;          // 1 or 2 groups of four epilogue warps taking alternate 128-byte column chunks
   int elem;                // operand element size: 4 = fp32 consumed as TF32, 2 = bf16
   int out_elem;            // output element size (TMA-store epilogue): 4 = fp32, 2 = bf16
   int kb_elems;            // K elements per stage (128 B per operand row): 32 / 64
