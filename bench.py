@@ -89,6 +89,8 @@ def kernel_alg_bytes(name, w, B, fe=4):
     table = {
         "sgemm_logits": logits, "tc_logits": logits,
         "tc_heads_forward": (2 * B * D + 2 * C * D + n_out * B * C) * f + 8 * B,
+        # fused QMF forward: features + heads in, z1 z2 avg z_df (fp32) + conf (2) + row statistics (4) out, labels in
+        "tc_forward_qmf": (2 * B * D + 2 * C * D) * fe + (4 * B * C + 6 * B) * f + 8 * B,
         "rows_forward_qmf": (2 * B * C + 2 * B * C + 2 * B + 4 * B) * f + 8 * B,
         "rows_forward_jlogits": (2 * B * C + B * C) * f + B * ldz * fe + 8 * B,
         "rows_backward_qmf": (2 * B * C + 8 * B) * f + 2 * B * ldz * fe + 8 * B,

@@ -62,16 +62,26 @@ static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 static thread_local cudaEvent_t g_pending = nullptr;
 
+// events come from a pool refilled in lf_profile_report: cudaEventCreate on the launch path made the profiled
+// (eager) steps host-bound, and the idle gaps landed inside the kernels' event brackets
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t take_event() {
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
 void prof_begin(const char*, cudaStream_t s) {
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
-  cudaEventCreate(&g_pending);
+  g_pending = take_event();
   cudaEventRecord(g_pending, s);
 }
 void prof_end(const char* name, cudaStream_t s) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (!g_prof_on.load(std::memory_order_relaxed) || !g_pending) return;
   ProfRec r; r.name = name; r.e0 = g_pending; g_pending = nullptr;
-  cudaEventCreate(&r.e1);
+  r.e1 = take_event();
   cudaEventRecord(r.e1, s);
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.push_back(r);
@@ -198,7 +208,13 @@ using namespace lf;
 extern "C" const char* lf_last_error(void) { return g_err; }
 extern "C" int32_t lf_abi_version(void) { return LF_ABI_VERSION; }
 extern "C" int64_t lf_launch_count(void) { return g_launches.load(); }
-extern "C" void lf_profile_enable(int32_t on) { g_prof_on.store(on ? 1 : 0); }
+extern "C" void lf_profile_enable(int32_t on) {
+  if (on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    while (g_event_pool.size() < 2048) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; g_event_pool.push_back(e); }
+  }
+  g_prof_on.store(on ? 1 : 0);
+}
 
 // Synchronises the device, then writes "name count total_ms\n" lines for every kernel timed since the
 // last report and clears the records.  Returns the number of bytes written (excluding the NUL).
@@ -213,7 +229,7 @@ extern "C" int32_t lf_profile_report(char* buf, int32_t buf_bytes) {
         auto& a = agg[r.name];
         a.first += 1; a.second += ms;
       }
-      cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+      g_event_pool.push_back(r.e0); g_event_pool.push_back(r.e1);
     }
     g_prof.clear();
   }

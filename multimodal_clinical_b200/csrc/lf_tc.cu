@@ -292,9 +292,35 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Encoded tensor maps are cached per thread, keyed by every argument of the encode call: an eager training step issues
+// 16 of them over the same handful of buffers, and cuTensorMapEncodeTiled (~1-2 us of host time each) was a visible
+// part of the host cost of a step that takes 150 us on the device.
+struct MapKey {
+  const void* base; long long d0, d1, d2, s0, s1; int b0, b1, b2, elem, swz, rank;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s0 == o.s0 && s1 == o.s1 && b0 == o.b0 && b1 == o.b1 &&
+           b2 == o.b2 && elem == o.elem && swz == o.swz && rank == o.rank;
+  }
+};
+struct MapCache {
+  static constexpr int N = 64;
+  MapKey key[N]; CUtensorMap val[N]; int used = 0, next = 0;
+  const CUtensorMap* find(const MapKey& k) const {
+    for (int i = 0; i < used; ++i) if (key[i] == k) return &val[i];
+    return nullptr;
+  }
+  void put(const MapKey& k, const CUtensorMap& v) {
+    const int i = used < N ? used++ : (next = (next + 1) % N);
+    key[i] = k; val[i] = v;
+  }
+};
+static thread_local MapCache g_maps;
+
 // 2-D tensor map: `inner` contiguous elements per row, `outer` rows, row pitch ld elements.
 int make_map(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld,
              int box_inner, int box_outer, bool mn_major, int elem, int mn_swizzle) {
+  const MapKey mk{base, inner, outer, 0, ld, 0, box_inner, box_outer, 0, elem, mn_major ? 1000 + mn_swizzle : 0, 2};
+  if (const CUtensorMap* hit = g_maps.find(mk)) { *map = *hit; return LF_OK; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return LF_ERR_CUDA; }
   if (((uintptr_t)base & 15) || (ld * elem) % 16) { set_error("TMA operand must be 16-byte aligned with a 16-byte row pitch"); return LF_ERR_BAD_ARG; }
@@ -308,12 +334,15 @@ int make_map(CUtensorMap* map, const void* base, long long inner, long long oute
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return LF_ERR_CUDA; }
+  g_maps.put(mk, *map);
   return LF_OK;
 }
 
 // 3-D output map for the TMA-store epilogue: (cols, rows, splits), box [32 x 128 x 1], SWIZZLE_128B.
 static int make_store_map(CUtensorMap* map, void* base, long long cols, long long rows, long long ld,
                           long long splits, long long split_stride, int elem, int tile_m) {
+  const MapKey mk{base, cols, rows, splits, ld, split_stride, 128 / elem, tile_m, 1, elem, 0, 3};
+  if (const CUtensorMap* hit = g_maps.find(mk)) { *map = *hit; return LF_OK; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return LF_ERR_CUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)splits};
@@ -324,6 +353,7 @@ static int make_store_map(CUtensorMap* map, void* base, long long cols, long lon
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(store) failed (%d)", (int)r); return LF_ERR_CUDA; }
+  g_maps.put(mk, *map);
   return LF_OK;
 }
 

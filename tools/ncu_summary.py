@@ -16,7 +16,7 @@ with open(out + "_ncu_full_summary.csv", "w", newline="") as f:
     wr.writerow([h[i] for i in idx]); wr.writerow([rows[1][i] for i in idx])
     for r in rows[2:]:
         wr.writerow([r[i] for i in idx])
-names = {"rows_forward_vec_kernel<1": "rows_forward_qmf", "rows_forward_vec_kernel<0": "rows_forward_jlogits",
+names = {"tc_fwd_qmf_kernel": "tc_forward_qmf", "rows_forward_vec_kernel<1": "rows_forward_qmf", "rows_forward_vec_kernel<0": "rows_forward_jlogits",
          "rows_backward_vec_kernel<1": "rows_backward_qmf", "rows_backward_vec_kernel<0": "rows_calibrated",
          "mid_kernel": "step_mid", "finalize_grads_kernel": "finalize_grads", "finalize_stats_kernel": "finalize_stats",
          "rows_forward_reg_kernel<1": "rows_forward_qmf", "rows_forward_reg_kernel<0": "rows_forward_jlogits",
