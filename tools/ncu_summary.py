@@ -28,7 +28,8 @@ for r in rows[2:]:
     n = r[ki]
     label = next((v for k, v in names.items() if k in n), None)
     if label is None and "tc_gemm_kernel" in n:
-        label = os.environ.get("TC_ORDER", "tc_dfeat,tc_dweight,tc_logits").split(",")[len([1 for k in traffic if k.startswith("tc_")]) % 3]
+        order = os.environ.get("TC_ORDER", "tc_dfeat,tc_dweight,tc_logits").split(",")
+        label = order[len([1 for k in traffic if k in order]) % len(order)]
     if label is None and "tc_heads_forward" in n:
         label = "tc_heads_forward"
     if label and label not in traffic:
