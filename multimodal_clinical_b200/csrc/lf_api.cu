@@ -369,6 +369,9 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
       d.lda = ldz; d.ldb = a->dim; d.ld_out = a->dim;
       d.a_mn_major = 0; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 64) * 64;
       d.splits = 1; d.split_stride = 0; d.balance_m = 0; d.name = "tc_dfeat";
+      // sharded runs (phase 2) overlap dfeat with the peer all-reduce on a side stream: keep the CTA small enough
+      // (192 threads) for the all-reduce CTAs to be co-resident, or the exchange waits for dfeat to drain
+      d.max_epi_halves = phase == 2 ? 1 : 2;
       rc = tc_gemm(d, s);
     } else {
       rc = gemm_dfeat(g, 2, s);

@@ -437,7 +437,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
   // the second epilogue half pays when the epilogue bounds the kernel: short K (tc_dfeat of a <= 128-way head: ten
   // 128 x 256 output tiles per CTA, two k-blocks each); with long K its two extra staging boxes cost a pipeline stage
-  p.epi_halves = (p.tma_store && d.K <= 128) ? 2 : 1;
+  p.epi_halves = (p.tma_store && d.K <= 128 && d.max_epi_halves >= 2) ? 2 : 1;
   const size_t staging_bytes = (size_t)2 * p.epi_halves * TC_BLOCK_M * 128;
   const size_t fixed = staging_bytes + 256;
   int stages = 8;
@@ -450,7 +450,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = p.total_items < 148 ? p.total_items : 148;
-  LF_LAUNCH(d.name, s, launch_pdl(tc_gemm_kernel, dim3(grid), dim3(TC_THREADS), smem, s, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p));
+  LF_LAUNCH(d.name, s, launch_pdl(tc_gemm_kernel, dim3(grid), dim3(64 + 128 * p.epi_halves), smem, s, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p));
   return check_launch(d.name);
 }
 

@@ -51,6 +51,7 @@ struct TcGemmDesc {
   long long split_stride;
   int elem = 4;            // 4 = fp32 operands (TF32 MMA), 2 = bf16 operands
   int out_elem = 4;        // 4 = fp32 output, 2 = bf16 output (TMA-store epilogue only)
+  int max_epi_halves = 2;  // 1: never add the second group of epilogue warps (the CTA then leaves room for a concurrent kernel)
   int balance_m = 0;           // 1: pick tile_m so that the number of work items is a multiple of the SM count (K-major A, plain-store epilogue only)
   const char* name;
 };
