@@ -165,6 +165,50 @@ def test_qmf_tensor_pipe_matches_oracle(B, D, C, N):
         assert_close(eng.ema_x, ref["ema_x"], TOL_TENSOR, "ema")
 
 
+@pytest.mark.parametrize("B,D,C,N,prec", [(300, 128, 32, 700, "tf32"), (257, 96, 33, 500, "tf32"), (515, 256, 48, 900, "bf16"),
+                                          (260, 64, 64, 300, "tf32"), (333, 128, 80, 600, "bf16"), (270, 192, 96, 400, "tf32"),
+                                          (1100, 128, 112, 2000, "tf32"), (520, 256, 128, 1500, "bf16"),
+                                          (20000, 128, 101, 30000, "tf32"), (19, 64, 57, 40, "tf32")])
+def test_fused_forward_kernel_all_widths_and_tilings(B, D, C, N, prec):
+    """The fused QMF forward (lf_tc_fwd.cu) is instantiated per 16-column chunk count (C = 32..128 -> 2..8 chunks, two or
+    four column shares per TMEM lane quarter) and sizes its M tiles from the batch (B = 20000 -> 296 tiles of 72 samples,
+    half-empty lane quarters): every instantiation against the fp64 oracle, forward outputs AND the statistics that feed
+    the History / EMA / loss, plus the integer accuracy counts of the fp32-rounded logits."""
+    inp = O.make_inputs(B, D, C, seed=B + C, n_data=N)
+    eng = _step(num_classes=C, mode="qmf", n_data=N, precision=prec)
+    hist = O.HistoryState(N)
+    ema = torch.zeros(2, C, dtype=torch.float64)
+    W = [inp["W1"], inp["W2"]]; b = [inp["b1"], inp["b2"]]
+    if prec == "bf16":
+        W = [w.bfloat16().float() for w in W]
+    for s in range(2):
+        step_in = O.make_inputs(B, D, C, seed=100 * s + B, n_data=N)
+        f = [step_in["f1"], step_in["f2"]]
+        if prec == "bf16":
+            f = [x.bfloat16().float() for x in f]
+        ref = O.qmf_step(f, W, b, step_in["y"], step_in["idx"], hist, ema_x=ema, dtype=torch.float64)
+        ema = ref["ema_x"]
+        out = eng.step([x.cuda() for x in f], [x.cuda() for x in W], [x.cuda() for x in b], step_in["y"].cuda(),
+                       idx=step_in["idx"].cuda())
+        torch.cuda.synchronize()
+        assert_close(out.loss, ref["loss"], TOL_TENSOR, "loss")
+        assert_close(out.logits_df, ref["logits_df"], TOL_TENSOR, "zdf")
+        assert_close(out.avg_logits, ref["avg_logits"], TOL_TENSOR, "avg")
+        for m in range(2):
+            assert_close(out.logits[m], ref["logits"][m], TOL_TENSOR, "logits")
+            assert_close(out.dweight[m], ref["dW"][m], TOL_TENSOR, "dW")
+            assert_close(out.dfeat[m].float(), ref["dfeat"][m], TOL_TENSOR, "dfeat")      # bf16 tensors in LF_PREC_BF16
+        assert_close(eng.ema_x, ref["ema_x"], TOL_TENSOR, "ema")
+        assert_close(eng.correctness, hist.correctness, 2e-3, "correctness")
+        # counts are exact functions of the logits the kernel itself produced
+        z1, z2, zdf, y = out.logits[0], out.logits[1], out.logits_df, step_in["y"].cuda()
+        acc = out.accuracies()
+        assert abs(acc["x1_acc_uncal"] - float((z1.argmax(1) == y).float().mean())) < 1e-6
+        assert abs(acc["x2_acc_uncal"] - float((z2.argmax(1) == y).float().mean())) < 1e-6
+        assert abs(acc["df_acc"] - float((zdf.argmax(1) == y).float().mean())) < 1e-6
+        assert abs(acc["joint_acc"] - float((out.avg_logits.argmax(1) == y).float().mean())) < 1e-6
+
+
 @pytest.mark.parametrize("B,D,C", [(2048, 768, 101), (777, 512, 309), (4096, 512, 309)])
 def test_jlogits_tensor_pipe_matches_oracle(B, D, C):
     inp = O.make_inputs(B, D, C, seed=B + C)
