@@ -266,7 +266,13 @@ class LateFusionStep:
         if qmf:
             if idx is None:
                 raise ValueError("QMF step needs the dataset indices of the batch (idx)")
-            p_idx.copy_(idx.reshape(-1))
+            idx = idx.reshape(-1)
+            if self.world == 1:
+                # one GPU: nothing is exchanged, step_mid reads the caller's indices in place (no copy kernel)
+                idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
+                self._idx_keep = idx
+            else:
+                p_idx.copy_(idx)
 
         a = LfHeadsArgs()
         a.batch, a.batch_global, a.dim, a.classes = B, Bg, D, Cn
@@ -308,7 +314,7 @@ class LateFusionStep:
         mid.stats_parts, mid.stats_stride = base, stride // 8
         if qmf:
             qs = self.qmf_state
-            mid.idx_parts, mid.idx_stride = base + self._off_idx, stride // 8
+            mid.idx_parts, mid.idx_stride = (idx.data_ptr() if self.world == 1 else base + self._off_idx), stride // 8
             mid.conf_parts, mid.conf_stride = base + self._off_conf, stride // 4
             mid.correctness, mid.confidence = _ptr(qs.correctness), _ptr(qs.confidence)
             mid.last_writer, mid.step_base = _ptr(qs.last_writer), 0      # device-resident ticket counter
