@@ -518,8 +518,21 @@ int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2],
   const size_t smem = (size_t)stages * stage_bytes + fixed;
   const int grid = p.m_tiles < 148 ? p.m_tiles : 148;
   if (grid_out) *grid_out = grid;
-  if (p.trace && ++trace_calls == 12) {
-    int rc = launch_fwd<7>(mA, mW, p, grid, smem, s);
+  int rc = LF_ERR_UNSUPPORTED;
+  switch (p.block_n / 16) {
+    case 2: rc = launch_fwd<2>(mA, mW, p, grid, smem, s); break;
+    case 3: rc = launch_fwd<3>(mA, mW, p, grid, smem, s); break;
+    case 4: rc = launch_fwd<4>(mA, mW, p, grid, smem, s); break;
+    case 5: rc = launch_fwd<5>(mA, mW, p, grid, smem, s); break;
+    case 6: rc = launch_fwd<6>(mA, mW, p, grid, smem, s); break;
+    case 7: rc = launch_fwd<7>(mA, mW, p, grid, smem, s); break;
+    case 8: rc = launch_fwd<8>(mA, mW, p, grid, smem, s); break;
+    default:
+      set_error("tc_heads_forward_qmf: unsupported class count %d", C);
+      return LF_ERR_UNSUPPORTED;
+  }
+  if (rc == LF_OK && p.trace && ++trace_calls == 12) {
+    // LF_FWD_TRACE=1 (eager launches only): per-role %globaltimer stamps of the 12th call, relative to the first CTA's entry
     cudaStreamSynchronize(s);
     static unsigned long long h[148 * 8];
     cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
@@ -531,19 +544,8 @@ int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2],
       for (int c = 0; c < grid; ++c) { const double v = (double)(h[c * 8 + k] - t0) / 1000.0; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; }
       fprintf(stderr, "[fwd trace] %-12s min %7.2f  avg %7.2f  max %7.2f us\n", nm[k], mn, sum / grid, mx);
     }
-    return rc;
   }
-  switch (p.block_n / 16) {
-    case 2: return launch_fwd<2>(mA, mW, p, grid, smem, s);
-    case 3: return launch_fwd<3>(mA, mW, p, grid, smem, s);
-    case 4: return launch_fwd<4>(mA, mW, p, grid, smem, s);
-    case 5: return launch_fwd<5>(mA, mW, p, grid, smem, s);
-    case 6: return launch_fwd<6>(mA, mW, p, grid, smem, s);
-    case 7: return launch_fwd<7>(mA, mW, p, grid, smem, s);
-    case 8: return launch_fwd<8>(mA, mW, p, grid, smem, s);
-  }
-  set_error("tc_heads_forward_qmf: unsupported class count %d", C);
-  return LF_ERR_UNSUPPORTED;
+  return rc;
 }
 
 }  // namespace lf
