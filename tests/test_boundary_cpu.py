@@ -127,3 +127,25 @@ def test_builtin_trainer_calls_hooks_in_lightning_order(tmp_path):
     assert os.path.exists(ck.best_model_path)
     tr.test(m, dataloaders=data)
     assert calls[-3:] == [("test", 0), ("test", 1), "test_end"]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores; the only bench arm that runs without a GPU):
+    one JSON line with the contract's keys, `impl: reference`, zero H2D/D2H bytes and a cpu_baseline describing itself."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "k2",
+                          "--steps", "2", "--warmup", "3"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "fusion_step_train_samples_per_sec"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert "workload" in line["config"] and line["config"]["workload"].startswith("k2")
