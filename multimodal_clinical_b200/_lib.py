@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "_lf_fusion.so")
 
 LF_MODE_JLOGITS, LF_MODE_QMF = 0, 1
 LF_PREC_FP32, LF_PREC_TF32, LF_PREC_BF16 = 0, 1, 2
+LF_LOSS_NO_JOINT, LF_LOSS_NO_UNI = 1, 2          # LfHeadsArgs.loss_terms / LfMidArgs.loss_terms bits (QMF loss ablations)
 LF_MOD_OGM_GE, LF_MOD_OGM, LF_MOD_NOISE = 0, 1, 2
 LF_STATS_HEADER = 16
 LF_MAX_TENSORS = 64

@@ -3,12 +3,11 @@ cremad/joint_model_qmf.py in ONE line each (which terms enter ``loss``), so they
 pass the dropped terms to the fused step as LF_LOSS_* bits (include/lf_fusion.h)."""
 import torch.nn as nn
 
+from .._lib import LF_LOSS_NO_JOINT, LF_LOSS_NO_UNI  # noqa: F401  (re-exported to the ablation modules)
 from ..existing_algos.QMF import QMF
 from ..heads import FusedLateFusionHead
 from ._pool import pool_features
 from .backbone import resnet18
-
-LF_LOSS_NO_JOINT, LF_LOSS_NO_UNI = 1, 2
 
 
 class QmfFusionNet(nn.Module):
