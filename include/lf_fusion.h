@@ -195,7 +195,8 @@ typedef struct LfPeerComm {
   void* recv_payload[LF_MAX_RANKS]; /* rank r's payload receive area: [2 parities][n_ranks][payload bytes] */
   void* recv_grad[LF_MAX_RANKS];    /* rank r's gradient receive area: [2 parities][n_ranks][n_padded floats] */
   int64_t* epoch;                   /* local, device-resident: epoch[0] payload exchanges done, epoch[1] gradient exchanges */
-  int32_t* error;                   /* local: set to 1 when a peer did not arrive within ~2 s */
+  int32_t* error;                   /* device-visible (ideally pinned host) flag: set to 1 right before the kernel traps
+                                       because a peer did not arrive within minutes */
 } LfPeerComm;
 
 typedef struct LfPeerReduceArgs {

@@ -17,7 +17,7 @@ def _datasets(args):
     except ImportError:
         n = int(getattr(args, "synthetic_samples", 256))
         # audio spectrogram (1,H,W), visual (3,T,H,W) -- small so the ResNet18 producers stay cheap
-        return splits(n, (1, 65, 65), (3, 2, 64, 64), args.num_classes, with_idx=args.model_type == "qmf", seed=args.seed)
+        return splits(n, (1, 65, 65), (3, 2, 64, 64), args.num_classes, with_idx=('qmf' in args.model_type or 'lreg' in args.model_type), seed=args.seed)
 
 
 def run_training(argv=None):

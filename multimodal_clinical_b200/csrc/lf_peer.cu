@@ -10,7 +10,8 @@
 // Receive areas are double-buffered by epoch parity: a rank can run at most one epoch ahead of the slowest
 // peer (it needs that peer's flag for the epoch in between), so slot [e & 1] is never overwritten while a
 // peer still reads it.  The epoch counter is device-resident, which makes the launches replayable from a
-// CUDA graph.  Spins are bounded (~2 s) so a lost peer surfaces as an error flag, not a hung GPU.
+// CUDA graph.  The flag wait is that of a collective: it tolerates rank skew of seconds; only a peer missing for
+// minutes makes the kernel record the failure in a host-visible flag and trap (lf_peer.cuh::peer_barrier).
 #include <cooperative_groups.h>
 #include <string.h>
 #include "lf_common.cuh"

@@ -15,6 +15,8 @@ __device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
   return v;
 }
 
+constexpr unsigned long long kPeerWaitNs = 120ull * 1000000000ull;
+
 // Called by every thread of the (cooperatively launched) grid after its peer stores.  flags_set: 0 = payload, 1 = gradients.
 __device__ __forceinline__ void peer_barrier(const LfPeerComm& c, int flags_set, long long epoch, cg::grid_group& grid) {
   __threadfence_system();
@@ -23,10 +25,24 @@ __device__ __forceinline__ void peer_barrier(const LfPeerComm& c, int flags_set,
     const int r = threadIdx.x;
     st_release_sys((long long*)c.flags[r] + flags_set * LF_MAX_RANKS + c.rank, epoch);       // my flag on rank r
     const long long* mine = (const long long*)c.flags[c.rank] + flags_set * LF_MAX_RANKS + r;  // rank r's flag here
-    const long long t0 = clock64();
+    // Wait like a collective does: rank skew of seconds is routine in training (checkpoint writes, data-loader
+    // respawns, first-iteration lazy init), so the wait is NOT bounded by a short timeout.  Only after
+    // kPeerWaitNs (2 minutes: a peer that is this late is gone) the kernel records the failure and TRAPS: the
+    // launch fails loudly (sticky CUDA error at the next synchronisation, PeerComm.check() reports the cause) and
+    // nothing after the barrier -- the receive area, epoch[], the replicated EMA / History -- is touched.
+    unsigned long long t0 = 0, spins = 0;
     while (ld_acquire_sys(mine) < epoch) {
-      if (clock64() - t0 > 4000000000LL) { c.error[0] = 1; break; }                            // ~2 s
       __nanosleep(64);
+      if ((++spins & 1023) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kPeerWaitNs) {
+          *(volatile int*)c.error = 1;
+          __threadfence_system();
+          __trap();
+        }
+      }
     }
   }
   grid.sync();

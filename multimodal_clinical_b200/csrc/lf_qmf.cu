@@ -202,9 +202,10 @@ extern "C" int lf_qmf_history_step(const LfQmfArgs* a, void* stream) {
       !a->workspace) { set_error("lf_qmf_history_step: null argument"); return LF_ERR_BAD_ARG; }
   if ((a->flags & ~LF_QMF_ALL) || a->flags == 0) { set_error("lf_qmf_history_step: bad flags %d", a->flags); return LF_ERR_BAD_ARG; }
   if ((a->flags & LF_QMF_REG) && !a->qmf_g) { set_error("lf_qmf_history_step: LF_QMF_REG needs qmf_g"); return LF_ERR_BAD_ARG; }
-  if (a->batch_global < 2) {
-    // the reference raises for B == 1 (len() of a 0-d array)
-    set_error("lf_qmf_history_step: batch_global must be >= 2 (reference raises for a batch of one)");
+  if (a->batch_global < 1 || ((a->flags & LF_QMF_REG) && a->batch_global < 2)) {
+    // the reference raises for B == 1 only in reg_loss / get_target_margin (len() of a 0-d array);
+    // History.correctness_update alone works on a batch of one (existing_algos/QMF.py:20-29)
+    set_error("lf_qmf_history_step: batch_global must be >= 2 for the ranking loss (reference raises for a batch of one)");
     return LF_ERR_BAD_ARG;
   }
   if (a->n_data < 1 || a->step_base < 0 || a->g_begin < 0 || a->g_count < 0 ||

@@ -370,14 +370,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   p.mn_box_bytes = 128 * p.kb_elems;
   if (p.elem == 4) { p.mn_step = 1024; p.mn_lbo = 4096; p.mn_sbo = 512; p.mn_lt = 1; }     // 128B swizzle, 32-byte atoms
   else { p.mn_step = 2048; p.mn_lbo = 8192; p.mn_sbo = 1024; p.mn_lt = 2; }                // plain 128B swizzle
-  int mn_swz = 0;
-  if (p.elem == 2) {                                       // experiment overrides (tools/dbg_tc16.py)
-    if (getenv("LF_TC16_STEP")) p.mn_step = (unsigned)atoi(getenv("LF_TC16_STEP"));
-    if (getenv("LF_TC16_LBO")) p.mn_lbo = (unsigned)atoi(getenv("LF_TC16_LBO"));
-    if (getenv("LF_TC16_SBO")) p.mn_sbo = (unsigned)atoi(getenv("LF_TC16_SBO"));
-    if (getenv("LF_TC16_LT")) p.mn_lt = (unsigned)atoi(getenv("LF_TC16_LT"));
-    if (getenv("LF_TC16_SWZ")) mn_swz = atoi(getenv("LF_TC16_SWZ"));
-  }
+  const int mn_swz = 0;
   if ((d.b_mn_major && d.block_n % p.mn_box) || (p.out_elem == 2 && d.block_n % 64)) { set_error("tc_gemm: block_n %d not a multiple of the box width", d.block_n); return LF_ERR_BAD_ARG; }
   p.block_n = d.block_n;
   p.nbatch = d.nbatch;

@@ -18,7 +18,7 @@ class FusionNet(nn.Module):
         self.x1_model = MLP(input_dim=768, hidden_dim=512, num_classes=num_classes)
         self.x2_model = MLP(input_dim=768, hidden_dim=512, num_classes=num_classes)
         self.fused = FusedLateFusionHead(num_classes, mode="jlogits",
-                                         precision=getattr(args, "head_precision", "fp32"))
+                                         precision=getattr(args, "head_precision", "auto"))
 
     def forward(self, x1_data, x2_data, label):
         output = self.model(x1_data, x2_data)

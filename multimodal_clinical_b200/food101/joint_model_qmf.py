@@ -23,7 +23,7 @@ class FusionNet(nn.Module):
         self.x1_model = MLP(input_dim=768, hidden_dim=512, num_classes=self.num_classes)
         self.x2_model = MLP(input_dim=768, hidden_dim=512, num_classes=self.num_classes)
         self.fused = FusedLateFusionHead(self.num_classes, mode="qmf", n_data=self.args.num_samples,
-                                         precision=getattr(args, "head_precision", "fp32"))
+                                         precision=getattr(args, "head_precision", "auto"))
         self.fused.bind_qmf(self.qmf)
 
     def forward(self, x1_data, x2_data, label, idx):

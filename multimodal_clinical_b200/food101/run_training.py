@@ -13,7 +13,7 @@ def _datasets(args):
         return get_data(args)
     except ImportError:
         n = int(getattr(args, "synthetic_samples", 1024))
-        return splits(n, (768,), (768,), args.num_classes, with_idx=args.model_type == "qmf", seed=args.seed)
+        return splits(n, (768,), (768,), args.num_classes, with_idx=('qmf' in args.model_type or 'lreg' in args.model_type), seed=args.seed)
 
 
 def run_training(argv=None):

@@ -70,20 +70,33 @@ class FusedLateFusionHead(nn.Module):
     """
 
     def __init__(self, num_classes: int, mode: str = "jlogits", n_data: Optional[int] = None,
-                 precision: str = "fp32", ema_smoothing: float = 0.05, loss_terms: int = 0):
+                 precision: str = "auto", ema_smoothing: float = 0.05, loss_terms: int = 0,
+                 process_group=None, sharded: bool = False):
         super().__init__()
         if mode not in ("jlogits", "ogm_ge", "qmf"):
             raise NotImplementedError(f"fused head mode {mode!r}")
+        if precision not in ("auto", "fp32", "tf32", "bf16"):
+            raise ValueError(f"head precision {precision!r}")
         self.num_classes = int(num_classes)
         self.mode = mode
         self.n_data = n_data
+        # "auto" follows what the trainer asked PyTorch for (utils/run_trainer.py:47, cremad/run_trainer.py:22), see
+        # resolve_precision(); "fp32" / "tf32" / "bf16" pin the arithmetic of the three head GEMMs
         self.precision = precision
+        # Batch-sharded (global-batch) semantics are OPT-IN: with sharded=False the head treats the batch it is
+        # given as the whole batch even when torch.distributed is initialised, which is what a DDP wrapper
+        # (Lightning strategy="auto" on several GPUs) expects -- DDP then averages every gradient, heads included.
+        # sharded=True (optionally with a process group) makes the step global: statistics, History, EMA and head
+        # gradients are exchanged inside the step and must NOT be reduced again by the caller.
+        self.sharded = bool(sharded) or process_group is not None
+        self.process_group = process_group
         self.ema_smoothing = ema_smoothing
         self.loss_terms = int(loss_terms)            # QMF loss ablations (LF_LOSS_* bits of include/lf_fusion.h)
         self.ogm_alpha: Optional[float] = None       # set by OGMGEBaseModel: coefficients come out of the same pass
         self.update_ema = True
         self.last_step: Optional[StepOutput] = None
         self._engine: Optional[LateFusionStep] = None
+        self._engines = {}                           # (device, precision) -> engine; all share the EMA / History state
         self._grad_enabled = True
         self._ema = None
         self._qmf_state = None
@@ -92,20 +105,58 @@ class FusedLateFusionHead(nn.Module):
         """Share the calibration state with the LightningModule's ``utils.EMA.EMA`` (utils/BaseModel.py:30)."""
         self._ema = ema
         self._engine = None
+        self._engines = {}
 
     def bind_qmf(self, qmf) -> None:
         """Share the History arrays with the FusionNet's ``existing_algos.QMF.QMF`` object."""
         self._qmf_state = qmf._state
         self.n_data = qmf._state.n_data
         self._engine = None
+        self._engines = {}
 
-    def _get_engine(self, device) -> LateFusionStep:
-        if self._engine is None or self._engine.device != device:
-            self._engine = LateFusionStep(self.num_classes, mode=self.mode, n_data=self.n_data, device=device,
-                                          precision=self.precision, ema_smoothing=self.ema_smoothing,
-                                          qmf_state=self._qmf_state, ema=self._ema, loss_terms=self.loss_terms)
-            self._engine.fresh_outputs = True
-        return self._engine
+    def resolve_precision(self, f1: torch.Tensor) -> str:
+        """Arithmetic of the head GEMMs for this call.  Explicit settings win; "auto" takes what the trainer set up:
+        bf16 activations or an active bf16 CUDA autocast region (Trainer(precision="bf16-mixed"),
+        utils/run_trainer.py:47) -> the bf16 tensor-pipe path; fp32 activations with
+        torch.get_float32_matmul_precision() != "highest" (cremad/run_trainer.py:22 sets "medium") -> TF32;
+        otherwise exact fp32.  Narrow heads (C < 32) are HBM-bound on the FMA pipe and always run exact fp32."""
+        if self.num_classes < 32:
+            if self.precision in ("bf16", "tf32"):
+                raise _lib.LfError(f"precision {self.precision!r} is a tensor-pipe mode for wide heads (C >= 32); "
+                                   f"C = {self.num_classes} runs the exact fp32 FMA path (use 'auto' or 'fp32')")
+            return "fp32"
+        if self.precision != "auto":
+            return self.precision
+        autocast_bf16 = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+        if (f1.dtype == torch.bfloat16 or autocast_bf16) and f1.shape[1] % 8 == 0:
+            return "bf16"
+        if f1.dtype == torch.float32 and torch.get_float32_matmul_precision() != "highest":
+            return "tf32"
+        return "fp32"
+
+    def _shared_state(self):
+        if self._ema is None:
+            from .utils.EMA import EMA
+            self._ema = EMA(torch.zeros(2, self.num_classes), smoothing=self.ema_smoothing)
+        if self.mode == "qmf" and self._qmf_state is None:
+            from .existing_algos.QMF import _QmfState
+            if self.n_data is None:
+                raise ValueError("QMF head needs n_data (args.num_samples)")
+            self._qmf_state = _QmfState(2, int(self.n_data))
+
+    def _get_engine(self, device, precision: str) -> LateFusionStep:
+        key = (str(device), precision)
+        eng = self._engines.get(key)
+        if eng is None:
+            self._shared_state()
+            eng = LateFusionStep(self.num_classes, mode=self.mode, n_data=self.n_data, device=device,
+                                 precision=precision, ema_smoothing=self.ema_smoothing, qmf_state=self._qmf_state,
+                                 ema=self._ema, loss_terms=self.loss_terms, process_group=self.process_group,
+                                 sharded=self.sharded)
+            eng.fresh_outputs = True
+            self._engines[key] = eng
+        self._engine = eng
+        return eng
 
     @property
     def engine(self) -> LateFusionStep:
@@ -121,7 +172,7 @@ class FusedLateFusionHead(nn.Module):
             raise ValueError("QMF head needs the dataset indices of the batch (idx)")
         # the reference's eval steps still compute the loss (and, QMF, mutate the History) but never touch
         # the EMA and need no gradients (utils/BaseModel.py:133-160, 1009-1040)
-        self._get_engine(f1.device)
+        self._get_engine(f1.device, self.resolve_precision(f1))
         self._grad_enabled = torch.is_grad_enabled()
         self.update_ema = self.training and self._grad_enabled
         return _FusedStep.apply(self, f1, f2, lin1.weight, lin1.bias, lin2.weight, lin2.bias, label,

@@ -108,7 +108,9 @@ class PeerComm:
                 self.bases.append(p.value)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.epoch = torch.zeros(2, dtype=torch.int64, device=dev)
-        self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+        # pinned, device-visible host flag: the kernels store 1 into it before they trap on a lost peer, so the host
+        # can read the cause without a CUDA call (the context is unusable after a trap)
+        self.error = torch.zeros(1, dtype=torch.int32).pin_memory()
         dist.barrier(group=pg)                      # every rank has mapped every buffer before the first push
 
     def fill(self, comm) -> None:
@@ -122,6 +124,29 @@ class PeerComm:
         comm.error = self.error.data_ptr()
 
     def check(self) -> None:
-        if int(self.error.item()) != 0:
+        """Host-memory read (no synchronisation): raises once a kernel has given up on a peer."""
+        if int(self.error[0]) != 0:
             from . import _lib
-            raise _lib.LfError("peer exchange timed out waiting for another rank")
+            raise _lib.LfError("peer exchange gave up waiting for another rank (a peer died or stalled for minutes); "
+                               "the CUDA context of this rank has been aborted")
+
+    def close(self) -> None:
+        """Unmap the peers' buffers and free the local one.  Safe to call twice; not a collective (a peer that
+        still has this rank's buffer mapped keeps the allocation alive until it closes its own mapping)."""
+        if getattr(self, "bases", None) is None:
+            return
+        from . import _lib
+        lib = _lib.load()
+        torch.cuda.synchronize()
+        for r, b in enumerate(self.bases):
+            if r != self.rank and b:
+                lib.lf_comm_ipc_close(b)
+        if self.local:
+            lib.lf_comm_free(self.local)
+        self.bases, self.local = None, None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

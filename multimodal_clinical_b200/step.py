@@ -85,7 +85,8 @@ class LateFusionStep:
 
     def __init__(self, num_classes: int, mode: str = "jlogits", n_data: Optional[int] = None,
                  device: Optional[torch.device] = None, precision: str = "fp32", ema_smoothing: float = 0.05,
-                 process_group=None, qmf_state=None, ema=None, comm: str = "auto", loss_terms: int = 0):
+                 process_group=None, qmf_state=None, ema=None, comm: str = "auto", loss_terms: int = 0,
+                 sharded: Optional[bool] = None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.LfError("LateFusionStep needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -97,7 +98,10 @@ class LateFusionStep:
         self.pg = process_group
         # QMF loss-term ablations (LF_LOSS_NO_JOINT = 1, LF_LOSS_NO_UNI = 2; include/lf_fusion.h)
         self.loss_terms = int(loss_terms)
-        self.rank, self.world = parallel.world(process_group)
+        # sharded=None: join the (default or given) process group when torch.distributed is initialised -- the
+        # explicit engine API used by bench.py; False: treat the batch as the whole batch whatever torch.distributed
+        # says (what FusedLateFusionHead passes under a DDP wrapper, where DDP reduces the gradients itself)
+        self.rank, self.world = parallel.world(process_group) if (sharded is None or sharded) else (0, 1)
         self.smoothing = float(ema_smoothing)
         dev = self.device
         self.ema_x = torch.zeros(2, self.C, device=dev)          # EMA.x      (utils/EMA.py:25)
@@ -126,6 +130,7 @@ class LateFusionStep:
         self.comm_mode = comm
         self.peer = None
         self._peer_key = None
+        self._peers = {}                 # (payload bytes, gradient floats) -> PeerComm or None, built once per size
         self.fresh_outputs = False
         self._pay = None
         self._pay_key = None
@@ -197,19 +202,39 @@ class LateFusionStep:
         if self.world == 1 or self.comm_mode == "nccl" or self.device.type != "cuda":
             return None
         key = (payload_bytes, grad_floats)
-        if self._peer_key != key:
+        if key not in self._peers:
+            # one communicator per exchange size, kept for the life of the engine: the short last batch of an epoch
+            # and the full batches that follow alternate between two cached communicators instead of re-mapping
             try:
-                self.peer = parallel.PeerComm(payload_bytes, grad_floats, self.pg)
+                peer = parallel.PeerComm(payload_bytes, grad_floats, self.pg)
             except _lib.LfError:
                 if self.comm_mode == "peer":
                     raise
-                self.peer = None                        # e.g. IPC not permitted: stay on the NCCL collectives
-            ok = torch.tensor([1 if self.peer is not None else 0], device=self.device)
+                peer = None                             # e.g. IPC not permitted: stay on the NCCL collectives
+            ok = torch.tensor([1 if peer is not None else 0], device=self.device)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg)
             if int(ok.item()) == 0:
-                self.peer = None
-            self._peer_key = key
+                if peer is not None:
+                    peer.close()
+                peer = None
+            self._peers[key] = peer
+        self.peer = self._peers[key]
+        self._peer_key = key
         return self.peer
+
+    def close(self) -> None:
+        """Unmap and free the peer-memory communicators (collective-free; call on every rank)."""
+        for peer in self._peers.values():
+            if peer is not None:
+                peer.close()
+        self._peers = {}
+        self.peer = None
+
+    def check_peer(self) -> None:
+        """Raise LfError if a peer exchange of an earlier step gave up waiting for another rank (one host sync)."""
+        for peer in self._peers.values():
+            if peer is not None:
+                peer.check()
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
@@ -298,6 +323,8 @@ class LateFusionStep:
 
         check(lib.lf_heads_forward(C.byref(a), st), "lf_heads_forward")
         peer = self._peer_comm(pay.numel(), gf.numel())
+        if peer is not None:
+            peer.check()                                          # pinned host flag: no synchronisation
         stride = pay.numel()
         mid = LfMidArgs()
         if peer is not None:

@@ -106,7 +106,7 @@ class JointLogitsBaseModel(pl.LightningModule, ABC):
         self.log(f"{kind}_step/{kind}_acc", acc["joint"], **kw)
         self.log(f"{kind}_step/{kind}_loss", loss, **kw)
         if with_df:
-            self.log(f"{kind}_step/{kind}_df_acc", acc["df"], **kw)
+            self.log(f"{kind}_step/logits_df_acc", acc["df"], **kw)          # the reference's key (utils/BaseModel.py:1034, 1110)
             metrics[f"{kind}_df_acc"].append(acc["df"])
         metrics[f"{kind}_logits"].append(torch.stack((x1_logits, x2_logits), dim=1))
         metrics[f"{kind}_labels"].append(label)

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from oracle import late_fusion as O
-from tests.util import TOL_FP32, assert_close, cu, load_golden
+from tests.util import TOL_FP32, TOL_TENSOR, assert_close, cu, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -322,3 +322,85 @@ def test_fused_head_sgd_matches_torch_sgd():
         for p, q in zip(ref, mine):
             assert_close(q, p, 1e-6, f"param after step {step}")
     assert_close(o2.state[mine[0]]["momentum_buffer"], o1.state[ref[0]]["momentum_buffer"], 1e-6, "momentum buffer")
+
+
+def _food_args(tmp=None, **kw):
+    import argparse
+    a = dict(num_classes=101, num_samples=4096, learning_rate=0.02, use_scheduler=True, encoder="precomputed",
+             grad_mod_type="OGM_GE", alpha=0.1, model_type="qmf")
+    a.update(kw)
+    return argparse.Namespace(**a)
+
+
+def test_default_bf16_mixed_trainer_takes_the_tensor_pipe_path(tmp_path, monkeypatch):
+    """`main.py --dir food101` under the reference's DEFAULT trainer precision (bf16-mixed, utils/run_trainer.py:47) and
+    the default head precision ("auto"): the tcgen05 kernels must be the ones that run -- not the exact-fp32 FMA GEMMs."""
+    import yaml
+    from multimodal_clinical_b200 import _lib, main
+    (tmp_path / "utils").mkdir(); (tmp_path / "food101").mkdir()
+    base = dict(num_classes=2, batch_size=64, learning_rate=1e-3, num_epochs=1, dropout_p=0.1, gpus=[0], num_cpus=0,
+                data_path=str(tmp_path / "data"), use_wandb=False, model_type="jlogits", group_name="t", seed=5,
+                use_scheduler=True, grad_mod_type="OGM_GE", alpha=0.1)
+    over = dict(num_classes=101, batch_size=256, learning_rate=0.02, model_type="qmf", encoder="precomputed", synthetic_samples=1024)
+    (tmp_path / "utils" / "base_cfg.yaml").write_text(yaml.safe_dump(base))
+    (tmp_path / "food101" / "food101.yaml").write_text(yaml.safe_dump(over))
+    monkeypatch.chdir(tmp_path)
+    lib = _lib.load()
+    _lib.profile_report()
+    lib.lf_profile_enable(1)
+    try:
+        tr = main.main(["--dir", "food101"])
+    finally:
+        prof = _lib.profile_report()
+        lib.lf_profile_enable(0)
+    assert tr.precision == "bf16-mixed"
+    names = set(prof)
+    assert any(n.startswith("tc_forward") for n in names), names
+    assert any(n.startswith("tc_dweight") for n in names) and any(n.startswith("tc_d") or n.startswith("tc_backward") for n in names), names
+    assert not any(n.startswith("sgemm") for n in names), names
+    got = {k: float(v) for k, v in tr.callback_metrics.items()}
+    assert np.isfinite(got["train_epoch/train_avg_loss"]) and "val_step/logits_df_acc" in got
+
+
+def test_food101_module_under_autocast_matches_oracle_on_bf16_rounded_inputs():
+    """QMFBaseModel.training_step of the Food101 module inside a bf16 autocast region (what Trainer(precision=
+    "bf16-mixed") does): loss, head gradients and feature gradients against the fp64 oracle on the bf16-rounded
+    features / heads, 2e-2 (BASELINE.json's bf16 tolerance).  The MLP's hidden layers are bypassed so that the
+    head sees the given 512-d features (food101/joint_model_qmf.py:22: the fused step owns mlp.6)."""
+    import multimodal_clinical_b200.food101.joint_model_qmf as fq
+    B, D, C, N = 512, 512, 101, 4096
+    torch.manual_seed(0)
+    m = fq.MultimodalFoodModel(_food_args(num_samples=N)).cuda()
+    m.train()
+    m.model.x1_model.hidden = lambda x: x
+    m.model.x2_model.hidden = lambda x: x
+    inp = O.make_inputs(B, D, C, seed=77, n_data=N)
+    W = [m.model.x1_model.classifier.weight.detach().cpu(), m.model.x2_model.classifier.weight.detach().cpu()]
+    b = [m.model.x1_model.classifier.bias.detach().cpu(), m.model.x2_model.classifier.bias.detach().cpu()]
+    r16 = lambda x: x.bfloat16().float()
+    hist = O.HistoryState(N)
+    ema = torch.zeros(2, C, dtype=torch.float64)
+    for s in range(2):
+        f1 = inp["f1"].cuda().requires_grad_(True); f2 = inp["f2"].cuda().requires_grad_(True)
+        ref = O.qmf_step([r16(inp["f1"]), r16(inp["f2"])], [r16(W[0]), r16(W[1])], b, inp["y"], inp["idx"], hist, ema_x=ema,
+                         dtype=torch.float64)
+        ema = ref["ema_x"]
+        m.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = m.training_step((f1, f2, inp["y"].cuda(), inp["idx"].cuda()), s)
+        loss.backward()
+        assert m.model.fused.engine.bf16
+        assert_close(loss, ref["loss"], TOL_TENSOR, "loss")
+        assert_close(m.model.x1_model.classifier.weight.grad, ref["dW"][0], TOL_TENSOR, "dW1")
+        assert_close(m.model.x2_model.classifier.bias.grad, ref["db"][1], TOL_TENSOR, "db2")
+        assert f1.grad.dtype == torch.float32
+        assert_close(f1.grad, ref["dfeat"][0], TOL_TENSOR, "df1")
+        assert_close(m.ema_offset.x, ref["ema_x"], TOL_TENSOR, "EMA.x")
+    # outside autocast with fp32 features and 'highest' matmul precision the same module runs the exact path
+    torch.set_float32_matmul_precision("highest")
+    assert m.model.fused.resolve_precision(inp["f1"].cuda()) == "fp32"
+    torch.set_float32_matmul_precision("medium")
+    try:
+        assert m.model.fused.resolve_precision(inp["f1"].cuda()) == "tf32"
+    finally:
+        torch.set_float32_matmul_precision("highest")
