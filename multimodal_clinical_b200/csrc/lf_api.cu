@@ -27,6 +27,9 @@ bool tc_fwd_supported(int mode, int B, int D, int C, int ld_z, int ld_f, int ele
 int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2], const float* const bias[2], int elem, int B, int D,
                          int C, float* const z[2], int ld_z, float* avg, float* zdf, int ld_f, float* conf, float* rowstat,
                          const int64_t* label, float* partials, int nb_total, int* grid_out, cudaStream_t s);
+// lf_tc_bwd.cu: dL/dz formed inside the dfeat GEMM (QMF, bf16, 32 <= C <= 128)
+bool tc_bwd_supported(int mode, int precision, int B, int D, int C, int ld_z, int ldz, int need_dfeat);
+int tc_backward_qmf(const RowsArgs& a, const void* const w16[2], void* const dfeat[2], int D, int* grid_out, cudaStream_t s);
 }
 
 namespace lf {
@@ -343,15 +346,26 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     if (rc) return rc;
     return finalize_db_cal(w.db_partials, grid, a->classes, w.cal_partials, nb_cal, a->dbias[0], a->dbias[1], a->stats, s);
   }
-  if (phase != 2) {
+  const int ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
+  const bool tc = use_tensor_pipe(a);
+  // QMF / bf16 / C <= 128: dz is formed inside the dfeat GEMM (lf_tc_bwd.cu); dz, db partials and the calibrated counts
+  // come out of the same kernel, so phase 1 of a sharded run already produces dfeat and phase 2 has nothing left to do
+  const bool fused_bwd = tc && tc_bwd_supported(a->mode, a->precision, a->batch, a->dim, a->classes,
+                                                a->ld_logits > 0 ? a->ld_logits : a->classes, ldz, a->need_dfeat);
+  int nb_parts = row_blocks(a->batch);           // per-CTA partial rows (db, calibrated counts) of the kernel that made dz
+  if (fused_bwd) {
+    if (phase == 2) return LF_OK;
+    const void* w16[2] = {w.w16, (const char*)w.w16 + (size_t)a->classes * a->dim * 2};
+    void* df[2] = {a->dfeat[0], a->dfeat[1]};
+    rc = tc_backward_qmf(rows_args(a, w), w16, df, a->dim, &nb_parts, s);
+    if (rc) return rc;
+  } else if (phase != 2) {
     rc = rows_backward(rows_args(a, w), a->mode, s);
     if (rc) return rc;
   }
   const float* dz[2] = {a->dlogits[0], a->mode == LF_MODE_QMF ? a->dlogits[1] : a->dlogits[0]};
-  const int ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
-  const bool tc = use_tensor_pipe(a);
   GemmArgs g;
-  if (a->need_dfeat && phase != 1) {
+  if (a->need_dfeat && phase != 1 && !fused_bwd) {
     memset(&g, 0, sizeof(g));
     for (int m = 0; m < 2; ++m) { g.A[m] = dz[m]; g.B[m] = a->weight[m]; g.bias[m] = nullptr; g.C[m] = a->dfeat[m]; }
     g.M = a->batch; g.N = a->dim; g.K = a->classes;
@@ -409,13 +423,13 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   }
   if (rc) return rc;
   // db_m (column sums of dZ_m, accumulated by the kernel that produced dZ) and the calibrated counts
-  const int nb_db = row_blocks(a->batch);
+  const int nb_db = nb_parts;
   if (finalize_grads_supported(w.dw_partials, a->dweight[0], a->dweight[1], splits, cd) && (kMaxSplits * cd) % 4 == 0)
     return finalize_grads(w.dw_partials, a->dweight[0], a->dweight[1], splits, kMaxSplits, cd, w.db_partials, nb_db, a->classes,
-                          w.cal_partials, row_blocks(a->batch), a->dbias[0], a->dbias[1], a->stats, s);
+                          w.cal_partials, nb_parts, a->dbias[0], a->dbias[1], a->stats, s);
   rc = reduce_splits2(w.dw_partials, a->dweight[0], a->dweight[1], splits, kMaxSplits, cd, s);
   if (rc) return rc;
-  return finalize_db_cal(w.db_partials, nb_db, a->classes, w.cal_partials, row_blocks(a->batch), a->dbias[0], a->dbias[1],
+  return finalize_db_cal(w.db_partials, nb_db, a->classes, w.cal_partials, nb_parts, a->dbias[0], a->dbias[1],
                          a->stats, s);
 }
 

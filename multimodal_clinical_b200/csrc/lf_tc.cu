@@ -36,18 +36,6 @@ namespace lf {
 constexpr int TC_THREADS = 320;                          // producer warp, MMA warp, 2 x 4 epilogue warps
 // staging: two [128 rows x 128 B] store boxes per epilogue half (TcGemmParams::epi_halves = 1 or 2)
 
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 struct Item { int batch, split, m0, n0, k_begin, num_kb, k_end; };
 
 __device__ __forceinline__ Item decode_item(const TcGemmParams& p, int item) {
@@ -339,7 +327,7 @@ int make_map(CUtensorMap* map, const void* base, long long inner, long long oute
 }
 
 // 3-D output map for the TMA-store epilogue: (cols, rows, splits), box [32 x 128 x 1], SWIZZLE_128B.
-static int make_store_map(CUtensorMap* map, void* base, long long cols, long long rows, long long ld,
+int make_store_map(CUtensorMap* map, void* base, long long cols, long long rows, long long ld,
                           long long splits, long long split_stride, int elem, int tile_m) {
   const MapKey mk{base, cols, rows, splits, ld, split_stride, 128 / elem, tile_m, 1, elem, 0, 3};
   if (const CUtensorMap* hit = g_maps.find(mk)) { *map = *hit; return LF_OK; }

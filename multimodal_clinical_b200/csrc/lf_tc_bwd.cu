@@ -1,0 +1,499 @@
+// Fused QMF backward for wide heads in the bf16 mode (32 <= C <= 128): dL/dz is produced INSIDE the tensor-pipe
+// kernel that consumes it, so `rows_backward` (an issue-bound pass whose only job was to materialise dz) and the
+// dz read of `tc_dfeat` disappear:
+//
+//   work item  = one M tile of <= 128 samples
+//   warps 12.. row math (16 warps, G = 8 lanes per sample): read z1 / z2 rows (128-bit loads), the per-sample
+//              scalars of the forward pass (conf, log-sum-exps) and dL_reg/dconf of the mid step, form
+//                dz_m = (w_uni (p_m - onehot) + w_joint c_m (softmax(z_df) - onehot)) / B + (g_m / 10) p_m    
+//              and write it as bf16 straight into shared memory in the K-major SWIZZLE_128B layout of the
+//              tcgen05 A operand ([128 samples x 64 classes] boxes); the calibrated-accuracy counts (z_m + EMA offset,
+//              utils/BaseModel.py:84-89) ride along.  The same boxes are TMA-stored to
+//              HBM (bf16, pitch ldz) for the dW GEMM that follows.
+//   warp 0     TMA producer of the head weights: W_m[:, n-tile] as the MN-major B operand, [64 x 64] boxes
+//   warp 1     TMEM allocator + single-thread MMA issuer: dF_m[tile, n-tile of 128] = dz_m W_m, K = classes
+//              (<= 7 k-steps), THREE 128-column accumulators in TMEM so the issuer runs up to two items ahead; and
+//              db_m += dz_m^T 1 as one more (N = 16) MMA per 16 samples: the dz tile read MN-major is dz^T, the B
+//              operand is a constant tile of ones, the accumulator (lane = class) lives for the whole kernel
+//   warps 4-11 epilogue, two halves of four warps (one per TMEM lane quarter): TMEM -> bf16 -> swizzled staging box
+//              -> TMA store of dF (same scheme as lf_tc.cu)
+//
+// Outputs (dz, dF, db partials, calibrated counts) are those of rows_backward + tc_dfeat; the arithmetic of the
+// row math is that of rows_backward_vec_kernel (lf_rows_vec.cu), reference lines in lf_rows.cu.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include "lf_common.cuh"
+#include "lf_rowvec.cuh"
+#include "lf_rows.cuh"
+#include "lf_tc.cuh"
+#include "lf_tc_ptx.cuh"
+
+namespace lf {
+
+using namespace rowvec;
+
+constexpr int BW_RW = 16;                         // row-math warps: the row math is a latency-bound chain per warp, so it
+                                                  // scales with the number of warps (8 warps: 11 us per tile, measured)
+constexpr int BW_EPI0 = 4;                        // first epilogue warp (warps 2, 3 idle: role groups start at warp % 4 == 0)
+constexpr int BW_RM0 = BW_EPI0 + 8;               // first row-math warp
+constexpr int BW_THREADS = 32 * (BW_RM0 + BW_RW); // 896
+constexpr int BW_UNITS = TC_BLOCK_M / (4 * BW_RW);// passes of 4 samples per warp over a 128-row tile
+constexpr int BW_BLOCK_N = 128;                   // dF columns per item
+constexpr int BW_BUFS = 3;                        // dF accumulators in TMEM (3 x 128 columns)
+constexpr int BW_DB_COL = BW_BUFS * BW_BLOCK_N;   // db accumulators: 16 columns per modality at TMEM columns 384 / 400
+constexpr int BW_BOX = 16384;                     // one [128 rows x 128 B] box
+
+struct TcBwdParams {
+  int B, B_global, C, D;
+  int ld_z;                 // pitch of z1 / z2 (fp32 elements, multiple of 4)
+  int tile_m, m_tiles, n_tiles;
+  int ksteps_last;          // k-steps (16 classes) of the last 64-class k-block
+  int stages;
+  const float* z[2];
+  const float* conf;        // (2,B)
+  const float* rowstat;     // (B,4) lse1, lse2, lse(z_df)
+  const float* qmf_g;       // (2,B)
+  const float* ema_off;     // (2,C)
+  const int64_t* label;
+  float* dbpart;            // [grid][2][C]
+  float* calpart;           // [grid][2]
+  float w_joint, w_uni;
+  unsigned long long* trace;   // LF_BWD_TRACE=1: [grid][16] %globaltimer stamps of the roles
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ unsigned long long bw_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int NKB>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+tc_bwd_qmf_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
+                  const __grid_constant__ CUtensorMap mapO0, const __grid_constant__ CUtensorMap mapO1,
+                  const __grid_constant__ CUtensorMap mapZ0, const __grid_constant__ CUtensorMap mapZ1, TcBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int stages = p.stages;
+  uint8_t* dzs = smem;                                           // [2 buffers][2 modalities][NKB][16 KB]  A operand
+  uint8_t* wring = dzs + 4 * NKB * BW_BOX;                       // [stages][16 KB]             B operand ring
+  uint8_t* staging = wring + (size_t)stages * BW_BOX;            // [2 halves][16 KB]           dF store boxes
+  float* soff = reinterpret_cast<float*>(staging + 2 * BW_BOX);  // [2][128] EMA offsets, -inf beyond C
+  uint8_t* ones = reinterpret_cast<uint8_t*>(soff + 256);        // [16 rows x 128 B] of bf16 1.0: B operand of the db MMA
+  float* scal = reinterpret_cast<float*>(ones + 2048);           // [BW_RW][2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(scal + BW_RW * 2);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;                  // [BW_BUFS]
+  uint64_t* tmem_empty_bar = tmem_full_bar + BW_BUFS;            // [BW_BUFS]
+  uint64_t* dz_full_bar = tmem_empty_bar + BW_BUFS;              // [2]: dz is double-buffered, so the row math of tile
+  uint64_t* dz_free_bar = dz_full_bar + 2;                       // [2]  i + 1 overlaps the MMAs / epilogue of tile i
+  uint64_t* db_full_bar = dz_free_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(db_full_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int C = p.C, B = p.B;
+  unsigned long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = bw_timer();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapW0); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapO0); tma_prefetch_desc(&mapO1);
+    tma_prefetch_desc(&mapZ0); tma_prefetch_desc(&mapZ1);
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < BW_BUFS; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&dz_full_bar[b], 1); mbar_init(&dz_free_bar[b], 1); }
+    mbar_init(db_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < 512; i += BW_THREADS) reinterpret_cast<uint32_t*>(ones)[i] = 0x3f803f80u;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  if (tr && threadIdx.x == 0) tr[1] = bw_timer();
+
+  if (warp == 0) {
+    // ===================== TMA producer: head weights (do not depend on the preceding kernels) =====================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x)
+        for (int m = 0; m < 2; ++m) {
+          const CUtensorMap* mapW = m == 0 ? &mapW0 : &mapW1;
+          for (int n = 0; n < p.n_tiles; ++n)
+            for (int kb = 0; kb < NKB; ++kb) {
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              uint8_t* sb = wring + (size_t)s * BW_BOX;
+              mbar_expect_tx(&full_bar[s], BW_BOX);
+              tma_load_2d(mapW, &full_bar[s], sb, n * BW_BLOCK_N, kb * 64);              // [64 columns of D x 64 classes]
+              tma_load_2d(mapW, &full_bar[s], sb + 8192, n * BW_BLOCK_N + 64, kb * 64);
+              if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
+            }
+        }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(TC_BLOCK_M, BW_BLOCK_N, 0, 1);
+      const uint64_t descA0 = make_smem_desc(0, 16, 1024, 2);          // K-major SWIZZLE_128B
+      const uint64_t descB0 = make_smem_desc(0, 8192, 1024, 2);        // MN-major: 64-column chunks 8192 B apart
+      const uint32_t dz0 = smem_u32(dzs), w0 = smem_u32(wring);
+      const uint32_t idesc_db = make_idesc_bf16(TC_BLOCK_M, 16, 1, 0);
+      const uint64_t descAT0 = make_smem_desc(0, BW_BOX, 1024, 2);     // dz^T: MN-major, 64-class chunks one box apart
+      const uint64_t descOnes = make_smem_desc(smem_u32(ones), 16, 1024, 2);
+      uint32_t li = 0, s = 0, ph = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t dzb = dz0 + (tl & 1) * (2 * NKB * BW_BOX);
+        mbar_wait(&dz_full_bar[tl & 1], (tl >> 1) & 1);               // the row-math warps have written this tile's dz
+        tc_fence_after();
+        if (tr && tl < 2) tr[6 + tl] = bw_timer();
+        for (int m = 0; m < 2; ++m)
+          for (int n = 0; n < p.n_tiles; ++n, ++li) {
+            const uint32_t buf = li % BW_BUFS;
+            mbar_wait(&tmem_empty_bar[buf], ((li / BW_BUFS) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + buf * BW_BLOCK_N;
+            for (int kb = 0; kb < NKB; ++kb) {
+              mbar_wait(&full_bar[s], ph);
+              tc_fence_after();
+              uint64_t da = descA0 + (uint64_t)((dzb + (uint32_t)(m * NKB + kb) * BW_BOX) >> 4);
+              uint64_t db = descB0 + (uint64_t)((w0 + s * BW_BOX) >> 4);
+              const int ksteps = kb == NKB - 1 ? p.ksteps_last : 4;
+              for (int k = 0; k < ksteps; ++k, da += 2, db += 128)     // 32 B of K (A), 16 k-rows x 128 B (B)
+                umma_f16(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_commit(&empty_bar[s]);
+              if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
+            }
+            umma_commit(&tmem_full_bar[buf]);
+          }
+        // db_m[c] += sum over the tile's samples of dz_m[., c]: the same boxes read MN-major (M = classes: 64-class
+        // chunks one box apart; K = samples: 16 rows x 128 B per instruction) times a tile of ones
+        for (int m = 0; m < 2; ++m) {
+          uint64_t da = descAT0 + (uint64_t)((dzb + (uint32_t)(m * NKB) * BW_BOX) >> 4);
+          for (int k = 0; k < TC_BLOCK_M / 16; ++k, da += 128)
+            umma_f16(tmem_base + BW_DB_COL + 16 * m, da, descOnes, idesc_db, (tl > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&dz_free_bar[tl & 1]);                            // every MMA that reads this tile's dz has completed
+        if (tr && tl < 2) tr[8 + tl] = bw_timer();
+      }
+      umma_commit(db_full_bar);
+    }
+  } else if (warp < BW_EPI0) {
+    // idle warps (keep the role groups aligned to TMEM lane quarters)
+  } else if (warp < BW_RM0) {
+    // ===================== epilogue: dF tiles out =====================
+    const int q = warp & 3;
+    const int half = (warp - BW_EPI0) >> 2;
+    const int et = (threadIdx.x - 32 * BW_EPI0) & 127;
+    const int row_in_tile = q * 32 + lane;
+    uint32_t li = 0, etl = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++etl) {
+      const int m0 = tile * p.tile_m;
+      if (tr && et == 0 && half == 0 && etl > 0 && etl < 3) tr[10 + etl - 1] = bw_timer();
+      for (int m = 0; m < 2; ++m) {
+        const CUtensorMap* mapO = m == 0 ? &mapO0 : &mapO1;
+        for (int n = 0; n < p.n_tiles; ++n, ++li) {
+          const uint32_t buf = li % BW_BUFS;
+          mbar_wait_warp(&tmem_full_bar[buf], (li / BW_BUFS) & 1);
+          tc_fence_after();
+          const uint32_t acc = tmem_base + buf * BW_BLOCK_N + half * 64 + ((uint32_t)(q * 32) << 16);
+          uint32_t pk[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {                 // this warp's 64 columns, 32 at a time (72 registers per thread)
+            uint32_t v[32];
+            tmem_ld32(acc + 32 * h, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+              pk[16 * h + i] = *reinterpret_cast<const uint32_t*>(&b2);
+            }
+          }
+          // this warp's share of the accumulator is in registers: hand the TMEM buffer back right away
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          uint8_t* box = staging + half * BW_BOX;      // one box per half: its previous store had the TMEM load and
+          if (et == 0) tma_store_wait_read<0>();       // the conversion above to finish reading it
+          named_bar_sync(1 + half, 128);
+          uint8_t* rowp = box + row_in_tile * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row_in_tile & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_proxy_async();
+          named_bar_sync(1 + half, 128);
+          if (et == 0) {
+            tma_store_3d(mapO, box, n * BW_BLOCK_N + half * 64, m0, 0);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (tr && et == 0 && half == 0) tr[12] = bw_timer();
+    if (half == 0) {
+      // db_m: accumulator lane = class, every one of the 16 columns holds the sum
+      mbar_wait_warp(db_full_bar, 0);
+      tc_fence_after();
+      const int c = q * 32 + lane;
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const float v = tmem_ld1(tmem_base + BW_DB_COL + 16 * m + ((uint32_t)(q * 32) << 16));
+        if (c < C) p.dbpart[(size_t)blockIdx.x * 2 * C + m * C + c] = v;
+      }
+    }
+    if (et == 0) tma_store_wait_all();
+  } else {
+    // ===================== row math: dz tiles in =====================
+    constexpr int G = 8, NK = 4;
+    const int rw = warp - BW_RM0, rt = threadIdx.x - 32 * BW_RM0;
+    const int l = lane % G, gi = lane / G;
+    const int ld = p.ld_z, nq = ld / 4;
+    const float invB = 1.f / (float)p.B_global;
+    // One unit of work = (tile, it): 32 samples of the tile, 4 per warp; the rows of the next unit are pulled into L2
+    // while the current one is computed.
+    const int n_my_tiles = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_units = n_my_tiles * BW_UNITS;
+    auto unit_row = [&](int u, int& r, int& m0) {
+      const int tile = (int)blockIdx.x + (u / BW_UNITS) * (int)gridDim.x;
+      m0 = tile * p.tile_m;
+      r = (u % BW_UNITS) * (4 * BW_RW) + rw * 4 + gi;
+    };
+    auto unit_sample = [&](int u, bool& valid) -> int {
+      int r, m0;
+      unit_row(u, r, m0);
+      const int bs = m0 + r;
+      valid = r < p.tile_m && bs < B;
+      return valid ? bs : B - 1;
+    };
+    pdl_wait();                                        // qmf_g / ema offsets come from the mid step
+    for (int c = rt; c < 256; c += 32 * BW_RW) {
+      const int m = c >> 7, cc = c & 127;
+      soff[c] = cc < C ? p.ema_off[m * C + cc] : -INFINITY;
+    }
+    float cal1 = 0.f, cal2 = 0.f;
+    if (tr && rt == 0) tr[2] = bw_timer();
+#pragma unroll 1
+    for (int u = 0; u < n_units; ++u) {
+      const int it = u % BW_UNITS, tl = u / BW_UNITS;
+      int r, m0;
+      unit_row(u, r, m0);
+      bool valid;
+      const int b = unit_sample(u, valid);
+      // ---- loads: both rows (chunks past the pitch stay 0) and the per-sample scalars, all independent
+      const float4* z1p = reinterpret_cast<const float4*>(p.z[0] + (size_t)b * ld);
+      const float4* z2p = reinterpret_cast<const float4*>(p.z[1] + (size_t)b * ld);
+      float4 v1[NK], v2[NK];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int qc = l + G * k;
+        v1[k] = make_float4(0.f, 0.f, 0.f, 0.f); v2[k] = v1[k];
+        if (qc < nq) { v1[k] = __ldg(z1p + qc); v2[k] = __ldg(z2p + qc); }
+      }
+      const int y = (int)p.label[b];
+      const float c1 = p.conf[b], c2 = p.conf[B + b];
+      const float4 rs = *reinterpret_cast<const float4*>(p.rowstat + (size_t)b * 4);
+      const float g1 = p.qmf_g[b] * 0.1f, g2 = p.qmf_g[B + b] * 0.1f;     // d conf / d energy (conf = energy / 10, QMF.py:114)
+      if (u + 1 < n_units && l < 4) {                  // next unit's rows into L2: 4 lanes x 128 B cover a 416-byte row
+        bool v;
+        const int bp = unit_sample(u + 1, v);
+        if (l * 128 < ld * 4) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.z[0] + (size_t)bp * ld) + l * 128));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.z[1] + (size_t)bp * ld) + l * 128));
+        }
+      }
+      if (it == 0) {
+        if (rt == 0) {
+          if (tl > 1) mbar_wait(&dz_free_bar[tl & 1], ((tl >> 1) - 1) & 1);   // the MMAs of tile tl - 2 are done with this buffer
+          tma_store_wait_read<1>();                                           // ... and so are its dz stores
+        }
+        named_bar_sync(3, 32 * BW_RW);
+      }
+      // the chunk that straddles C: pitch padding may be uninitialised memory (k is compile-time, the test is warp-uniform)
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+        if (4 * (G * k + G) > C) {
+          const int c0 = 4 * (l + G * k);
+          if (c0 + 0 >= C) { v1[k].x = 0.f; v2[k].x = 0.f; }
+          if (c0 + 1 >= C) { v1[k].y = 0.f; v2[k].y = 0.f; }
+          if (c0 + 2 >= C) { v1[k].z = 0.f; v2[k].z = 0.f; }
+          if (c0 + 3 >= C) { v1[k].w = 0.f; v2[k].w = 0.f; }
+        }
+      // dz_m = (w_uni (p_m - onehot) + w_joint c_m (softmax(z_df) - onehot)) / B + g_m p_m, regrouped so that the class
+      // loop is packed fp32x2 FMAs around three ex2 per element:  dz_m = a_m p_m + b_m softmax(z_df) - k_m onehot.
+      // Columns past C hold finite values that nothing consumes (W rows >= C are zero-filled, dW rows >= C clipped).
+      const float vs = valid ? 1.f : 0.f;               // rows past the tile / batch: dz = 0
+      const float wu = p.w_uni * invB, wj = p.w_joint * invB;
+      const float a1 = (wu + g1) * vs, a2 = (wu + g2) * vs;
+      const float bj1 = wj * c1 * vs, bj2 = wj * c2 * vs;
+      const float k1 = (wu + wj * c1) * vs, k2 = (wu + wj * c2) * vs;
+      const float2 C1 = make_float2(c1, c1), C2 = make_float2(c2, c2), LL = make_float2(kLog2e, kLog2e);
+      const float2 L1 = make_float2(-rs.x * kLog2e, -rs.x * kLog2e), L2 = make_float2(-rs.y * kLog2e, -rs.y * kLog2e),
+                   LD = make_float2(-rs.z * kLog2e, -rs.z * kLog2e);
+      const float2 A1 = make_float2(a1, a1), A2 = make_float2(a2, a2), B1 = make_float2(bj1, bj1), B2 = make_float2(bj2, bj2);
+      const int yy = y - 4 * l;                          // this lane owns class y iff yy == 32 k + e
+      uint8_t* row1 = dzs + (tl & 1) * (2 * NKB * BW_BOX) + r * 128;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int qc = l + G * k;                      // float4 chunk index: classes 4 qc .. 4 qc + 3
+        float d1[4], d2[4];
+        const float a[4] = {v1[k].x, v1[k].y, v1[k].z, v1[k].w}, c[4] = {v2[k].x, v2[k].y, v2[k].z, v2[k].w};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 w1 = make_float2(a[2 * h], a[2 * h + 1]), w2 = make_float2(c[2 * h], c[2 * h + 1]);
+          const float2 t = __ffma2_rn(w2, C2, __fmul2_rn(w1, C1));
+          const float2 x1 = __ffma2_rn(w1, LL, L1), x2 = __ffma2_rn(w2, LL, L2), xd = __ffma2_rn(t, LL, LD);
+          const float2 p1 = make_float2(ex2f(x1.x), ex2f(x1.y)), p2 = make_float2(ex2f(x2.x), ex2f(x2.y));
+          const float2 pd = make_float2(ex2f(xd.x), ex2f(xd.y));
+          const float2 e1 = __ffma2_rn(p1, A1, __fmul2_rn(pd, B1)), e2 = __ffma2_rn(p2, A2, __fmul2_rn(pd, B2));
+          d1[2 * h] = e1.x; d1[2 * h + 1] = e1.y; d2[2 * h] = e2.x; d2[2 * h + 1] = e2.y;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (yy == 32 * k + e) { d1[e] -= k1; d2[e] -= k2; }
+        // K-major SWIZZLE_128B box of 64 classes: row r at r * 128 B, 16-byte piece j stored at j ^ (r & 7)
+        const int kb = qc >> 4, piece = (qc & 15) >> 1, hlf = qc & 1;
+        if (kb < NKB) {
+          const uint32_t o = (uint32_t)kb * BW_BOX + (uint32_t)(((piece ^ (r & 7)) << 4) + hlf * 8);
+          const __nv_bfloat162 a0 = __floats2bfloat162_rn(d1[0], d1[1]), a1b = __floats2bfloat162_rn(d1[2], d1[3]);
+          const __nv_bfloat162 b0 = __floats2bfloat162_rn(d2[0], d2[1]), b1b = __floats2bfloat162_rn(d2[2], d2[3]);
+          uint2 u1, u2;
+          u1.x = *reinterpret_cast<const uint32_t*>(&a0); u1.y = *reinterpret_cast<const uint32_t*>(&a1b);
+          u2.x = *reinterpret_cast<const uint32_t*>(&b0); u2.y = *reinterpret_cast<const uint32_t*>(&b1b);
+          *reinterpret_cast<uint2*>(row1 + o) = u1;
+          *reinterpret_cast<uint2*>(row1 + NKB * BW_BOX + o) = u2;
+        }
+      }
+      // calibrated accuracies: argmax(z_m + EMA offset of this step), first index on ties (torch.argmax)
+      {
+        float w1[16], w2[16];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          const float4 o1 = *reinterpret_cast<const float4*>(soff + 4 * (l + G * k));
+          const float4 o2 = *reinterpret_cast<const float4*>(soff + 128 + 4 * (l + G * k));
+          w1[4 * k] = v1[k].x + o1.x; w1[4 * k + 1] = v1[k].y + o1.y; w1[4 * k + 2] = v1[k].z + o1.z; w1[4 * k + 3] = v1[k].w + o1.w;
+          w2[4 * k] = v2[k].x + o2.x; w2[4 * k + 1] = v2[k].y + o2.y; w2[4 * k + 2] = v2[k].z + o2.z; w2[4 * k + 3] = v2[k].w + o2.w;
+        }
+        float mx; int i1, i2;
+        row_max_arg<G, NK>(w1, l, mx, i1);
+        row_max_arg<G, NK>(w2, l, mx, i2);
+        if (valid) { cal1 += (i1 == y); cal2 += (i2 == y); }
+      }
+      if (it == BW_UNITS - 1) {
+        fence_proxy_async();                             // generic-proxy writes -> visible to the MMA / TMA store
+        named_bar_sync(3, 32 * BW_RW);
+        if (rt == 0) {
+          mbar_arrive(&dz_full_bar[tl & 1]);
+          if (tr && tl < 2) tr[3 + tl] = bw_timer();
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb)
+              tma_store_2d(m == 0 ? &mapZ0 : &mapZ1, dzs + ((tl & 1) * 2 * NKB + m * NKB + kb) * BW_BOX, kb * 64, m0);   // dz for the dW GEMM
+          tma_store_commit();
+        }
+      }
+    }
+    // ---- calibrated counts of this CTA in fixed order (db comes out of the tensor pipe, see the epilogue warps)
+    cal1 = across_groups_sum<G>(cal1); cal2 = across_groups_sum<G>(cal2);     // every lane of a group holds the same count
+    if (lane == 0) { scal[rw * 2] = cal1; scal[rw * 2 + 1] = cal2; }
+    named_bar_sync(3, 32 * BW_RW);
+    if (rt < 2) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < BW_RW; ++w) s += scal[w * 2 + rt];
+      p.calpart[(size_t)blockIdx.x * 2 + rt] = s;
+    }
+    if (rt == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  if (tr && threadIdx.x == 0) tr[13] = bw_timer();
+}
+
+// ---------------------------------------------------------------------------------- host side
+bool tc_bwd_supported(int mode, int precision, int B, int D, int C, int ld_z, int ldz, int need_dfeat) {
+  if (getenv("LF_NO_FUSED_BWD")) return false;
+  if (mode != LF_MODE_QMF || precision != LF_PREC_BF16 || !need_dfeat) return false;
+  if (C < 32 || C > 128 || B < 1 || D % 8 || ld_z % 4 || ld_z < C || ld_z > 128 || ldz % 8 || ldz < C) return false;
+  return true;
+}
+
+// dF_m (bf16) = dz_m W_m with dz formed in the kernel; also writes dz (bf16, pitch ldz), the per-CTA db partials
+// [grid][2][C] and calibrated-count partials [grid][2].  w16: bf16 copies of the heads, (C,D) each.
+int tc_backward_qmf(const RowsArgs& a, const void* const w16[2], void* const dfeat[2], int D, int* grid_out, cudaStream_t s) {
+  TcBwdParams p;
+  p.B = a.B; p.B_global = a.B_global; p.C = a.C; p.D = D; p.ld_z = a.ld_z;
+  {
+    const int base = div_up(a.B, TC_BLOCK_M), waves = div_up(base, 148);
+    int tm = div_up(div_up(a.B, waves * 148), 8) * 8;
+    if (tm < 64) tm = 64;
+    if (tm > TC_BLOCK_M || base <= 148 / 2) tm = TC_BLOCK_M;
+    p.tile_m = tm;
+  }
+  p.m_tiles = div_up(a.B, p.tile_m);
+  p.n_tiles = div_up(D, BW_BLOCK_N);
+  const int nkb = div_up(a.C, 64);
+  p.ksteps_last = div_up(a.C - (nkb - 1) * 64, 16);
+  for (int m = 0; m < 2; ++m) p.z[m] = a.z[m];
+  p.conf = a.conf; p.rowstat = a.rowstat; p.qmf_g = a.qmf_g; p.ema_off = a.ema_off; p.label = a.label;
+  p.dbpart = a.dbpart; p.calpart = a.calpart; p.w_joint = a.w_joint; p.w_uni = a.w_uni;
+  static unsigned long long* trace_buf = nullptr;
+  static int trace_calls = 0;
+  p.trace = nullptr;
+  if (getenv("LF_BWD_TRACE")) {
+    if (!trace_buf) { cudaMalloc(&trace_buf, 148 * 16 * sizeof(unsigned long long)); cudaMemset(trace_buf, 0, 148 * 16 * sizeof(unsigned long long)); }
+    p.trace = trace_buf;
+  }
+  if (((uintptr_t)a.z[0] | (uintptr_t)a.z[1] | (uintptr_t)a.rowstat) & 15) { set_error("tc_backward_qmf: z / rowstat must be 16-byte aligned"); return LF_ERR_BAD_ARG; }
+  CUtensorMap mW[2], mO[2], mZ[2];
+  for (int m = 0; m < 2; ++m) {
+    int rc = make_map(&mW[m], w16[m], D, a.C, D, 64, 64, true, 2);                 // MN-major boxes [64 columns x 64 classes]
+    if (rc) return rc;
+    rc = make_store_map(&mO[m], dfeat[m], D, a.B, D, 1, 0, 2, p.tile_m);
+    if (rc) return rc;
+    rc = make_map(&mZ[m], a.dz[m], a.ldz, a.B, a.ldz, 64, p.tile_m, false, 2);     // dz rows out: box [64 classes x tile_m]
+    if (rc) return rc;
+  }
+  const size_t fixed = (size_t)(4 * nkb + 2) * BW_BOX + (256 + BW_RW * 2) * sizeof(float) + 2048 + 512;
+  int stages = 6;
+  while (stages > 2 && (size_t)stages * BW_BOX + fixed > 226 * 1024) --stages;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * BW_BOX + fixed;
+  const int grid = p.m_tiles < 148 ? p.m_tiles : 148;
+  if (grid_out) *grid_out = grid;
+  static bool attr_set[2] = {false, false};
+  if (nkb == 1) {
+    if (!attr_set[0]) { cudaFuncSetAttribute(tc_bwd_qmf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)); attr_set[0] = true; }
+    LF_LAUNCH("tc_backward_qmf", s, launch_pdl(tc_bwd_qmf_kernel<1>, dim3(grid), dim3(BW_THREADS), smem, s, mW[0], mW[1], mO[0], mO[1], mZ[0], mZ[1], p));
+  } else {
+    if (!attr_set[1]) { cudaFuncSetAttribute(tc_bwd_qmf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)); attr_set[1] = true; }
+    LF_LAUNCH("tc_backward_qmf", s, launch_pdl(tc_bwd_qmf_kernel<2>, dim3(grid), dim3(BW_THREADS), smem, s, mW[0], mW[1], mO[0], mO[1], mZ[0], mZ[1], p));
+  }
+  if (p.trace && ++trace_calls == 12) {
+    // LF_BWD_TRACE=1 (eager launches only): per-role %globaltimer stamps of the 12th call, relative to the first CTA's entry
+    cudaStreamSynchronize(s);
+    static unsigned long long h[148 * 16];
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < grid; ++c) if (h[c * 16] < t0) t0 = h[c * 16];
+    const char* nm[14] = {"entry", "setup", "rm_start", "rm_T0_done", "rm_T1_done", "-", "mma_T0_start", "mma_T1_start", "mma_T0_issued",
+                          "mma_T1_issued", "epi_T0_done", "epi_T1_done", "epi_done", "exit"};
+    for (int k = 0; k < 14; ++k) {
+      double mn = 1e30, mx = 0, sum = 0; int cnt = 0;
+      for (int c = 0; c < grid; ++c) { if (h[c * 16 + k] == 0) continue; const double v = (double)(h[c * 16 + k] - t0) / 1000.0; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; ++cnt; }
+      if (cnt) fprintf(stderr, "[bwd trace] %-14s min %7.2f  avg %7.2f  max %7.2f us  (%d CTAs)\n", nm[k], mn, sum / cnt, mx, cnt);
+    }
+  }
+  return check_launch("tc_bwd_qmf_kernel");
+}
+
+}  // namespace lf
