@@ -94,6 +94,8 @@ def kernel_alg_bytes(name, w, B, fe=4):
         "rows_forward_qmf": (2 * B * C + 2 * B * C + 2 * B + 4 * B) * f + 8 * B,
         "rows_forward_jlogits": (2 * B * C + B * C) * f + B * ldz * fe + 8 * B,
         "rows_backward_qmf": (2 * B * C + 8 * B) * f + 2 * B * ldz * fe + 8 * B,
+        # fused backward: z1 z2 + per-sample scalars in, bf16 heads in, dF and dz (for the dW GEMM) out, labels in
+        "tc_backward_qmf": (2 * B * C + 8 * B) * f + 2 * C * D * fe + 2 * B * D * fe + 2 * B * ldz * fe + 8 * B,
         "rows_calibrated": 2 * B * C * f + 8 * B,
         "sgemm_dfeat": dfeat, "tc_dfeat": dfeat,
         "sgemm_dweight": dweight, "tc_dweight": dweight,
@@ -233,6 +235,8 @@ def workload_config(w, args, world):
     return {"workload": f"{args.workload}: {w['desc']}", "head": w["mode"], "batch_per_gpu": w["B"],
             "global_batch": w["B"] * world, "feature_dim": w["D"], "classes": w["C"], "history_len": w["N"],
             "precision": args.precision, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+            "optimizer": ("SGD(momentum 0.9, wd 1e-4) on the heads fused into the step" if getattr(args, "fused_sgd", False)
+                          else "none (gradients only)"),
             "l2": ("inputs rotate over buffer sets totalling > 2x the 126 MB L2"
                    if 2 * w["B"] * w["D"] * (2 if args.precision == "bf16" else 4) * 8 >= 2 * L2_BYTES
                    else "256 MB L2 flush between steps, outside the per-step CUDA-event brackets")}
@@ -276,6 +280,9 @@ def main():
                          "(C >= 32), exact fp32 FMA for narrow heads; tf32 = fp32 features consumed as TF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-sgd", action="store_true",
+                    help="leave the optimizer step out (default: SGD(momentum 0.9, wd 1e-4) on the heads, utils/BaseModel.py:275-285, "
+                         "fused into the tail of the dW kernel for the tensor-pipe workloads on one GPU)")
     ap.add_argument("--batch", type=int, default=None, help="override the workload's per-GPU batch (experiments)")
     ap.add_argument("--dim", type=int, default=None, help="override the feature width (experiments)")
     ap.add_argument("--classes", type=int, default=None, help="override the class count (experiments)")
@@ -307,6 +314,10 @@ def main():
     eng = LateFusionStep(w["C"], mode=w["mode"], n_data=w["N"], device=dev, precision=args.precision)
     W, b = head_params(w)
     W = [x.to(dev) for x in W]; b = [x.to(dev) for x in b]
+    fused_sgd = (not args.no_sgd) and args.precision != "fp32" and w["C"] >= 32 and world == 1
+    args.fused_sgd = fused_sgd
+    if fused_sgd:
+        eng.enable_sgd(lr=1e-3, momentum=0.9, weight_decay=1.0e-4)
     fe = 2 if args.precision == "bf16" else 4
     in_bytes = 2 * w["B"] * w["D"] * fe
     need_sets = max(2, -(-2 * L2_BYTES // in_bytes))

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 8
+#define LF_ABI_VERSION 9
 
 /* error codes */
 #define LF_OK 0
@@ -71,6 +71,19 @@ extern "C" {
 #define LF_LOSS_NO_JOINT 1 /* loss_joint = 0 */
 #define LF_LOSS_NO_UNI 2   /* the sum of the unimodal CE terms is dropped */
 
+/*
+ * Optional SGD(momentum, weight decay) update of the head parameters fused into the tail of lf_heads_backward
+ * (utils/BaseModel.py:275-285: torch.optim.SGD(lr, momentum=0.9, weight_decay=1e-4), dampening 0, no nesterov):
+ *   d = g + wd*p;  buf = momentum*buf + d;  p -= lr*buf        (zero-initialised buf == torch's first-step buf = d)
+ * applied in place to weight[] / bias[] right after dW / db have been reduced, in the same launch.  Single-GPU
+ * steps only (batch_global == batch): a sharded step must all-reduce the gradients first (LfPeerReduceArgs.sgd).
+ */
+typedef struct LfSgdFused {
+  const float* hyper;        /* device: [lr, momentum, weight_decay, unused], read at run time so a captured graph follows StepLR */
+  float* momentum_buf[4];    /* W1, b1, W2, b2 momentum buffers (device), zero-initialised by the caller */
+  void* weight_bf16_out[2];  /* optional: bf16 copies of the UPDATED weights (what LfHeadsArgs.weight_bf16 consumes) */
+} LfSgdFused;
+
 typedef struct LfHeadsArgs {
   int32_t batch;        /* B: samples in this shard */
   int32_t batch_global; /* denominator of every batch mean (== batch on one GPU) */
@@ -108,9 +121,22 @@ typedef struct LfHeadsArgs {
                              aligned bases) lets the row kernels write them with 128-bit stores. */
   int32_t loss_terms;     /* QMF: LF_LOSS_* bits */
   int32_t reserved3;
+  const void* weight_bf16[2]; /* LF_PREC_BF16, optional: bf16 copies of weight[0/1] that the caller keeps current
+                                 (lf_cast_heads_bf16 after an optimizer step, or LfSgdFused.weight_bf16_out).  NULL:
+                                 lf_heads_forward casts the heads itself on every call, like autocast does */
+  const LfSgdFused* sgd;      /* optional (host pointer): fused SGD update in lf_heads_backward, see LfSgdFused */
+  uint64_t* stats_rows_out;   /* optional (HOST pointer to 2 words): when the forward leaves its statistics as per-CTA
+                                 partial rows (the fused tensor-pipe forward), lf_heads_forward skips the launch that sums
+                                 them into `stats` and returns {device pointer of the float rows, number of rows} here for
+                                 LfMidArgs.stats_rows; otherwise it writes {0, 0} and `stats` holds the sums as usual */
 } LfHeadsArgs;
 
-/* Bytes of caller-provided scratch the heads calls need. */
+/* bf16 copies of two (n_each)-element fp32 tensors: out16 = [bf16(w0) | bf16(w1)] (the cast autocast does per step). */
+int lf_cast_heads_bf16(const float* w0, const float* w1, void* out16, size_t n_each, void* stream);
+
+/* Bytes of caller-provided scratch the heads calls need.  The workspace starts with LF_WS_SYNC_BYTES of inter-CTA
+   counters: zero-fill the workspace ONCE after allocating it; every call leaves the counters zero. */
+#define LF_WS_SYNC_BYTES 256
 size_t lf_workspace_bytes(int32_t batch, int32_t dim, int32_t classes);
 
 /*
@@ -266,6 +292,8 @@ typedef struct LfMidArgs {
   int64_t off_idx;
   int64_t off_conf;
   LfPeerComm comm;
+  const float* stats_rows;   /* optional, n_ranks == 1 only: per-CTA partial rows [n_stats_rows][LF_STATS_HEADER + 2C] of the */
+  int64_t n_stats_rows;      /* forward (LfHeadsArgs.stats_rows_out); summed in row order instead of reading stats_parts */
 } LfMidArgs;
 
 size_t lf_mid_workspace_bytes(int32_t batch_global);

@@ -24,6 +24,10 @@ _f32p = C.c_void_p   # device pointers travel as plain integers
 _P2 = C.c_void_p * 2
 
 
+class LfSgdFused(C.Structure):
+    _fields_ = [("hyper", C.c_void_p), ("momentum_buf", C.c_void_p * 4), ("weight_bf16_out", _P2)]
+
+
 class LfHeadsArgs(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("batch_global", C.c_int32), ("dim", C.c_int32), ("classes", C.c_int32),
@@ -33,6 +37,7 @@ class LfHeadsArgs(C.Structure):
         ("dlogits", _P2), ("dfeat", _P2), ("dweight", _P2), ("dbias", _P2),
         ("qmf_g", C.c_void_p), ("ema_offset", C.c_void_p), ("stats", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("fwd_only", C.c_int32), ("bwd_phase", C.c_int32), ("ld_logits", C.c_int32), ("ld_fused", C.c_int32), ("loss_terms", C.c_int32), ("reserved3", C.c_int32),
+        ("weight_bf16", _P2), ("sgd", C.POINTER(LfSgdFused)), ("stats_rows_out", C.POINTER(C.c_uint64)),
     ]
 
 
@@ -72,6 +77,7 @@ class LfMidArgs(C.Structure):
         ("qmf_g", C.c_void_p), ("loss_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("use_peer", C.c_int32), ("loss_terms", C.c_int32), ("payload_local", C.c_void_p), ("payload_bytes", C.c_int64),
         ("off_idx", C.c_int64), ("off_conf", C.c_int64), ("comm", LfPeerComm),
+        ("stats_rows", C.c_void_p), ("n_stats_rows", C.c_int64),
     ]
 
 
@@ -94,6 +100,7 @@ SIGNATURES = {
     "lf_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "lf_heads_forward": (C.c_int, [C.POINTER(LfHeadsArgs), C.c_void_p]),
     "lf_heads_backward": (C.c_int, [C.POINTER(LfHeadsArgs), C.c_void_p]),
+    "lf_cast_heads_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lf_loss_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "lf_ema_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "lf_ogm_coeff": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),

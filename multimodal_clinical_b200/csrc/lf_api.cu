@@ -26,7 +26,8 @@ void finalize_forward_stats(const float* partials, int nblocks, int C, double* s
 bool tc_fwd_supported(int mode, int B, int D, int C, int ld_z, int ld_f, int elem);
 int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2], const float* const bias[2], int elem, int B, int D,
                          int C, float* const z[2], int ld_z, float* avg, float* zdf, int ld_f, float* conf, float* rowstat,
-                         const int64_t* label, float* partials, int nb_total, int* grid_out, cudaStream_t s);
+                         const int64_t* label, float* partials, int nb_total, int* grid_out, double* stats, unsigned* sync,
+                         cudaStream_t s);
 // lf_tc_bwd.cu: dL/dz formed inside the dfeat GEMM (QMF, bf16, 32 <= C <= 128)
 bool tc_bwd_supported(int mode, int precision, int B, int D, int C, int ld_z, int ldz, int need_dfeat);
 int tc_backward_qmf(const RowsArgs& a, const void* const w16[2], void* const dfeat[2], int D, int* grid_out, cudaStream_t s);
@@ -107,6 +108,7 @@ HeadsWorkspace carve_heads_workspace(void* base, int B, int D, int C) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align_up(bytes, 256); return r; };
   const int part_rows = kMaxRowBlocks;
+  w.sync = (unsigned*)take(LF_WS_SYNC_BYTES);
   w.row_partials = (float*)take((size_t)part_rows * stat_len(C) * sizeof(float));
   w.dw_partials = (float*)take((size_t)2 * kMaxSplits * C * D * sizeof(float));
   w.db_partials = (float*)take((size_t)part_rows * 2 * C * sizeof(float));
@@ -135,6 +137,12 @@ static int narrow_grid(const LfHeadsArgs* a, bool fwd_only) {
   if (grid > 148) grid = 148;
   const int rpc = div_up(a->batch, grid);
   return div_up(a->batch, rpc);
+}
+
+// bf16 copy of head m: the caller's (kept current across optimizer steps) or the per-call cast in the workspace
+static const void* heads_w16(const LfHeadsArgs* a, const HeadsWorkspace& w, int m) {
+  if (a->weight_bf16[0] && a->weight_bf16[1]) return a->weight_bf16[m];
+  return (const char*)w.w16 + (size_t)m * a->classes * a->dim * 2;
 }
 
 static int tc_block_n(int n) {            // N tile: <= 256, multiple of 16, balanced over the tiles
@@ -257,6 +265,7 @@ extern "C" size_t lf_workspace_bytes(int32_t batch, int32_t dim, int32_t classes
 extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
   int rc = check_heads(a, false);
   if (rc) return rc;
+  if (a->stats_rows_out) { a->stats_rows_out[0] = 0; a->stats_rows_out[1] = 0; }
   cudaStream_t s = (cudaStream_t)stream;
   HeadsWorkspace w = carve_heads_workspace(a->workspace, a->batch, a->dim, a->classes);
   GemmArgs g;
@@ -282,13 +291,15 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
     d.nbatch = 2;
     const size_t cd = (size_t)a->classes * a->dim;
     if (is_bf16(a)) {
-      rc = cast_weights_bf16(a->weight[0], a->weight[1], w.w16, cd, s);       // what autocast does for nn.Linear every step
-      if (rc) return rc;
+      if (!(a->weight_bf16[0] && a->weight_bf16[1])) {
+        rc = cast_weights_bf16(a->weight[0], a->weight[1], w.w16, cd, s);     // what autocast does for nn.Linear every step
+        if (rc) return rc;
+      }
       d.elem = 2;
     }
     for (int m = 0; m < 2; ++m) {
       d.A[m] = a->feat[m];
-      d.B[m] = is_bf16(a) ? (const void*)((const char*)w.w16 + m * cd * 2) : (const void*)a->weight[m];
+      d.B[m] = is_bf16(a) ? heads_w16(a, w, m) : (const void*)a->weight[m];
       d.bias[m] = a->bias[m]; d.out[m] = a->logits[m];
     }
     {
@@ -300,8 +311,11 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
         float* zp[2] = {a->logits[0], a->logits[1]};
         rc = tc_heads_forward_qmf(fp, d.B, a->bias, d.elem, a->batch, a->dim, a->classes, zp, ldz, a->avg_logits, a->logits_df, ldf,
                                   a->conf, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), a->label, w.row_partials, 0,
-                                  &grid, s);
+                                  &grid, nullptr, nullptr, s);
         if (rc) return rc;
+        // single-GPU steps hand the per-CTA rows to lf_step_mid (LfMidArgs.stats_rows), which sums them with its
+        // whole grid; the exchange of a sharded step needs finished statistics, so they are summed here
+        if (a->stats_rows_out) { a->stats_rows_out[0] = (uint64_t)(uintptr_t)w.row_partials; a->stats_rows_out[1] = (uint64_t)grid; return LF_OK; }
         finalize_forward_stats(w.row_partials, grid, a->classes, a->stats, s);
         return check_launch("finalize_stats");
       }
@@ -355,7 +369,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   int nb_parts = row_blocks(a->batch);           // per-CTA partial rows (db, calibrated counts) of the kernel that made dz
   if (fused_bwd) {
     if (phase == 2) return LF_OK;
-    const void* w16[2] = {w.w16, (const char*)w.w16 + (size_t)a->classes * a->dim * 2};
+    const void* w16[2] = {heads_w16(a, w, 0), heads_w16(a, w, 1)};
     void* df[2] = {a->dfeat[0], a->dfeat[1]};
     rc = tc_backward_qmf(rows_args(a, w), w16, df, a->dim, &nb_parts, s);
     if (rc) return rc;
@@ -376,7 +390,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
       if (is_bf16(a)) { d.elem = 2; d.out_elem = 2; }
       for (int m = 0; m < 2; ++m) {
         d.A[m] = dz[m];
-        d.B[m] = is_bf16(a) ? (const void*)((const char*)w.w16 + (size_t)m * a->classes * a->dim * 2) : (const void*)a->weight[m];
+        d.B[m] = is_bf16(a) ? heads_w16(a, w, m) : (const void*)a->weight[m];
         d.bias[m] = nullptr; d.out[m] = a->dfeat[m];
       }
       d.M = a->batch; d.N = a->dim; d.K = a->classes;
@@ -416,7 +430,30 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     if (splits > kMaxSplits) splits = kMaxSplits;
     if (splits < 1) splits = 1;
     d.splits = splits; d.split_stride = (long long)cd; d.balance_m = 0; d.name = "tc_dweight";
+    // the reduction of the split-K partials, db, the calibrated counts (and the optional SGD step) run in the kernel's tail
+    const bool tail = cd % 4 == 0 && tiles * splits <= 148 && !getenv("LF_NO_DW_TAIL");
+    if (a->sgd && (!tail || a->batch_global != a->batch)) {
+      set_error("fused SGD needs the tensor-pipe dW tail on a single-GPU step (batch_global == batch)");
+      return LF_ERR_UNSUPPORTED;
+    }
+    if (tail) {
+      TcTail& t = d.tail;
+      t.on = 1; t.sync = w.sync + 4;
+      t.dw[0] = a->dweight[0]; t.dw[1] = a->dweight[1]; t.n = (long long)cd;
+      t.dbpart = w.db_partials; t.calpart = w.cal_partials; t.nb_db = nb_parts; t.nb_cal = nb_parts; t.C = a->classes;
+      t.db[0] = a->dbias[0]; t.db[1] = a->dbias[1]; t.stats = a->stats;
+      if (a->sgd) {
+        t.hyper = a->sgd->hyper;
+        for (int m = 0; m < 2; ++m) {
+          t.param_w[m] = const_cast<float*>(a->weight[m]); t.param_b[m] = const_cast<float*>(a->bias[m]);
+          t.mom_w[m] = a->sgd->momentum_buf[2 * m]; t.mom_b[m] = a->sgd->momentum_buf[2 * m + 1];
+          t.w16[m] = a->sgd->weight_bf16_out[m];
+        }
+      }
+    }
     rc = tc_gemm(d, s);
+    if (rc) return rc;
+    if (tail) return LF_OK;
   } else {
     g.splits = splits; g.k_chunk = div_up(a->batch, splits); g.split_stride = cd;
     rc = gemm_dweight(g, 2, s);
@@ -431,6 +468,11 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   if (rc) return rc;
   return finalize_db_cal(w.db_partials, nb_db, a->classes, w.cal_partials, nb_parts, a->dbias[0], a->dbias[1],
                          a->stats, s);
+}
+
+extern "C" int lf_cast_heads_bf16(const float* w0, const float* w1, void* out16, size_t n_each, void* stream) {
+  if (!w0 || !w1 || !out16 || n_each == 0) { set_error("lf_cast_heads_bf16: bad argument"); return LF_ERR_BAD_ARG; }
+  return cast_weights_bf16(w0, w1, out16, n_each, (cudaStream_t)stream);
 }
 
 extern "C" int lf_loss_finalize(const double* stats, int32_t mode, int32_t batch_global, float* loss_out, void* stream) {

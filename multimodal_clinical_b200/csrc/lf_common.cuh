@@ -86,6 +86,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- workspace carving (shared by lf_api.cu and tests of lf_workspace_bytes) -------------------
 struct HeadsWorkspace {
+  unsigned* sync;        // [LF_WS_SYNC_BYTES / 4] inter-CTA counters, zero between calls: [0] forward tail, [4..5] dW tail
   float* row_partials;   // [kMaxRowBlocks][stat_len]   per-block partial statistics
   float* dw_partials;    // [2][splits][C][D]
   float* db_partials;    // [part_rows][2][C]  column sums of dz per producing CTA

@@ -127,11 +127,42 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
       if ((unsigned long long)i < (unsigned long long)N) atomicMax(&lw[i], base + j);
     }
 
-  // ---- P0: global statistics in rank order
-  for (int i = threadIdx.x; i < len; i += blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < a.n_ranks; ++r) s += stats_parts[(size_t)r * stats_stride + i];
-    s_stats[i] = s;
+  // ---- P0: global statistics in rank order -- or, on one GPU, straight from the per-CTA partial rows of the forward
+  // kernel (the separate finalize_stats launch folded in): 256 columns x blockDim / 256 row groups, every thread's
+  // loads independent, partial sums combined in group order (fixed summation order)
+  if (a.stats_rows) {
+    __shared__ double s_part[4][256];
+    const int ng = (int)blockDim.x / 256, g = threadIdx.x / 256, c0 = threadIdx.x % 256;
+    const int nrow = (int)a.n_stats_rows;
+    for (int cb = 0; cb < len; cb += 256) {
+      const int c = cb + c0;
+      double s = 0.0;
+      if (c < len) {
+        int r = g;
+        for (; r + 7 * ng < nrow; r += 8 * ng) {
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = a.stats_rows[(size_t)(r + k * ng) * len + c];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s += (double)v[k];
+        }
+        for (; r < nrow; r += ng) s += (double)a.stats_rows[(size_t)r * len + c];
+      }
+      s_part[g][c0] = s;
+      __syncthreads();
+      if (g == 0 && c < len) {
+        double t = s_part[0][c0];
+        for (int k = 1; k < ng; ++k) t += s_part[k][c0];
+        s_stats[c] = t;
+      }
+      __syncthreads();
+    }
+  } else {
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+      double s = 0.0;
+      for (int r = 0; r < a.n_ranks; ++r) s += stats_parts[(size_t)r * stats_stride + i];
+      s_stats[i] = s;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -215,17 +246,24 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
     }
   }
   grid.sync();                                             // History updated, per-CTA min / max published
-  if (threadIdx.x < 2) {
-    const int m = threadIdx.x;
-    double lo = p.minmax[m * 2], hi = p.minmax[m * 2 + 1];
-    bool nan = (lo != lo);
-    for (int b = 1; b < ncta; ++b) {
+  if (threadIdx.x < 64) {
+    // warp m combines the per-CTA min / max of modality m: every lane's loads are independent (one memory round trip
+    // instead of a chain of ncta), min / max are order-independent, NaN wins
+    const int m = threadIdx.x / 32, ln = threadIdx.x % 32;
+    double lo = INFINITY, hi = -INFINITY;
+    bool nan = false;
+    for (int b = ln; b < ncta; b += 32) {
       const double l = p.minmax[(b * 2 + m) * 2], h = p.minmax[(b * 2 + m) * 2 + 1];
       nan |= (l != l);
       lo = fmin(lo, l); hi = fmax(hi, h);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(kFull, lo, o)); hi = fmax(hi, __shfl_xor_sync(kFull, hi, o));
+    }
+    nan = __any_sync(kFull, nan);
     if (nan) { lo = NAN; hi = NAN; }
-    sh.lo[m] = lo; sh.hi[m] = hi;
+    if (ln == 0) { sh.lo[m] = lo; sh.hi[m] = hi; }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -273,9 +311,13 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
   }
   grid.sync();
   // ---- P5: loss = CE(z_df) + CE(z1) + CE(z2) + L_reg, each a separate fp32 mean like the reference
-  if (cta == 0 && threadIdx.x == 0) {
+  if (cta == 0 && threadIdx.x < 32) {
+    // lane l adds the partials of CTAs l, l + 32, ... in order, then a fixed xor butterfly (bit-reproducible)
     double rs = 0.0;
-    for (int b = 0; b < ncta; ++b) rs += (double)p.regpart[b];
+    for (int b = threadIdx.x; b < ncta; b += 32) rs += (double)p.regpart[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(kFull, rs, o);
+    if (threadIdx.x == 0) {
     a.stats[LF_STAT_REG_SUM] = rs;
     if (!a.step_base) lw[N] = base - 1 + Bg;
     if (a.use_peer) a.comm.epoch[0] = epoch;
@@ -285,6 +327,7 @@ __global__ void __launch_bounds__(kMidThreads) mid_kernel(MidParams p) {
       const float uni = (a.loss_terms & LF_LOSS_NO_UNI) ? 0.f : (float)(s_stats[LF_STAT_CE_X1] * inv) + (float)(s_stats[LF_STAT_CE_X2] * inv);
       const float joint = (a.loss_terms & LF_LOSS_NO_JOINT) ? 0.f : (float)(s_stats[LF_STAT_CE_JOINT] * inv);
       a.loss_out[0] = (joint + uni) + (float)(rs * inv);
+    }
     }
   }
 }
@@ -304,7 +347,11 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
     set_error("lf_step_mid: bad peer-exchange arguments");
     return LF_ERR_BAD_ARG;
   }
-  if (!a || (!a->stats_parts && !a->use_peer) || !a->stats || a->classes < 1 || a->batch_global < 1 || a->n_ranks < 1 ||
+  if (a && a->stats_rows && (a->n_ranks != 1 || a->use_peer || a->n_stats_rows < 1)) {
+    set_error("lf_step_mid: stats_rows is a single-GPU input (n_ranks == 1, no peer exchange)");
+    return LF_ERR_BAD_ARG;
+  }
+  if (!a || (!a->stats_parts && !a->use_peer && !a->stats_rows) || !a->stats || a->classes < 1 || a->batch_global < 1 || a->n_ranks < 1 ||
       a->batch_local < 1 || a->batch_local * a->n_ranks != a->batch_global || a->rank < 0 || a->rank >= a->n_ranks) {
     set_error("lf_step_mid: bad argument");
     return LF_ERR_BAD_ARG;

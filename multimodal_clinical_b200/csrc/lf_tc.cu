@@ -38,6 +38,121 @@ constexpr int TC_THREADS = 320;                          // producer warp, MMA w
 
 struct Item { int batch, split, m0, n0, k_begin, num_kb, k_end; };
 
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Tail of the split-K dW GEMM, run by every thread of every CTA after the main loop (TcTail).
+__device__ __forceinline__ void gemm_tail(const TcGemmParams& p, float* s_rows) {   // s_rows: >= 384 floats of shared memory
+  const TcTail& t = p.tail;
+  unsigned long long* tr = t.trace ? t.trace + (size_t)blockIdx.x * 8 : nullptr;
+  auto stamp = [&](int k) { if (tr && threadIdx.x == 0) { unsigned long long x; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(x)); tr[k] = x; } };
+  stamp(1);
+  // ---- grid barrier: every CTA's partial tiles are in global memory (the TMA stores were waited for and fenced)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&t.sync[0], 1u);
+    while (ld_acquire_gpu_u32(&t.sync[0]) < gridDim.x) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+  stamp(2);
+  const float lr = t.hyper ? t.hyper[0] : 0.f, mom = t.hyper ? t.hyper[1] : 0.f, wd = t.hyper ? t.hyper[2] : 0.f;
+  // ---- dW: float4 i of modality m = sum over the splits, in split order; the work is spread over the whole grid
+  const long long n4 = t.n / 4, total4 = 2 * n4;
+  const long long per_cta = (total4 + gridDim.x - 1) / gridDim.x;
+  const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < total4 ? lo + per_cta : total4;
+  for (long long j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+    const int m = j >= n4 ? 1 : 0;
+    const long long i = (j - (long long)m * n4) * 4;
+    const float* part = (const float*)p.out[m] + i;
+    // parameter and momentum of this float4 are fetched with the partials (one round trip for everything)
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = w4;
+    if (t.hyper) {
+      w4 = *reinterpret_cast<const float4*>(t.param_w[m] + i);
+      b4 = *reinterpret_cast<const float4*>(t.mom_w[m] + i);
+    }
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = 0;
+    for (; k + 8 <= p.splits; k += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(part + (long long)(k + u) * p.split_stride));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; k < p.splits; ++k) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (long long)k * p.split_stride));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* o = t.dw[m] + i;               // the flat gradient buffer packs dW2 after db1: not always 16-byte aligned
+    const float g[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = g[e];
+    if (t.hyper) {                        // torch.optim.SGD: d = g + wd p; buf = mom buf + d; p -= lr buf
+      const float w0[4] = {w4.x, w4.y, w4.z, w4.w}, m0[4] = {b4.x, b4.y, b4.z, b4.w};
+      float np[4], nb[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = g[e] + wd * w0[e];
+        nb[e] = mom * m0[e] + d;
+        np[e] = w0[e] - lr * nb[e];
+      }
+      *reinterpret_cast<float4*>(t.mom_w[m] + i) = make_float4(nb[0], nb[1], nb[2], nb[3]);
+      *reinterpret_cast<float4*>(t.param_w[m] + i) = make_float4(np[0], np[1], np[2], np[3]);
+      if (t.w16[m]) {
+        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(np[0], np[1]), hi2 = __floats2bfloat162_rn(np[2], np[3]);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&lo2); u.y = *reinterpret_cast<const uint32_t*>(&hi2);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(t.w16[m]) + i) = u;
+      }
+    }
+  }
+  stamp(3);
+  // ---- db and the calibrated counts: column sums of the per-CTA partials of the kernel that produced dz.  One output
+  // per CTA and pass: every thread fetches one partial row (a single memory round trip), thread 0 adds them in row order
+  for (int i = blockIdx.x; i < 2 * t.C + 2; i += gridDim.x) {
+    const bool is_db = i < 2 * t.C;
+    const float* src = is_db ? t.dbpart + i : t.calpart + (i - 2 * t.C);
+    const int pitch = is_db ? 2 * t.C : 2, nb = is_db ? t.nb_db : t.nb_cal;
+    double s = 0.0;
+    for (int b0 = 0; b0 < nb; b0 += 384) {
+      __syncthreads();
+      for (int b = threadIdx.x; b < 384 && b0 + b < nb; b += blockDim.x) s_rows[b] = src[(size_t)(b0 + b) * pitch];
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        // lane l adds rows l, l + 32, ... in order, then a fixed xor butterfly: the same order on every launch
+        double q = 0.0;
+        for (int b = threadIdx.x; b < 384 && b0 + b < nb; b += 32) q += (double)s_rows[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        s += q;
+      }
+    }
+    if (threadIdx.x != 0) continue;
+    if (!is_db) { t.stats[LF_STAT_CNT_X1_CAL + (i - 2 * t.C)] = s; continue; }
+    const int m = i >= t.C ? 1 : 0, c = i - m * t.C;
+    const float g = (float)s;
+    t.db[m][c] = g;
+    if (t.hyper) {
+      const float w0 = t.param_b[m][c];
+      const float d = g + wd * w0;
+      const float bb = mom * t.mom_b[m][c] + d;
+      t.mom_b[m][c] = bb;
+      t.param_b[m][c] = w0 - lr * bb;
+    }
+  }
+  // ---- leave the counters zero for the next launch: the last CTA to depart resets them
+  __syncthreads();
+  stamp(4);
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&t.sync[1], 1u) == gridDim.x - 1) { t.sync[0] = 0u; t.sync[1] = 0u; __threadfence(); }
+  }
+}
+
 __device__ __forceinline__ Item decode_item(const TcGemmParams& p, int item) {
   Item it;
   const int n_t = item % p.n_tiles; int r = item / p.n_tiles;
@@ -111,6 +226,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (p.tail.trace && threadIdx.x == 0) { unsigned long long x; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(x)); p.tail.trace[(size_t)blockIdx.x * 8] = x; }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapB0);
@@ -253,7 +369,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-    if (p.tma_store && et == 0) tma_store_wait_all();
+    if (p.tma_store && et == 0) {
+      tma_store_wait_all();
+      if (p.tail.on) asm volatile("fence.proxy.async;" ::: "memory");    // async-proxy stores -> generic-proxy readers of the tail
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -261,6 +380,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  if (p.tail.on) gemm_tail(p, reinterpret_cast<float*>(staging));      // the store boxes are idle by now
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -431,6 +551,40 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = p.total_items < 148 ? p.total_items : 148;
+  p.tail = d.tail;
+  static unsigned long long* trace_buf = nullptr;
+  static int trace_calls = 0;
+  if (p.tail.on && getenv("LF_DW_TRACE")) {
+    if (!trace_buf) { cudaMalloc(&trace_buf, 148 * 8 * sizeof(unsigned long long)); cudaMemset(trace_buf, 0, 148 * 8 * sizeof(unsigned long long)); }
+    p.tail.trace = trace_buf;
+  }
+  if (p.tail.on) {
+    // the tail's grid barrier needs every CTA resident at once: a cooperative launch guarantees it (or fails)
+    if (!p.tma_store || p.tail.n % 4) { set_error("tc_gemm: the fused dW tail needs the TMA-store epilogue and C*D %% 4 == 0"); return LF_ERR_BAD_ARG; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 128 * p.epi_halves); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = getenv("LF_DW_NOCOOP") ? 0 : 1;
+    cudaError_t e = cudaSuccess;
+    LF_LAUNCH(d.name, s, (e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p)));
+    if (e != cudaSuccess) { set_error("%s: %s", d.name, cudaGetErrorString(e)); return LF_ERR_CUDA; }
+    if (p.tail.trace && ++trace_calls == 12) {
+      cudaStreamSynchronize(s);
+      static unsigned long long h[148 * 8];
+      cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull;
+      for (int c = 0; c < grid; ++c) if (h[c * 8] < t0) t0 = h[c * 8];
+      const char* nm[5] = {"entry", "gemm_done", "barrier_done", "dw_reduced", "db_done"};
+      for (int k = 0; k < 5; ++k) {
+        double mn = 1e30, mx = 0, sum = 0;
+        for (int c = 0; c < grid; ++c) { const double v = (double)(h[c * 8 + k] - t0) / 1000.0; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; }
+        fprintf(stderr, "[dw trace] %-13s min %7.2f  avg %7.2f  max %7.2f us\n", nm[k], mn, sum / grid, mx);
+      }
+    }
+    return check_launch(d.name);
+  }
   LF_LAUNCH(d.name, s, launch_pdl(tc_gemm_kernel, dim3(grid), dim3(64 + 128 * p.epi_halves), smem, s, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p));
   return check_launch(d.name);
 }

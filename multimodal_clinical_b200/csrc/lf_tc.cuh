@@ -4,6 +4,28 @@
 
 namespace lf {
 
+// Optional tail of the split-K dW GEMM (replaces the separate finalize_grads launch): after a grid-wide barrier every
+// CTA sums a slice of the split-K partials in split order (bit-reproducible), CTA 0 sums the db / calibrated-count
+// partials of the kernel that produced dz, and -- when hyper != null -- the SGD update of the heads is applied in place.
+struct TcTail {
+  int on;
+  unsigned* sync;            // [0] arrivals, [1] departures; zero before the launch, zero after it
+  float* dw[2];              // out (C*D)
+  long long n;               // C*D
+  const float* dbpart;       // [nb_db][2][C]
+  const float* calpart;      // [nb_cal][2]
+  int nb_db, nb_cal, C;
+  float* db[2];              // out (C)
+  double* stats;             // calibrated counts land in stats[LF_STAT_CNT_X1_CAL ..]
+  const float* hyper;        // device [lr, momentum, weight_decay]; null = no optimizer step
+  float* param_w[2];
+  float* param_b[2];
+  float* mom_w[2];
+  float* mom_b[2];
+  void* w16[2];              // optional bf16 copies of the updated weights
+  unsigned long long* trace; // LF_DW_TRACE=1: [grid][8] %globaltimer stamps
+};
+
 // Device-side parameters of the persistent tc_gemm_kernel.
 struct TcGemmParams {
   int M, N, K;             // true problem sizes (ragged edges are zero-filled by TMA / clipped on store)
@@ -30,6 +52,7 @@ struct TcGemmParams {
   const float* bias[2];
   long long ld_out;        // output row pitch (elements)
   long long split_stride;  // elements between split partials
+  TcTail tail;
 };
 
 // Host-side description of one (batched x2) GEMM:  out[b] (M x N) = A[b] * B[b] (+ bias[b]).
@@ -53,6 +76,7 @@ struct TcGemmDesc {
   int out_elem = 4;        // 4 = fp32 output, 2 = bf16 output (TMA-store epilogue only)
   int max_epi_halves = 2;  // 1: never add the second group of epilogue warps (the CTA then leaves room for a concurrent kernel)
   int balance_m = 0;           // 1: pick tile_m so that the number of work items is a multiple of the SM count (K-major A, plain-store epilogue only)
+  TcTail tail = {};            // tail.on: fused reduction of the split-K partials (needs all CTAs co-resident: grid <= 148)
   const char* name;
 };
 

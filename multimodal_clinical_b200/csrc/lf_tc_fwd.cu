@@ -52,6 +52,8 @@ struct TcFwdParams {
   float* rowstat;          // (B,4): lse1, lse2, lse(z_df), -
   const int64_t* label;
   float* partials;         // [nb_total][stat_len]
+  double* stats;           // when sync != null: the LAST CTA to finish sums the per-CTA partial rows into stats (fixed order)
+  unsigned* sync;          // zero-initialised arrival counter, left zero
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -430,6 +432,46 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     for (int r = blockIdx.x + gridDim.x; r < p.nb_total; r += gridDim.x)       // rows no CTA owns
       for (int c = et; c < stat_len_dev(C); c += 128 * H) p.partials[(size_t)r * stat_len_dev(C) + c] = 0.f;
+    if (p.sync) {
+      // ---- the separate finalize_stats launch, folded in: the last CTA to arrive sums every CTA's partial row, rows in
+      // CTA order and in fp64, so the result does not depend on which CTA happens to be last
+      double* s_half = reinterpret_cast<double*>(xch);     // [256]: the exchange slots are free by now (H = 4: 4 KB)
+      volatile int* s_last = reinterpret_cast<volatile int*>(sstg);
+      named_bar_sync(1, 128 * H);                    // this CTA's row is written
+      if (et == 0) {
+        __threadfence();
+        *s_last = atomicAdd(p.sync, 1u) == gridDim.x - 1;
+      }
+      named_bar_sync(1, 128 * H);
+      if (*s_last) {
+        __threadfence();
+        const int len = stat_len_dev(C), nrow = (int)gridDim.x;
+        constexpr int NG = (128 * H >= 512) ? 2 : 1;  // row groups of 256 threads (one column each)
+        const int half = NG == 2 ? (nrow + 1) / 2 : nrow;
+        const int g = et / 256, c0 = et % 256;
+        for (int cb = 0; cb < len; cb += 256) {       // uniform trip count: every thread takes every barrier
+          const int c = cb + c0;
+          double s = 0.0;
+          if (c < len && g < NG) {
+            const int r0 = g * half, r1 = min(nrow, r0 + half);
+            int r = r0;
+            for (; r + 8 <= r1; r += 8) {
+              float v[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = __ldcg(p.partials + (size_t)(r + k) * len + c);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) s += (double)v[k];
+            }
+            for (; r < r1; ++r) s += (double)__ldcg(p.partials + (size_t)r * len + c);
+            if (g == 1) s_half[c0] = s;
+          }
+          named_bar_sync(1, 128 * H);
+          if (c < len && g == 0) p.stats[c] = NG == 2 ? s + s_half[c0] : s;
+          named_bar_sync(1, 128 * H);
+        }
+        if (et == 0) { *p.sync = 0u; __threadfence(); }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -469,8 +511,10 @@ static int launch_fwd(const CUtensorMap* mA, const CUtensorMap* mW, const TcFwdP
 // feat / weight: bf16 (elem 2) or fp32 consumed as TF32 (elem 4); everything else fp32.
 int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2], const float* const bias[2], int elem, int B, int D,
                          int C, float* const z[2], int ld_z, float* avg, float* zdf, int ld_f, float* conf, float* rowstat,
-                         const int64_t* label, float* partials, int nb_total, int* grid_out, cudaStream_t s) {
+                         const int64_t* label, float* partials, int nb_total, int* grid_out, double* stats, unsigned* sync,
+                         cudaStream_t s) {
   TcFwdParams p;
+  p.stats = stats; p.sync = stats ? sync : nullptr;
   p.B = B; p.C = C; p.D = D; p.ld_z = ld_z; p.ld_f = ld_f;
   p.block_n = div_up(C, 16) * 16;
   p.elem = elem == 2 ? 2 : 4;

@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 from . import _lib, parallel
 from ._lib import (LF_MODE_JLOGITS, LF_MODE_QMF, LF_PREC_BF16, LF_PREC_FP32, LF_PREC_TF32, LF_STATS_HEADER, STAT,
-                   LfHeadsArgs, LfMidArgs, LfQmfArgs, LfTensorList, check)
+                   LfHeadsArgs, LfMidArgs, LfQmfArgs, LfSgdFused, LfTensorList, check)
 
 _MOD = {"OGM_GE": _lib.LF_MOD_OGM_GE, "OGM": _lib.LF_MOD_OGM, "noise": _lib.LF_MOD_NOISE}
 
@@ -138,6 +138,43 @@ class LateFusionStep:
         self._ws_key = None
         self._bufs = {}
         self.mod_ws = torch.empty(self.lib.lf_modulate_workspace_bytes(), dtype=torch.uint8, device=dev)
+        # bf16 copies of the heads (LF_PREC_BF16), re-cast only when a head tensor changes (torch bumps ``_version`` on
+        # every in-place update) or kept current by the fused SGD step; ``cache_w16 = False`` casts on every call
+        self.cache_w16 = True
+        self._w16 = None
+        self._w16_key = None
+        self._sgd = None
+        self._capturing = False
+
+    # ------------------------------------------------------------------ fused SGD on the heads
+    def enable_sgd(self, lr: float, momentum: float = 0.9, weight_decay: float = 1.0e-4) -> None:
+        """Apply torch.optim.SGD(lr, momentum, weight_decay) (utils/BaseModel.py:275-285) to the head tensors passed
+        to ``step`` INSIDE the step: the update runs in the tail of the dW kernel, right after the gradients are
+        reduced (after the gradient all-reduce on several GPUs), and also refreshes the bf16 copies of the heads.
+        The hyper-parameters live on the device, so a captured graph follows ``set_lr`` (StepLR)."""
+        if self.precision == LF_PREC_FP32 or self.C < 32:
+            raise _lib.LfError("the fused SGD step is part of the tensor-pipe backward (wide heads, tf32 / bf16)")
+        self._sgd = {"hyper": torch.tensor([lr, momentum, weight_decay, 0.0], device=self.device), "mom": None, "key": None}
+
+    def set_lr(self, lr: float) -> None:
+        self._sgd["hyper"][0:1].fill_(float(lr))
+
+    def disable_sgd(self) -> None:
+        self._sgd = None
+
+    def _heads_bf16(self, W):
+        """(ptr0, ptr1) of current bf16 copies of the heads, or None to let lf_heads_forward cast per call."""
+        if not self.bf16 or not self.cache_w16 or (self._capturing and self._sgd is None):
+            return None                       # inside a graph only the fused SGD keeps the copies current
+        key = (W[0].data_ptr(), W[0]._version, W[1].data_ptr(), W[1]._version)
+        if self._w16 is None or self._w16.shape[1:] != W[0].shape:
+            self._w16 = torch.empty((2,) + tuple(W[0].shape), dtype=torch.bfloat16, device=self.device)
+            self._w16_key = None
+        if self._w16_key != key:
+            check(self.lib.lf_cast_heads_bf16(W[0].data_ptr(), W[1].data_ptr(), self._w16.data_ptr(), W[0].numel(), _stream()),
+                  "lf_cast_heads_bf16")
+            self._w16_key = key
+        return self._w16[0].data_ptr(), self._w16[1].data_ptr()
 
     @property
     def correctness(self) -> torch.Tensor:
@@ -154,7 +191,7 @@ class LateFusionStep:
         if self._ws_key != key:
             dev, Cn = self.device, self.C
             nbytes = self.lib.lf_workspace_bytes(B, D, Cn)
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)     # starts with zeroed inter-CTA counters
             qmf = self.mode == LF_MODE_QMF
             b = {}
             # tensor-pipe path: logits rows padded to 16 B so the GEMM epilogue can TMA-store them; callers get views
@@ -320,7 +357,28 @@ class LateFusionStep:
         a.stats = _ptr(p_stats)                                   # forward writes the LOCAL partial sums
         a.workspace = _ptr(self._ws); a.workspace_bytes = self._ws.numel()
         st = _stream()
+        w16 = self._heads_bf16(W)
+        if w16 is not None:
+            a.weight_bf16[0], a.weight_bf16[1] = w16
+        sgd = None
+        if self._sgd is not None and backward and self.world == 1:
+            if W[0] is not weights[0] or W[1] is not weights[1] or bb[0] is not biases[0] or bb[1] is not biases[1]:
+                raise _lib.LfError("the fused SGD step updates the head tensors in place: pass contiguous fp32 CUDA tensors")
+            key = (W[0].data_ptr(), bb[0].data_ptr(), W[1].data_ptr(), bb[1].data_ptr())
+            if self._sgd["key"] != key:          # momentum buffers follow the parameter tensors (zero = torch's first step)
+                self._sgd["mom"] = [torch.zeros_like(t) for t in (W[0], bb[0], W[1], bb[1])]
+                self._sgd["key"] = key
+            sgd = LfSgdFused()
+            sgd.hyper = _ptr(self._sgd["hyper"])
+            for k, t in enumerate(self._sgd["mom"]):
+                sgd.momentum_buf[k] = _ptr(t)
+            if w16 is not None:
+                sgd.weight_bf16_out[0], sgd.weight_bf16_out[1] = w16
+            a.sgd = C.pointer(sgd)
 
+        rows_out = (C.c_uint64 * 2)(0, 0)
+        if self.world == 1:
+            a.stats_rows_out = rows_out       # one GPU: lf_step_mid sums the forward's per-CTA rows itself
         check(lib.lf_heads_forward(C.byref(a), st), "lf_heads_forward")
         peer = self._peer_comm(pay.numel(), gf.numel())
         if peer is not None:
@@ -339,6 +397,8 @@ class LateFusionStep:
         mid.batch_local, mid.rank, mid.n_data, mid.update_ema = B, self.rank, self.n_data or 0, int(update_ema)
         base = gathered.data_ptr()
         mid.stats_parts, mid.stats_stride = base, stride // 8
+        if rows_out[0]:
+            mid.stats_rows, mid.n_stats_rows = rows_out[0], rows_out[1]
         if qmf:
             qs = self.qmf_state
             mid.idx_parts, mid.idx_stride = (idx.data_ptr() if self.world == 1 else base + self._off_idx), stride // 8
@@ -413,10 +473,14 @@ class LateFusionStep:
         cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            out = self.step(feats, weights, biases, label, idx=idx, **kw)
-            if extra is not None:
-                extra()
+        self._capturing = True
+        try:
+            with torch.cuda.graph(graph):
+                out = self.step(feats, weights, biases, label, idx=idx, **kw)
+                if extra is not None:
+                    extra()
+        finally:
+            self._capturing = False
         return graph, out
 
     # ------------------------------------------------------------------ host-fed steps

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, n), f"{n} declared in include/lf_fusion.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.lf_abi_version() == 8
+    assert lib.lf_abi_version() == 9
 
 
 def test_struct_layout_matches_c(tmp_path):
@@ -42,14 +42,14 @@ def test_struct_layout_matches_c(tmp_path):
     from multimodal_clinical_b200 import _lib
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lf_fusion.h"\nint main(){'
-                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(LfHeadsArgs), offsetof(LfHeadsArgs, feat),'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(LfSgdFused), offsetof(LfHeadsArgs, sgd), sizeof(LfHeadsArgs), offsetof(LfHeadsArgs, feat),'
                     'offsetof(LfHeadsArgs, stats), sizeof(LfQmfArgs), offsetof(LfQmfArgs, step_base),'
                     'offsetof(LfQmfArgs, workspace), sizeof(LfTensorList), sizeof(LfMidArgs), offsetof(LfMidArgs, stats),'
                     'offsetof(LfMidArgs, step_base), offsetof(LfHeadsArgs, fwd_only)); return 0;}')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    want = [C.sizeof(_lib.LfHeadsArgs), _lib.LfHeadsArgs.feat.offset, _lib.LfHeadsArgs.stats.offset,
+    want = [C.sizeof(_lib.LfSgdFused), _lib.LfHeadsArgs.sgd.offset, C.sizeof(_lib.LfHeadsArgs), _lib.LfHeadsArgs.feat.offset, _lib.LfHeadsArgs.stats.offset,
             C.sizeof(_lib.LfQmfArgs), _lib.LfQmfArgs.step_base.offset, _lib.LfQmfArgs.workspace.offset,
             C.sizeof(_lib.LfTensorList), C.sizeof(_lib.LfMidArgs), _lib.LfMidArgs.stats.offset,
             _lib.LfMidArgs.step_base.offset, _lib.LfHeadsArgs.fwd_only.offset]

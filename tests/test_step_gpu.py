@@ -198,3 +198,54 @@ def test_stream_from_host_matches_eager_steps():
     got = list(eg.stream_from_host(iter(host), W, b))
     assert got == want[4:]
     assert torch.equal(eg.correctness, ea.correctness) and torch.equal(eg.ema_x, ea.ema_x)
+
+
+def test_fused_sgd_in_the_dw_tail_matches_torch_sgd():
+    """SGD(momentum 0.9, wd 1e-4) applied inside the tail of the dW kernel == torch.optim.SGD fed
+    with the gradients the step returns (utils/BaseModel.py:275-285), including the bf16 copies the next forward uses."""
+    B, D, Cn, N = 2048, 768, 101, 5000
+    s = _batch(B, D, Cn, 11, N)
+    f = [s["f1"].bfloat16(), s["f2"].bfloat16()]
+    Wa = [s["W1"].clone(), s["W2"].clone()]; ba = [s["b1"].clone(), s["b2"].clone()]
+    Wb = [s["W1"].clone().requires_grad_(True), s["W2"].clone().requires_grad_(True)]
+    bb = [s["b1"].clone().requires_grad_(True), s["b2"].clone().requires_grad_(True)]
+    ea = _eng(num_classes=Cn, mode="qmf", n_data=N, precision="bf16")
+    ea.enable_sgd(lr=0.05, momentum=0.9, weight_decay=1e-4)
+    eb = _eng(num_classes=Cn, mode="qmf", n_data=N, precision="bf16")
+    opt = torch.optim.SGD(Wb + bb, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    for step in range(4):
+        if step == 2:
+            ea.set_lr(0.025)
+            opt.param_groups[0]["lr"] = 0.025
+        oa = ea.step(f, Wa, ba, s["y"], idx=s["idx"])
+        ob = eb.step(f, [w.detach() for w in Wb], [x.detach() for x in bb], s["y"], idx=s["idx"])
+        torch.cuda.synchronize()
+        assert_close(oa.loss, ob.loss, 1e-6, f"loss step {step}")          # same heads -> same step
+        assert_close(oa.dweight[1], ob.dweight[1], 1e-6, "dW2")
+        for p, g in zip(Wb + bb, ob.dweight + ob.dbias):
+            p.grad = g.clone()
+        opt.step()
+        for m in range(2):
+            assert_close(Wa[m], Wb[m], 1e-6, f"W{m + 1} after step {step}")
+            assert_close(ba[m], bb[m], 1e-6, f"b{m + 1} after step {step}")
+            assert torch.equal(ea._w16[m], Wa[m].bfloat16())              # the copies the next forward consumes
+
+
+def test_dw_tail_equals_separate_finalize_launch():
+    B, D, Cn, N = 4096, 768, 101, 9000
+    s = _batch(B, D, Cn, 3, N)
+    f = [s["f1"].bfloat16(), s["f2"].bfloat16()]
+    outs = []
+    for tail in (True, False):
+        if not tail:
+            os.environ["LF_NO_DW_TAIL"] = "1"
+        try:
+            e = _eng(num_classes=Cn, mode="qmf", n_data=N, precision="bf16")
+            o = e.step(f, [s["W1"], s["W2"]], [s["b1"], s["b2"]], s["y"], idx=s["idx"])
+            torch.cuda.synchronize()
+            outs.append([o.dweight[0].clone(), o.dweight[1].clone(), o.dbias[0].clone(), o.dbias[1].clone(), o.stats.clone()])
+        finally:
+            os.environ.pop("LF_NO_DW_TAIL", None)
+    for a, b in zip(*outs):
+        assert_close(a, b, 1e-6, "tail vs finalize_grads")
+    assert torch.equal(outs[0][4][5:11], outs[1][4][5:11])
