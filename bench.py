@@ -222,10 +222,11 @@ def run_reference(args, w, rank, world):
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": "fusion_step_train_samples_per_sec", "value": val, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(w, args, 1),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(w, args, world),
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} full-batch steps (B={Bs}) of the oracle port on {cores} host threads"},
+                             "sample": f"{steps} steps of B={Bs} samples (one GPU's share of the global batch {Bs * world}; the port's "
+                                       f"samples/s does not depend on the batch) of the oracle port on {cores} host threads"},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -234,7 +235,7 @@ def run_reference(args, w, rank, world):
 def workload_config(w, args, world):
     return {"workload": f"{args.workload}: {w['desc']}", "head": w["mode"], "batch_per_gpu": w["B"],
             "global_batch": w["B"] * world, "feature_dim": w["D"], "classes": w["C"], "history_len": w["N"],
-            "precision": args.precision, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+            "precision": args.precision, "parallelism": f"dp{world}", "scaling": args.scaling, "cuda_graph": not args.no_graph,
             "optimizer": ("SGD(momentum 0.9, wd 1e-4) on the heads fused into the step" if getattr(args, "fused_sgd", False)
                           else "none (gradients only)"),
             "l2": ("inputs rotate over buffer sets totalling > 2x the 126 MB L2"
@@ -283,6 +284,11 @@ def main():
     ap.add_argument("--no-sgd", action="store_true",
                     help="leave the optimizer step out (default: SGD(momentum 0.9, wd 1e-4) on the heads, utils/BaseModel.py:275-285, "
                          "fused into the tail of the dW kernel for the tensor-pipe workloads on one GPU)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU holds the workload's batch (global batch grows with N); strong: BASELINE.json's fixed "
+                         "global batch split over the N GPUs")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="skip the pre-timing check (N ranks == one GPU on the concatenated batch == CPU oracle on a small problem)")
     ap.add_argument("--batch", type=int, default=None, help="override the workload's per-GPU batch (experiments)")
     ap.add_argument("--dim", type=int, default=None, help="override the feature width (experiments)")
     ap.add_argument("--classes", type=int, default=None, help="override the class count (experiments)")
@@ -298,10 +304,24 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.scaling == "weak" and world > 1 and w["N"]:
+        # weak scaling grows the global batch, so the dataset the QMF History indexes grows with it (a global batch larger
+        # than the dataset would visit entries several times per step)
+        w["N"] *= world
+
+    if args.scaling == "strong" and world > 1:
+        if w["B"] % (2 * world):
+            raise SystemExit(f"--scaling strong: global batch {w['B']} is not divisible by 2 x {world} ranks")
+        w["B"] //= world
+        w["desc"] += f" [strong scaling: global batch split over {world} GPUs]"
 
     if args.impl == "reference":
         run_reference(args, w, rank, world)
         return
+
+    # CPU baseline first, on rank 0, while the other ranks wait in the (host-side) rendezvous below: nothing spins
+    # on a GPU meanwhile and the host cores are not shared with the timed region
+    cpu_line = cpu_baseline(w) if (rank == 0 and not args.no_cpu_baseline) else None
 
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -314,8 +334,19 @@ def main():
     eng = LateFusionStep(w["C"], mode=w["mode"], n_data=w["N"], device=dev, precision=args.precision)
     W, b = head_params(w)
     W = [x.to(dev) for x in W]; b = [x.to(dev) for x in b]
-    fused_sgd = (not args.no_sgd) and args.precision != "fp32" and w["C"] >= 32 and world == 1
+    # SGD on the heads inside the step: in the tail of the dW kernel, after the gradient all-reduce on several GPUs
+    fused_sgd = (not args.no_sgd) and args.precision != "fp32" and w["C"] >= 32
     args.fused_sgd = fused_sgd
+    parity = None
+    if not args.no_parity_check:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import parity_multigpu
+        parity = parity_multigpu.run(w, args.precision, dev, rank, world, fused_sgd)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"parity_check": parity, "error": "parity check failed: nothing was timed"}), flush=True)
+            torch.cuda.synchronize()
+            os._exit(3)
     if fused_sgd:
         eng.enable_sgd(lr=1e-3, momentum=0.9, weight_decay=1.0e-4)
     fe = 2 if args.precision == "bf16" else 4
@@ -487,7 +518,7 @@ def main():
         step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
         line = {"metric": "fusion_step_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
+                "scaling": args.scaling, "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
                 "data": "synthetic", "config": workload_config(w, args, world),
                 "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
@@ -495,8 +526,10 @@ def main():
                                   "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak},
                 "kernels": {k: {"launches": v["launches"], "avg_us": round(v["avg_us"], 2), "share": round(v["share"], 4)}
                             for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["share"])}}
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(w)
+        if cpu_line is not None:
+            line["cpu_baseline"] = cpu_line
+        if parity is not None:
+            line["parity_check"] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
         # captured graphs hold NCCL work: drop them and drain the device before leaving; skip

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 9
+#define LF_ABI_VERSION 10
 
 /* error codes */
 #define LF_OK 0
@@ -125,11 +125,26 @@ typedef struct LfHeadsArgs {
                                  (lf_cast_heads_bf16 after an optimizer step, or LfSgdFused.weight_bf16_out).  NULL:
                                  lf_heads_forward casts the heads itself on every call, like autocast does */
   const LfSgdFused* sgd;      /* optional (host pointer): fused SGD update in lf_heads_backward, see LfSgdFused */
+  const struct LfPeerComm* grad_comm; /* optional (host pointer), sharded steps: lf_heads_backward all-reduces
+                                 [dW1|dW2|db1|db2|calibrated counts|ranking-loss partial] over peer memory INSIDE the tail of
+                                 the dW kernel (every CTA stores the chunk it has reduced into all peers' receive slots and
+                                 polls the same chunk of every rank against the sentinel -- no fence, flag or barrier -- then
+                                 sums in rank order), so dweight / dbias / stats come back as global sums and the fused SGD
+                                 step may follow.  Only honoured when lf_heads_backward_fuses_allreduce() says so. */
+  const float* reg_partial;   /* with grad_comm, QMF: this rank's ranking-loss partial (LfMidArgs.reg_partial_out) */
+  float* loss_out;            /* with grad_comm, QMF: the loss lf_step_mid wrote without the ranking term; the term is added here */
   uint64_t* stats_rows_out;   /* optional (HOST pointer to 2 words): when the forward leaves its statistics as per-CTA
                                  partial rows (the fused tensor-pipe forward), lf_heads_forward skips the launch that sums
                                  them into `stats` and returns {device pointer of the float rows, number of rows} here for
                                  LfMidArgs.stats_rows; otherwise it writes {0, 0} and `stats` holds the sums as usual */
 } LfHeadsArgs;
+
+/* 1 when lf_heads_backward(args) would run the gradient all-reduce inside the dW kernel (tensor-pipe heads whose dW
+   tiles fit one wave), i.e. when LfHeadsArgs.grad_comm is honoured; 0: the caller exchanges dweight / dbias itself. */
+int lf_heads_backward_fuses_allreduce(const LfHeadsArgs* args);
+
+/* Floats per rank slot LfPeerComm.recv_grad must provide for that fused all-reduce ([dW1|dW2|db1|db2|cal x2|reg], 16-byte padded). */
+size_t lf_grad_exchange_floats(int32_t dim, int32_t classes);
 
 /* bf16 copies of two (n_each)-element fp32 tensors: out16 = [bf16(w0) | bf16(w1)] (the cast autocast does per step). */
 int lf_cast_heads_bf16(const float* w0, const float* w1, void* out16, size_t n_each, void* stream);
@@ -214,12 +229,16 @@ int lf_qmf_history_step(const LfQmfArgs* args, void* stream);
  * All pointers below are device pointers valid on THIS rank; index r addresses rank r's buffer.
  */
 #define LF_MAX_RANKS 8
+#define LF_PEER_FLAGS_BYTES (2 * LF_MAX_RANKS * 8)
 typedef struct LfPeerComm {
   int32_t n_ranks;
   int32_t rank;
-  void* flags[LF_MAX_RANKS];        /* rank r's flag array: 2 sets x LF_MAX_RANKS int64 (set 0 payload, set 1 gradients) */
-  void* recv_payload[LF_MAX_RANKS]; /* rank r's payload receive area: [2 parities][n_ranks][payload bytes] */
-  void* recv_grad[LF_MAX_RANKS];    /* rank r's gradient receive area: [2 parities][n_ranks][n_padded floats] */
+  void* flags[LF_MAX_RANKS];        /* rank r's flag array, LF_PEER_FLAGS_BYTES: 2 sets x LF_MAX_RANKS int64 (set 1: the stand-alone
+                                       lf_peer_allreduce; the exchanges fused into lf_step_mid and the dW kernel need no flags) */
+  void* recv_payload[LF_MAX_RANKS]; /* rank r's payload receive area: [2 parities][n_ranks][payload bytes]; filled with 0xFF bytes by
+                                       the caller once (lf_comm_fill): the exchanges validate every word against that sentinel
+                                       and re-arm the slots themselves */
+  void* recv_grad[LF_MAX_RANKS];    /* rank r's gradient receive area: [2 parities][n_ranks][n_padded floats]; 0xFF-filled likewise */
   int64_t* epoch;                   /* local, device-resident: epoch[0] payload exchanges done, epoch[1] gradient exchanges */
   int32_t* error;                   /* device-visible (ideally pinned host) flag: set to 1 right before the kernel traps
                                        because a peer did not arrive within minutes */
@@ -236,6 +255,7 @@ typedef struct LfPeerReduceArgs {
 } LfPeerReduceArgs;
 
 int lf_comm_alloc(size_t bytes, void** ptr);                 /* cudaMalloc + zero fill (host call) */
+int lf_comm_fill(void* ptr, int32_t byte_value, size_t bytes); /* cudaMemset + sync (host call): the receive areas start as 0xFF */
 int lf_comm_free(void* ptr);
 int lf_comm_ipc_handle(void* ptr, void* handle64);           /* 64-byte CUDA IPC handle of an lf_comm_alloc buffer */
 int lf_comm_ipc_open(const void* handle64, void** ptr);      /* map a peer's buffer (enables peer access lazily) */
@@ -279,7 +299,8 @@ typedef struct LfMidArgs {
   int64_t step_base;       /* QMF: as in LfQmfArgs; 0 = device-resident counter at last_writer[N] (graph-replayable) */
   float* qmf_g;            /* QMF out (2, batch_local) dL_reg/dconf of this rank's samples, or NULL (forward only) */
   float* loss_out;         /* out (1) total loss, or NULL */
-  void* workspace;         /* QMF: >= lf_mid_workspace_bytes(batch_global) */
+  void* workspace;         /* QMF: >= lf_mid_workspace_bytes(batch_global), ZERO-INITIALISED once by the caller (holds an
+                              inter-CTA arrival counter that every launch leaves at zero) */
   size_t workspace_bytes;
   /* optional fused exchange: when use_peer != 0 the kernel first pushes this rank's payload (payload_bytes,
      multiple of 16, laid out [stats | idx | conf] like the gathered buffer) into every peer's receive area and
@@ -292,6 +313,12 @@ typedef struct LfMidArgs {
   int64_t off_idx;
   int64_t off_conf;
   LfPeerComm comm;
+  float* reg_partial_out;    /* optional, QMF sharded steps: the ranking terms are evaluated for this rank's slice only and
+                                their sum is written here (a later exchange adds the ranks' partials, LfHeadsArgs.reg_partial);
+                                stats[LF_STAT_REG_SUM] is left alone and loss_out gets the loss WITHOUT the ranking term.
+                                NULL: every rank walks the pairs of the whole global batch itself */
+  const int64_t* payload_idx_src; /* optional with use_peer: the idx part of the payload is pushed from here (the caller's
+                                index tensor) instead of payload_local + off_idx */
   const float* stats_rows;   /* optional, n_ranks == 1 only: per-CTA partial rows [n_stats_rows][LF_STATS_HEADER + 2C] of the */
   int64_t n_stats_rows;      /* forward (LfHeadsArgs.stats_rows_out); summed in row order instead of reading stats_parts */
 } LfMidArgs;

@@ -28,6 +28,16 @@ class LfSgdFused(C.Structure):
     _fields_ = [("hyper", C.c_void_p), ("momentum_buf", C.c_void_p * 4), ("weight_bf16_out", _P2)]
 
 
+LF_MAX_RANKS = 8
+LF_PEER_FLAGS_BYTES = 2 * LF_MAX_RANKS * 8
+_P8 = C.c_void_p * LF_MAX_RANKS
+
+
+class LfPeerComm(C.Structure):
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("flags", _P8), ("recv_payload", _P8), ("recv_grad", _P8),
+                ("epoch", C.c_void_p), ("error", C.c_void_p)]
+
+
 class LfHeadsArgs(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("batch_global", C.c_int32), ("dim", C.c_int32), ("classes", C.c_int32),
@@ -37,7 +47,9 @@ class LfHeadsArgs(C.Structure):
         ("dlogits", _P2), ("dfeat", _P2), ("dweight", _P2), ("dbias", _P2),
         ("qmf_g", C.c_void_p), ("ema_offset", C.c_void_p), ("stats", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("fwd_only", C.c_int32), ("bwd_phase", C.c_int32), ("ld_logits", C.c_int32), ("ld_fused", C.c_int32), ("loss_terms", C.c_int32), ("reserved3", C.c_int32),
-        ("weight_bf16", _P2), ("sgd", C.POINTER(LfSgdFused)), ("stats_rows_out", C.POINTER(C.c_uint64)),
+        ("weight_bf16", _P2), ("sgd", C.POINTER(LfSgdFused)),
+        ("grad_comm", C.POINTER(LfPeerComm)), ("reg_partial", C.c_void_p), ("loss_out", C.c_void_p),
+        ("stats_rows_out", C.POINTER(C.c_uint64)),
     ]
 
 
@@ -50,15 +62,6 @@ class LfQmfArgs(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("flags", C.c_int32), ("reserved", C.c_int32), ("loss_uni", _P2),
     ]
-
-
-LF_MAX_RANKS = 8
-_P8 = C.c_void_p * LF_MAX_RANKS
-
-
-class LfPeerComm(C.Structure):
-    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("flags", _P8), ("recv_payload", _P8), ("recv_grad", _P8),
-                ("epoch", C.c_void_p), ("error", C.c_void_p)]
 
 
 class LfPeerReduceArgs(C.Structure):
@@ -77,6 +80,7 @@ class LfMidArgs(C.Structure):
         ("qmf_g", C.c_void_p), ("loss_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("use_peer", C.c_int32), ("loss_terms", C.c_int32), ("payload_local", C.c_void_p), ("payload_bytes", C.c_int64),
         ("off_idx", C.c_int64), ("off_conf", C.c_int64), ("comm", LfPeerComm),
+        ("reg_partial_out", C.c_void_p), ("payload_idx_src", C.c_void_p),
         ("stats_rows", C.c_void_p), ("n_stats_rows", C.c_int64),
     ]
 
@@ -100,6 +104,8 @@ SIGNATURES = {
     "lf_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "lf_heads_forward": (C.c_int, [C.POINTER(LfHeadsArgs), C.c_void_p]),
     "lf_heads_backward": (C.c_int, [C.POINTER(LfHeadsArgs), C.c_void_p]),
+    "lf_heads_backward_fuses_allreduce": (C.c_int, [C.POINTER(LfHeadsArgs)]),
+    "lf_grad_exchange_floats": (C.c_size_t, [C.c_int32, C.c_int32]),
     "lf_cast_heads_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lf_loss_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "lf_ema_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
@@ -107,6 +113,7 @@ SIGNATURES = {
     "lf_qmf_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "lf_qmf_history_step": (C.c_int, [C.POINTER(LfQmfArgs), C.c_void_p]),
     "lf_comm_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "lf_comm_fill": (C.c_int, [C.c_void_p, C.c_int32, C.c_size_t]),
     "lf_comm_free": (C.c_int, [C.c_void_p]),
     "lf_comm_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lf_comm_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -150,6 +150,23 @@ static int tc_block_n(int n) {            // N tile: <= 256, multiple of 16, bal
   return div_up(div_up(n, tiles), 16) * 16;
 }
 
+// Split-K plan of the tensor-pipe dW GEMM and whether its tail (reduction of the partials, db, calibrated counts,
+// optional gradient all-reduce and SGD step) can run inside the kernel: all CTAs must be co-resident (one wave).
+static bool dw_tail_plan(const LfHeadsArgs* a, int* splits_out, int* block_n_out) {
+  const int block_n = div_up(tc_block_n(a->dim), 64) * 64;
+  // split-K so that (C tiles x D tiles x 2 modalities x splits) covers the 148 SMs about once
+  const int tiles = div_up(a->classes, 128) * div_up(a->dim, block_n) * 2;
+  int splits = 148 / tiles;                    // floor: one full wave, no second-wave tail
+  const int by_rows = div_up(a->batch, 128);
+  if (splits > by_rows) splits = by_rows;
+  if (splits > kMaxSplits) splits = kMaxSplits;
+  if (splits < 1) splits = 1;
+  if (splits_out) *splits_out = splits;
+  if (block_n_out) *block_n_out = block_n;
+  const size_t cd = (size_t)a->classes * a->dim;
+  return cd % 4 == 0 && tiles * splits <= 148 && !getenv("LF_NO_DW_TAIL");
+}
+
 static int check_heads(const LfHeadsArgs* a, bool backward) {
   if (!a) { set_error("null LfHeadsArgs"); return LF_ERR_BAD_ARG; }
   if (a->batch < 1 || a->batch_global < a->batch || a->dim < 4 || a->dim % 4 || a->classes < 1) {
@@ -311,13 +328,13 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
         float* zp[2] = {a->logits[0], a->logits[1]};
         rc = tc_heads_forward_qmf(fp, d.B, a->bias, d.elem, a->batch, a->dim, a->classes, zp, ldz, a->avg_logits, a->logits_df, ldf,
                                   a->conf, rowstat_ptr(a->workspace, a->batch, a->dim, a->classes), a->label, w.row_partials, 0,
-                                  &grid, nullptr, nullptr, s);
+                                  &grid, a->stats_rows_out ? nullptr : a->stats, w.sync, s);
         if (rc) return rc;
         // single-GPU steps hand the per-CTA rows to lf_step_mid (LfMidArgs.stats_rows), which sums them with its
         // whole grid; the exchange of a sharded step needs finished statistics, so they are summed here
-        if (a->stats_rows_out) { a->stats_rows_out[0] = (uint64_t)(uintptr_t)w.row_partials; a->stats_rows_out[1] = (uint64_t)grid; return LF_OK; }
-        finalize_forward_stats(w.row_partials, grid, a->classes, a->stats, s);
-        return check_launch("finalize_stats");
+        // (a sharded step exchanges finished statistics: there the last CTA of the forward kernel to finish sums them)
+        if (a->stats_rows_out) { a->stats_rows_out[0] = (uint64_t)(uintptr_t)w.row_partials; a->stats_rows_out[1] = (uint64_t)grid; }
+        return LF_OK;
       }
     }
     d.M = a->batch; d.N = a->classes; d.K = a->dim;
@@ -421,19 +438,17 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     for (int m = 0; m < 2; ++m) { d.A[m] = dz[m]; d.B[m] = a->feat[m]; d.bias[m] = nullptr; d.out[m] = w.dw_partials + (size_t)m * kMaxSplits * cd; }
     d.M = a->classes; d.N = a->dim; d.K = a->batch;
     d.lda = ldz; d.ldb = a->dim; d.ld_out = a->dim;
-    d.a_mn_major = 1; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 64) * 64;
-    // split-K so that (C tiles x D tiles x 2 modalities x splits) covers the 148 SMs about once or twice
-    const int tiles = div_up(a->classes, 128) * div_up(a->dim, d.block_n) * 2;
-    splits = 148 / tiles;                    // floor: one full wave, no second-wave tail
-    const int by_rows = div_up(a->batch, 128);
-    if (splits > by_rows) splits = by_rows;
-    if (splits > kMaxSplits) splits = kMaxSplits;
-    if (splits < 1) splits = 1;
+    d.a_mn_major = 1; d.b_mn_major = 1;
+    // the reduction of the split-K partials, db, the calibrated counts (and the optional all-reduce / SGD step) run in the kernel's tail
+    const bool tail = dw_tail_plan(a, &splits, &d.block_n);
     d.splits = splits; d.split_stride = (long long)cd; d.balance_m = 0; d.name = "tc_dweight";
-    // the reduction of the split-K partials, db, the calibrated counts (and the optional SGD step) run in the kernel's tail
-    const bool tail = cd % 4 == 0 && tiles * splits <= 148 && !getenv("LF_NO_DW_TAIL");
-    if (a->sgd && (!tail || a->batch_global != a->batch)) {
-      set_error("fused SGD needs the tensor-pipe dW tail on a single-GPU step (batch_global == batch)");
+    const bool peer = tail && a->grad_comm && a->batch_global != a->batch;
+    if (a->grad_comm && a->batch_global != a->batch && !peer) {
+      set_error("grad_comm given but this shape cannot fuse the all-reduce (ask lf_heads_backward_fuses_allreduce first)");
+      return LF_ERR_UNSUPPORTED;
+    }
+    if (a->sgd && (!tail || (a->batch_global != a->batch && !peer))) {
+      set_error("fused SGD needs the tensor-pipe dW tail, and on a sharded step the all-reduce fused into it (grad_comm)");
       return LF_ERR_UNSUPPORTED;
     }
     if (tail) {
@@ -442,6 +457,19 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
       t.dw[0] = a->dweight[0]; t.dw[1] = a->dweight[1]; t.n = (long long)cd;
       t.dbpart = w.db_partials; t.calpart = w.cal_partials; t.nb_db = nb_parts; t.nb_cal = nb_parts; t.C = a->classes;
       t.db[0] = a->dbias[0]; t.db[1] = a->dbias[1]; t.stats = a->stats;
+      if (peer) {
+        const LfPeerComm& c = *a->grad_comm;
+        if (c.n_ranks < 2 || c.n_ranks > LF_MAX_RANKS || c.rank < 0 || c.rank >= c.n_ranks || !c.epoch || !c.error ||
+            a->batch_global != a->batch * c.n_ranks) {
+          set_error("lf_heads_backward: bad grad_comm");
+          return LF_ERR_BAD_ARG;
+        }
+        t.peer_on = 1; t.comm = c;
+        t.n_padded = (int)lf_grad_exchange_floats(a->dim, a->classes);
+        t.reg_local = a->mode == LF_MODE_QMF ? a->reg_partial : nullptr;
+        t.loss_out = a->mode == LF_MODE_QMF ? a->loss_out : nullptr;
+        t.batch_global = a->batch_global;
+      }
       if (a->sgd) {
         t.hyper = a->sgd->hyper;
         for (int m = 0; m < 2; ++m) {
@@ -468,6 +496,18 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   if (rc) return rc;
   return finalize_db_cal(w.db_partials, nb_db, a->classes, w.cal_partials, nb_parts, a->dbias[0], a->dbias[1],
                          a->stats, s);
+}
+
+extern "C" int lf_heads_backward_fuses_allreduce(const LfHeadsArgs* a) {
+  if (!a || a->dim < 4 || a->classes < 1 || a->batch < 1) return 0;
+  if (!use_tensor_pipe(a) || use_narrow(a)) return 0;
+  return dw_tail_plan(a, nullptr, nullptr) ? 1 : 0;
+}
+
+/* floats per rank slot of LfPeerComm.recv_grad for the fused all-reduce: [dW1 | dW2 | db1 | db2 | cal x2 | reg], padded to 16 B */
+extern "C" size_t lf_grad_exchange_floats(int32_t dim, int32_t classes) {
+  if (dim < 1 || classes < 1) return 0;
+  return ((size_t)2 * classes * dim + 2 * (size_t)classes + 3 + 3) / 4 * 4;
 }
 
 extern "C" int lf_cast_heads_bf16(const float* w0, const float* w1, void* out16, size_t n_each, void* stream) {

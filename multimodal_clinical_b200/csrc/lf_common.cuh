@@ -78,6 +78,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// utils/EMA.py:33  x <- smoothing * x_new + (1 - smoothing) * x, evaluated like torch does (two products, one sum: no
+// FMA contraction), so every kernel that applies it -- and the reference -- produce the same bits
+__device__ __forceinline__ float ema_mix(float mean, float x, float beta) {
+  return __fadd_rn(__fmul_rn(beta, mean), __fmul_rn(__fsub_rn(1.0f, beta), x));
+}
+
 // relu that lets NaN through (torch.clamp_min semantics; fmaxf would swallow it)
 __device__ __forceinline__ float relu_nan(float x) { return (x > 0.f || x != x) ? x : 0.f; }
 

@@ -66,6 +66,13 @@ extern "C" int lf_comm_alloc(size_t bytes, void** ptr) {
   if (e != cudaSuccess) { set_error("lf_comm_alloc: %s", cudaGetErrorString(e)); return LF_ERR_CUDA; }
   return LF_OK;
 }
+extern "C" int lf_comm_fill(void* ptr, int32_t byte_value, size_t bytes) {
+  if (!ptr || bytes == 0) { set_error("lf_comm_fill: bad argument"); return LF_ERR_BAD_ARG; }
+  cudaError_t e = cudaMemset(ptr, byte_value, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { set_error("lf_comm_fill: %s", cudaGetErrorString(e)); return LF_ERR_CUDA; }
+  return LF_OK;
+}
 extern "C" int lf_comm_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? LF_OK : LF_ERR_CUDA; }
 extern "C" int lf_comm_ipc_handle(void* ptr, void* handle64) {
   cudaIpcMemHandle_t h;

@@ -457,8 +457,8 @@ __global__ void ema_update_kernel(float* __restrict__ x, float* __restrict__ off
   if (c >= C) return;
   const float mean1 = (float)(stats[LF_STATS_HEADER + c] / (double)Bg);
   const float mean2 = (float)(stats[LF_STATS_HEADER + C + c] / (double)Bg);
-  const float x1 = mean1 * beta + x[c] * (1.0f - beta);        // utils/EMA.py:33
-  const float x2 = mean2 * beta + x[C + c] * (1.0f - beta);
+  const float x1 = ema_mix(mean1, x[c], beta);                  // utils/EMA.py:33
+  const float x2 = ema_mix(mean2, x[C + c], beta);
   x[c] = x1; x[C + c] = x2;
   const float mu = (x1 + x2) / 2.f;                             // utils/EMA.py:38
   off[c] = mu - x1;

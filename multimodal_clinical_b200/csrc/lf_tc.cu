@@ -28,6 +28,7 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include "lf_common.cuh"
+#include "lf_peer.cuh"
 #include "lf_tc.cuh"
 #include "lf_tc_ptx.cuh"
 
@@ -61,17 +62,42 @@ __device__ __forceinline__ void gemm_tail(const TcGemmParams& p, float* s_rows) 
   __syncthreads();
   stamp(2);
   const float lr = t.hyper ? t.hyper[0] : 0.f, mom = t.hyper ? t.hyper[1] : 0.f, wd = t.hyper ? t.hyper[2] : 0.f;
-  // ---- dW: float4 i of modality m = sum over the splits, in split order; the work is spread over the whole grid
   const long long n4 = t.n / 4, total4 = 2 * n4;
   const long long per_cta = (total4 + gridDim.x - 1) / gridDim.x;
   const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < total4 ? lo + per_cta : total4;
+  const int n_entries = 2 * t.C + 2 + ((t.peer_on && t.reg_local) ? 1 : 0);      // db1, db2, calibrated counts x2, ranking-loss partial
+  const bool peer = t.peer_on != 0;
+  const long long epoch = peer ? t.comm.epoch[1] + 1 : 0;
+  const int parity = (int)(epoch & 1), G = peer ? t.comm.n_ranks : 1;
+  const size_t slot_me = ((size_t)parity * G + (peer ? t.comm.rank : 0)) * (size_t)t.n_padded;
+
+  // SGD on one float4 of head m (torch.optim.SGD: d = g + wd p; buf = mom buf + d; p -= lr buf) + the bf16 copy
+  auto sgd4 = [&](int m, long long i, const float g[4], const float4& w4, const float4& b4) {
+    const float w0[4] = {w4.x, w4.y, w4.z, w4.w}, m0[4] = {b4.x, b4.y, b4.z, b4.w};
+    float np[4], nb[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d = g[e] + wd * w0[e];
+      nb[e] = mom * m0[e] + d;
+      np[e] = w0[e] - lr * nb[e];
+    }
+    *reinterpret_cast<float4*>(t.mom_w[m] + i) = make_float4(nb[0], nb[1], nb[2], nb[3]);
+    *reinterpret_cast<float4*>(t.param_w[m] + i) = make_float4(np[0], np[1], np[2], np[3]);
+    if (t.w16[m]) {
+      const __nv_bfloat162 lo2 = __floats2bfloat162_rn(np[0], np[1]), hi2 = __floats2bfloat162_rn(np[2], np[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&lo2); u.y = *reinterpret_cast<const uint32_t*>(&hi2);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(t.w16[m]) + i) = u;
+    }
+  };
+  // ---- dW: float4 j of [dW1 | dW2] = sum over the splits, in split order; the work is spread over the whole grid
   for (long long j = lo + threadIdx.x; j < hi; j += blockDim.x) {
     const int m = j >= n4 ? 1 : 0;
     const long long i = (j - (long long)m * n4) * 4;
     const float* part = (const float*)p.out[m] + i;
     // parameter and momentum of this float4 are fetched with the partials (one round trip for everything)
     float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = w4;
-    if (t.hyper) {
+    if (t.hyper && !peer) {
       w4 = *reinterpret_cast<const float4*>(t.param_w[m] + i);
       b4 = *reinterpret_cast<const float4*>(t.mom_w[m] + i);
     }
@@ -88,52 +114,30 @@ __device__ __forceinline__ void gemm_tail(const TcGemmParams& p, float* s_rows) 
       const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (long long)k * p.split_stride));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
+    if (peer) {                           // this rank's reduced float4 -> every rank's receive area (NVLink stores)
+      s.x = clean_f32(s.x); s.y = clean_f32(s.y); s.z = clean_f32(s.z); s.w = clean_f32(s.w);
+#pragma unroll
+      for (int r = 0; r < LF_MAX_RANKS; ++r)
+        if (r < G) reinterpret_cast<float4*>((float*)t.comm.recv_grad[r] + slot_me)[j] = s;
+      continue;
+    }
     float* o = t.dw[m] + i;               // the flat gradient buffer packs dW2 after db1: not always 16-byte aligned
     const float g[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[e] = g[e];
-    if (t.hyper) {                        // torch.optim.SGD: d = g + wd p; buf = mom buf + d; p -= lr buf
-      const float w0[4] = {w4.x, w4.y, w4.z, w4.w}, m0[4] = {b4.x, b4.y, b4.z, b4.w};
-      float np[4], nb[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float d = g[e] + wd * w0[e];
-        nb[e] = mom * m0[e] + d;
-        np[e] = w0[e] - lr * nb[e];
-      }
-      *reinterpret_cast<float4*>(t.mom_w[m] + i) = make_float4(nb[0], nb[1], nb[2], nb[3]);
-      *reinterpret_cast<float4*>(t.param_w[m] + i) = make_float4(np[0], np[1], np[2], np[3]);
-      if (t.w16[m]) {
-        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(np[0], np[1]), hi2 = __floats2bfloat162_rn(np[2], np[3]);
-        uint2 u;
-        u.x = *reinterpret_cast<const uint32_t*>(&lo2); u.y = *reinterpret_cast<const uint32_t*>(&hi2);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(t.w16[m]) + i) = u;
-      }
-    }
+    if (t.hyper) sgd4(m, i, g, w4, b4);
   }
   stamp(3);
-  // ---- db and the calibrated counts: column sums of the per-CTA partials of the kernel that produced dz.  One output
-  // per CTA and pass: every thread fetches one partial row (a single memory round trip), thread 0 adds them in row order
-  for (int i = blockIdx.x; i < 2 * t.C + 2; i += gridDim.x) {
-    const bool is_db = i < 2 * t.C;
-    const float* src = is_db ? t.dbpart + i : t.calpart + (i - 2 * t.C);
-    const int pitch = is_db ? 2 * t.C : 2, nb = is_db ? t.nb_db : t.nb_cal;
-    double s = 0.0;
-    for (int b0 = 0; b0 < nb; b0 += 384) {
-      __syncthreads();
-      for (int b = threadIdx.x; b < 384 && b0 + b < nb; b += blockDim.x) s_rows[b] = src[(size_t)(b0 + b) * pitch];
-      __syncthreads();
-      if (threadIdx.x < 32) {
-        // lane l adds rows l, l + 32, ... in order, then a fixed xor butterfly: the same order on every launch
-        double q = 0.0;
-        for (int b = threadIdx.x; b < 384 && b0 + b < nb; b += 32) q += (double)s_rows[b];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        s += q;
-      }
+  // ---- db, the calibrated counts (and the ranking-loss partial of a sharded QMF step): column sums of the per-CTA
+  // partials of the kernel that produced dz.  One output per CTA and pass: every thread fetches one partial row (a
+  // single memory round trip), warp 0 adds them in a fixed order
+  auto finish_entry = [&](int i, double s) {          // thread 0: final value of entry i
+    if (i >= 2 * t.C + 2) {                            // ranking loss: sum of the ranks' slices
+      t.stats[LF_STAT_REG_SUM] = s;
+      if (t.loss_out) t.loss_out[0] = t.loss_out[0] + (float)(s / (double)t.batch_global);
+      return;
     }
-    if (threadIdx.x != 0) continue;
-    if (!is_db) { t.stats[LF_STAT_CNT_X1_CAL + (i - 2 * t.C)] = s; continue; }
+    if (i >= 2 * t.C) { t.stats[LF_STAT_CNT_X1_CAL + (i - 2 * t.C)] = s; return; }
     const int m = i >= t.C ? 1 : 0, c = i - m * t.C;
     const float g = (float)s;
     t.db[m][c] = g;
@@ -144,12 +148,109 @@ __device__ __forceinline__ void gemm_tail(const TcGemmParams& p, float* s_rows) 
       t.mom_b[m][c] = bb;
       t.param_b[m][c] = w0 - lr * bb;
     }
+  };
+  for (int i = blockIdx.x; i < n_entries; i += gridDim.x) {
+    double s = 0.0;
+    if (i >= 2 * t.C + 2) {
+      s = (double)t.reg_local[0];
+    } else {
+      const bool is_db = i < 2 * t.C;
+      const float* src = is_db ? t.dbpart + i : t.calpart + (i - 2 * t.C);
+      const int pitch = is_db ? 2 * t.C : 2, nb = is_db ? t.nb_db : t.nb_cal;
+      for (int b0 = 0; b0 < nb; b0 += 384) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < 384 && b0 + b < nb; b += blockDim.x) s_rows[b] = src[(size_t)(b0 + b) * pitch];
+        __syncthreads();
+        if (threadIdx.x < 32) {
+          // lane l adds rows l, l + 32, ... in order, then a fixed xor butterfly: the same order on every launch
+          double q = 0.0;
+          for (int b = threadIdx.x; b < 384 && b0 + b < nb; b += 32) q += (double)s_rows[b];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+          s += q;
+        }
+      }
+    }
+    if (threadIdx.x != 0) continue;
+    if (peer) {
+#pragma unroll
+      for (int r = 0; r < LF_MAX_RANKS; ++r)
+        if (r < G) ((float*)t.comm.recv_grad[r] + slot_me)[4 * total4 + i] = clean_f32((float)s);
+    } else {
+      finish_entry(i, s);
+    }
+  }
+  if (peer) {
+    // ---- no fence, no flag: the receive slots were armed with the sentinel, every word read below validates itself
+    // (lf_peer.cuh).  Sum of the ranks' chunks in rank order from LOCAL memory (bit-identical on every rank), the slot
+    // is re-armed for epoch + 2, then the optimizer.
+    stamp(5);
+    float* rbase = (float*)t.comm.recv_grad[t.comm.rank] + (size_t)parity * G * (size_t)t.n_padded;
+    const uint4 ones = make_uint4(kSentinel32, kSentinel32, kSentinel32, kSentinel32);
+    for (long long j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+      const int m = j >= n4 ? 1 : 0;
+      const long long i = (j - (long long)m * n4) * 4;
+      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = w4;
+      if (t.hyper) {
+        w4 = *reinterpret_cast<const float4*>(t.param_w[m] + i);
+        b4 = *reinterpret_cast<const float4*>(t.mom_w[m] + i);
+      }
+      uint4 v[LF_MAX_RANKS];
+      bool ok[LF_MAX_RANKS];
+#pragma unroll
+      for (int r = 0; r < LF_MAX_RANKS; ++r) ok[r] = r >= G;
+      PeerSpin spin;
+      for (;;) {
+#pragma unroll
+        for (int r = 0; r < LF_MAX_RANKS; ++r)          // every missing rank's load in flight together
+          if (!ok[r]) v[r] = ld_volatile_u4(reinterpret_cast<const uint4*>(rbase + (size_t)r * t.n_padded) + j);
+        bool all = true;
+#pragma unroll
+        for (int r = 0; r < LF_MAX_RANKS; ++r) {
+          if (!ok[r]) ok[r] = v[r].x != kSentinel32 && v[r].y != kSentinel32 && v[r].z != kSentinel32 && v[r].w != kSentinel32;
+          all = all && ok[r];
+        }
+        if (all) break;
+        spin.wait(t.comm.error);
+      }
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < LF_MAX_RANKS; ++r)
+        if (r < G) {
+          s.x += __uint_as_float(v[r].x); s.y += __uint_as_float(v[r].y); s.z += __uint_as_float(v[r].z); s.w += __uint_as_float(v[r].w);
+          reinterpret_cast<uint4*>(rbase + (size_t)r * t.n_padded)[j] = ones;
+        }
+      float* o = t.dw[m] + i;
+      const float g[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = g[e];
+      if (t.hyper) sgd4(m, i, g, w4, b4);
+    }
+    stamp(6);
+    if (threadIdx.x == 0)
+      for (int i = blockIdx.x; i < n_entries; i += gridDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < G; ++r) {
+          unsigned* q = reinterpret_cast<unsigned*>(rbase + (size_t)r * t.n_padded + 4 * total4 + i);
+          unsigned u = ld_volatile_u32(q);
+          PeerSpin spin;
+          while (u == kSentinel32) { spin.wait(t.comm.error); u = ld_volatile_u32(q); }
+          s += (double)__uint_as_float(u);
+          *q = kSentinel32;
+        }
+        finish_entry(i, s);
+      }
+    stamp(7);
   }
   // ---- leave the counters zero for the next launch: the last CTA to depart resets them
   __syncthreads();
   stamp(4);
   if (threadIdx.x == 0) {
-    if (atomicAdd(&t.sync[1], 1u) == gridDim.x - 1) { t.sync[0] = 0u; t.sync[1] = 0u; __threadfence(); }
+    if (atomicAdd(&t.sync[1], 1u) == gridDim.x - 1) {
+      t.sync[0] = 0u; t.sync[1] = 0u;
+      if (peer) t.comm.epoch[1] = epoch;
+      __threadfence();
+    }
   }
 }
 
@@ -576,8 +677,9 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
       cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
       unsigned long long t0 = ~0ull;
       for (int c = 0; c < grid; ++c) if (h[c * 8] < t0) t0 = h[c * 8];
-      const char* nm[5] = {"entry", "gemm_done", "barrier_done", "dw_reduced", "db_done"};
-      for (int k = 0; k < 5; ++k) {
+      const char* nm[8] = {"entry", "gemm_done", "barrier_done", "dw_reduced", "end", "entries_pushed", "chunks_summed", "entries_summed"};
+      for (int k = 0; k < 8; ++k) {
+        if (k >= 5 && !p.tail.peer_on) break;
         double mn = 1e30, mx = 0, sum = 0;
         for (int c = 0; c < grid; ++c) { const double v = (double)(h[c * 8 + k] - t0) / 1000.0; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; }
         fprintf(stderr, "[dw trace] %-13s min %7.2f  avg %7.2f  max %7.2f us\n", nm[k], mn, sum / grid, mx);

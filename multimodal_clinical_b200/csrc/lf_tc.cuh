@@ -1,6 +1,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "../../include/lf_fusion.h"
 
 namespace lf {
 
@@ -24,6 +25,17 @@ struct TcTail {
   float* mom_b[2];
   void* w16[2];              // optional bf16 copies of the updated weights
   unsigned long long* trace; // LF_DW_TRACE=1: [grid][8] %globaltimer stamps
+  // Sharded steps: the gradient all-reduce runs in here.  Every CTA stores the chunk it has just reduced into slot
+  // [parity][rank] of every rank's receive area (layout [dW1 | dW2 | db1 | db2 | cal x2 | reg], n_padded floats) and then
+  // polls the same chunk of every rank in its LOCAL receive area against the sentinel the slots are armed with
+  // (lf_peer.cuh: no fence, flag or barrier; the ranks run the same grid over the same chunks), sums the ranks' chunks
+  // in rank order and re-arms the slot.
+  int peer_on;
+  LfPeerComm comm;
+  int n_padded;
+  const float* reg_local;    // QMF: this rank's ranking-loss partial (lf_step_mid), or null
+  float* loss_out;           // QMF: loss without the ranking term; the all-reduced term / batch_global is added
+  int batch_global;
 };
 
 // Device-side parameters of the persistent tc_gemm_kernel.

@@ -59,7 +59,7 @@ class _QmfState:
     def mid_workspace(self, batch_global: int) -> torch.Tensor:
         need = _lib.load().lf_mid_workspace_bytes(int(batch_global))
         if self.mid_ws is None or self.mid_ws.numel() < need:
-            self.mid_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self.mid_ws = torch.zeros(need, dtype=torch.uint8, device=self.device)    # holds a counter the kernel leaves at zero
         return self.mid_ws
 
     def run(self, idx: torch.Tensor, conf: torch.Tensor, flags: int, loss_uni=(None, None),

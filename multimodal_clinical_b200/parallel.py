@@ -86,14 +86,16 @@ class PeerComm:
             raise _lib.LfError(f"PeerComm supports up to {_lib.LF_MAX_RANKS} ranks on one NVSwitch domain")
         self.payload_bytes = (payload_bytes + 15) // 16 * 16
         self.grad_padded = (grad_floats + 3) // 4 * 4
-        flags_bytes = 2 * _lib.LF_MAX_RANKS * 8
-        self.off_payload = 256
+        flags_bytes = _lib.LF_PEER_FLAGS_BYTES            # two barrier sets (stand-alone lf_peer_allreduce)
+        self.off_payload = (flags_bytes + 255) // 256 * 256
         self.off_grad = self.off_payload + (2 * self.world * self.payload_bytes + 255) // 256 * 256
         total = self.off_grad + 2 * self.world * self.grad_padded * 4
         assert flags_bytes <= self.off_payload
         base = C.c_void_p()
         _lib.check(lib.lf_comm_alloc(total, C.byref(base)), "lf_comm_alloc")
         self.local = base.value
+        # receive areas start armed with the all-ones sentinel of the flag-less exchanges (csrc/lf_peer.cuh); flags stay zero
+        _lib.check(lib.lf_comm_fill(self.local + self.off_payload, 0xFF, total - self.off_payload), "lf_comm_fill")
         handle = C.create_string_buffer(64)
         _lib.check(lib.lf_comm_ipc_handle(self.local, handle), "lf_comm_ipc_handle")
         handles = [None] * self.world

@@ -329,11 +329,12 @@ class LateFusionStep:
             if idx is None:
                 raise ValueError("QMF step needs the dataset indices of the batch (idx)")
             idx = idx.reshape(-1)
-            if self.world == 1:
-                # one GPU: nothing is exchanged, step_mid reads the caller's indices in place (no copy kernel)
-                idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
-                self._idx_keep = idx
-            else:
+            # step_mid reads the caller's indices in place (one GPU) or pushes them to the peers from where they are
+            # (peer exchange): no staging copy kernel in the step.  Only the NCCL all-gather needs them in the payload.
+            idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
+            self._idx_keep = idx
+            idx_in_place = self.world == 1 or (self.comm_mode != "nccl" and B % 2 == 0 and idx.data_ptr() % 16 == 0)
+            if not idx_in_place:
                 p_idx.copy_(idx)
 
         a = LfHeadsArgs()
@@ -360,8 +361,15 @@ class LateFusionStep:
         w16 = self._heads_bf16(W)
         if w16 is not None:
             a.weight_bf16[0], a.weight_bf16[1] = w16
+        # sharded steps: the peer-memory communicator (None: NCCL collectives) and whether the gradient all-reduce can run
+        # inside the dW kernel (tensor-pipe heads), in which case the fused SGD step may follow it there
+        peer = self._peer_comm(pay.numel(), max(gf.numel(), int(lib.lf_grad_exchange_floats(D, Cn)))) if self.world > 1 else None
+        fuse_ar = peer is not None and backward and bool(lib.lf_heads_backward_fuses_allreduce(C.byref(a)))
         sgd = None
-        if self._sgd is not None and backward and self.world == 1:
+        if self._sgd is not None and backward and self.world > 1 and not fuse_ar:
+            raise _lib.LfError("the fused SGD step of a sharded run follows the gradient all-reduce inside the dW kernel: it needs the "
+                               "peer-memory communicator (comm='auto' / 'peer') and tensor-pipe heads")
+        if self._sgd is not None and backward:
             if W[0] is not weights[0] or W[1] is not weights[1] or bb[0] is not biases[0] or bb[1] is not biases[1]:
                 raise _lib.LfError("the fused SGD step updates the head tensors in place: pass contiguous fp32 CUDA tensors")
             key = (W[0].data_ptr(), bb[0].data_ptr(), W[1].data_ptr(), bb[1].data_ptr())
@@ -380,7 +388,6 @@ class LateFusionStep:
         if self.world == 1:
             a.stats_rows_out = rows_out       # one GPU: lf_step_mid sums the forward's per-CTA rows itself
         check(lib.lf_heads_forward(C.byref(a), st), "lf_heads_forward")
-        peer = self._peer_comm(pay.numel(), gf.numel())
         if peer is not None:
             peer.check()                                          # pinned host flag: no synchronisation
         stride = pay.numel()
@@ -391,7 +398,11 @@ class LateFusionStep:
             mid.off_idx, mid.off_conf = self._off_idx, self._off_conf
             peer.fill(mid.comm)
             gathered = pay
+            if qmf and idx_in_place:
+                mid.payload_idx_src = idx.data_ptr()
         else:
+            if qmf and idx_in_place and self.world > 1:
+                p_idx.copy_(idx)                                  # fell back to NCCL after all (no peer mapping)
             gathered = parallel.gather_payload(pay, self.pg)      # (world, payload bytes); identity on one GPU
         mid.mode, mid.classes, mid.batch_global, mid.n_ranks = self.mode, Cn, Bg, self.world
         mid.batch_local, mid.rank, mid.n_data, mid.update_ema = B, self.rank, self.n_data or 0, int(update_ema)
@@ -414,6 +425,11 @@ class LateFusionStep:
             mid.alpha, mid.coeff_out = float(ogm_alpha), _ptr(self.coeff)
         mid.loss_out = _ptr(self.loss)
         mid.loss_terms = self.loss_terms
+        if fuse_ar and qmf:
+            # ranking terms of this rank's slice only; the partial sums ride in the gradient all-reduce
+            if getattr(self, "_reg_partial", None) is None:
+                self._reg_partial = torch.zeros(4, device=self.device)
+            mid.reg_partial_out = _ptr(self._reg_partial)
         check(lib.lf_step_mid(C.byref(mid), st), "lf_step_mid")
         if update_ema:
             self.ema_counter += 1
@@ -422,6 +438,15 @@ class LateFusionStep:
         if backward:
             a.stats = _ptr(self.stats)                            # calibrated counts join the GLOBAL statistics
             if self.world == 1:
+                check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
+            elif fuse_ar:
+                # ONE launch sequence: the all-reduce of [dW|db|calibrated counts|ranking-loss partial] (and the SGD step)
+                # run in the tail of the dW kernel over peer memory
+                gcomm = _lib.LfPeerComm()
+                peer.fill(gcomm)
+                a.grad_comm = C.pointer(gcomm)
+                if qmf:
+                    a.reg_partial, a.loss_out = _ptr(self._reg_partial), _ptr(self.loss)
                 check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
             else:
                 # dW / db first, then their exchange on a side stream while dfeat (which no other rank needs) is

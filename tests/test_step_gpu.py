@@ -99,7 +99,7 @@ def test_step_mid_matches_the_separate_entry_points():
         m.alpha, m.coeff_out = 0.8, b["coeff"].data_ptr()
         m.correctness, m.confidence, m.last_writer, m.step_base = b["corr"].data_ptr(), b["confid"].data_ptr(), b["lw"].data_ptr(), 0
         m.qmf_g, m.loss_out = b["qmf_g"].data_ptr(), b["loss"].data_ptr()
-        ws2 = torch.empty(lib.lf_mid_workspace_bytes(B), dtype=torch.uint8, device="cuda")
+        ws2 = torch.zeros(lib.lf_mid_workspace_bytes(B), dtype=torch.uint8, device="cuda")     # zero-initialised once (header contract)
         m.workspace, m.workspace_bytes = ws2.data_ptr(), ws2.numel()
         _lib.check(lib.lf_step_mid(C.byref(m), st), "mid")
         torch.cuda.synchronize()

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r2g_tests.log
+LF_MID_TRACE=1 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-graph --no-parity-check > gpurun_out/r2g_trace.json 2> gpurun_out/r2g_trace.err
+timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r2g_k4_n1.json 2> gpurun_out/r2g_k4_n1.err
+timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --workload k2 > gpurun_out/r2g_k2_n1.json 2> gpurun_out/r2g_k2_n1.err
+echo done
