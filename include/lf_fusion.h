@@ -136,7 +136,8 @@ typedef struct LfHeadsArgs {
   uint64_t* stats_rows_out;   /* optional (HOST pointer to 2 words): when the forward leaves its statistics as per-CTA
                                  partial rows (the fused tensor-pipe forward), lf_heads_forward skips the launch that sums
                                  them into `stats` and returns {device pointer of the float rows, number of rows} here for
-                                 LfMidArgs.stats_rows; otherwise it writes {0, 0} and `stats` holds the sums as usual */
+                                 LfMidArgs.stats_rows; otherwise it writes {0, 0} and `stats` holds the sums as usual.  NULL: the
+                                 forward always finishes the sums itself (what an NCCL all-gather of the statistics needs) */
 } LfHeadsArgs;
 
 /* 1 when lf_heads_backward(args) would run the gradient all-reduce inside the dW kernel (tensor-pipe heads whose dW
@@ -319,8 +320,9 @@ typedef struct LfMidArgs {
                                 NULL: every rank walks the pairs of the whole global batch itself */
   const int64_t* payload_idx_src; /* optional with use_peer: the idx part of the payload is pushed from here (the caller's
                                 index tensor) instead of payload_local + off_idx */
-  const float* stats_rows;   /* optional, n_ranks == 1 only: per-CTA partial rows [n_stats_rows][LF_STATS_HEADER + 2C] of the */
-  int64_t n_stats_rows;      /* forward (LfHeadsArgs.stats_rows_out); summed in row order instead of reading stats_parts */
+  const float* stats_rows;   /* optional (QMF; one rank, or use_peer): per-CTA partial rows [n_stats_rows][LF_STATS_HEADER + 2C] of THIS */
+  int64_t n_stats_rows;      /* rank's forward (LfHeadsArgs.stats_rows_out), summed in row order instead of reading stats_parts;
+                                with use_peer the ranks' column sums are exchanged inside the kernel and added in rank order */
 } LfMidArgs;
 
 size_t lf_mid_workspace_bytes(int32_t batch_global);

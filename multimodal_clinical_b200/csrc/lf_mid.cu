@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_kernel(MidParams p) {
     const int parity = (int)(epoch & 1);
     const size_t slot = ((size_t)parity * a.n_ranks + a.rank) * (size_t)a.payload_bytes;
     const double* st_src = (const double*)a.payload_local;
-    for (int c = tid; c < len; c += nthr) {
+    // (with stats_rows the statistics are exchanged as column sums further down, by the CTA that owns the column)
+    for (int c = a.stats_rows ? len : tid; c < len; c += nthr) {
       const double v = clean_f64(st_src[c]);
 #pragma unroll 1
       for (int r = 0; r < a.n_ranks; ++r) reinterpret_cast<double*>((char*)a.comm.recv_payload[r] + slot)[c] = v;
@@ -236,14 +237,17 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_kernel(MidParams p) {
   // statistic c of row r: the forward's per-CTA partial rows (one GPU), the ranks' finished statistics polled from the
   // receive area (peer exchange) or read from the gathered buffer (NCCL)
   const int nrow = a.stats_rows ? (int)a.n_stats_rows : a.n_ranks;
-  auto stat_at = [&](int r, int c) -> double {
-    if (a.stats_rows) return (double)a.stats_rows[(size_t)r * len + c];
-    if (!rec_base) return a.stats_parts[(size_t)r * a.stats_stride + c];
+  auto stat_polled = [&](int r, int c) -> double {       // statistic c of rank r from the receive area
     const void* q = rec_base + (size_t)r * a.payload_bytes + (size_t)c * 8;
     unsigned long long v = ld_volatile_u64(q);
     PeerSpin spin;
     while (v == kSentinel64) { spin.wait(a.comm.error); v = ld_volatile_u64(q); }
     return __longlong_as_double((long long)v);
+  };
+  auto stat_at = [&](int r, int c) -> double {
+    if (a.stats_rows) return (double)a.stats_rows[(size_t)r * len + c];
+    if (!rec_base) return a.stats_parts[(size_t)r * a.stats_stride + c];
+    return stat_polled(r, c);
   };
   // re-arm this epoch's receive slots once everything has been read (grid-strided; local stores)
   auto rearm = [&]() {
@@ -361,7 +365,26 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_kernel(MidParams p) {
         }
         __syncthreads();
       }
-      if (warp == 0 && lane < kMidCols) s_col[lane] = acc;
+      if (warp == 0 && lane < kMidCols) {
+        if (a.stats_rows && rec_base && s_cols[lane] >= 0) {
+          // sharded step fed with the forward's per-CTA rows: `acc` is this RANK's sum of the column.  The CTA that owns
+          // a column (CTA 0 for the CE sums) stores it into every rank's receive slot; everybody who needs the column
+          // polls the ranks' values and adds them in rank order
+          const int col = s_cols[lane];
+          const bool ce = first && lane < 3;
+          if (!ce || cta == 0) {
+            const size_t slot = ((size_t)(epoch & 1) * a.n_ranks + a.rank) * (size_t)a.payload_bytes;
+            const double v = clean_f64(acc);
+#pragma unroll 1
+            for (int r = 0; r < a.n_ranks; ++r) reinterpret_cast<double*>((char*)a.comm.recv_payload[r] + slot)[col] = v;
+          }
+          double t = 0.0;
+#pragma unroll 1
+          for (int r = 0; r < a.n_ranks; ++r) t += stat_polled(r, col);
+          acc = t;
+        }
+        s_col[lane] = acc;
+      }
       __syncthreads();
       if (score_pass) {
         if (threadIdx.x == 0) ogm_coeff_write(a, (float)s_col[0], (float)s_col[1]);
@@ -580,8 +603,8 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
     set_error("lf_step_mid: bad peer-exchange arguments");
     return LF_ERR_BAD_ARG;
   }
-  if (a && a->stats_rows && (a->n_ranks != 1 || a->use_peer || a->n_stats_rows < 1)) {
-    set_error("lf_step_mid: stats_rows is a single-GPU input (n_ranks == 1, no peer exchange)");
+  if (a && a->stats_rows && ((a->n_ranks != 1 && !a->use_peer) || a->n_stats_rows < 1 || a->mode != LF_MODE_QMF)) {
+    set_error("lf_step_mid: stats_rows (QMF) needs one rank or the peer exchange (the column sums are exchanged in the kernel)");
     return LF_ERR_BAD_ARG;
   }
   if (!a || (!a->stats_parts && !a->use_peer && !a->stats_rows) || !a->stats || a->classes < 1 || a->batch_global < 1 || a->n_ranks < 1 ||

@@ -385,8 +385,9 @@ class LateFusionStep:
             a.sgd = C.pointer(sgd)
 
         rows_out = (C.c_uint64 * 2)(0, 0)
-        if self.world == 1:
-            a.stats_rows_out = rows_out       # one GPU: lf_step_mid sums the forward's per-CTA rows itself
+        if self.world == 1 or (peer is not None and qmf):
+            # lf_step_mid sums the forward's per-CTA rows itself (sharded: and exchanges the column sums over peer memory)
+            a.stats_rows_out = rows_out
         check(lib.lf_heads_forward(C.byref(a), st), "lf_heads_forward")
         if peer is not None:
             peer.check()                                          # pinned host flag: no synchronisation
