@@ -70,6 +70,9 @@ extern "C" {
    untouched; they vanish from the reported loss and from dL/dz. */
 #define LF_LOSS_NO_JOINT 1 /* loss_joint = 0 */
 #define LF_LOSS_NO_UNI 2   /* the sum of the unimodal CE terms is dropped */
+#define LF_LOSS_NO_REG 4   /* no ranking regulariser and no History: with LF_LOSS_NO_JOINT this is the ENSEMBLE loss
+                              CE(z1) + CE(z2) of cremad/ensemble_model_noised.py:52-53 (one CE per modality); lf_step_mid
+                              then needs neither idx nor the History arrays and leaves qmf_g (all zeros) alone */
 
 /*
  * Optional SGD(momentum, weight decay) update of the head parameters fused into the tail of lf_heads_backward
@@ -326,6 +329,29 @@ typedef struct LfMidArgs {
 } LfMidArgs;
 
 size_t lf_mid_workspace_bytes(int32_t batch_global);
+
+/*
+ * Feature-side pooling in front of the heads (cremad/joint_model_qmf.py:48-55):
+ *   pooled[b, c] = mean over t < frames, k < hw of maps[(b*frames + t), c, k]       maps: (batch*frames, channels, hw) contiguous
+ * i.e. F.adaptive_avg_pool2d(a, 1) for frames = 1 and view(B, T, C, H, W).permute(0, 2, 1, 3, 4) + adaptive_avg_pool3d(v, 1)
+ * for the frame-stacked visual stream.  elem_bytes = 4 (fp32) or 2 (bf16); fp32 accumulation, output in the input's type.
+ * lf_pool_mean_backward writes dmaps[(b*frames + t), c, k] = dpooled[b, c] / (frames * hw).
+ */
+int lf_pool_mean(const void* maps, void* pooled, int32_t batch, int32_t frames, int32_t channels, int32_t hw, int32_t elem_bytes, void* stream);
+int lf_pool_mean_backward(const void* dpooled, void* dmaps, int32_t batch, int32_t frames, int32_t channels, int32_t hw, int32_t elem_bytes, void* stream);
+
+/*
+ * Epoch-end unimodal offset correction over all logits collected during a validation / test epoch
+ * (utils/BaseModel.py:168-185): logits (n, 2, classes) fp32 contiguous, labels (n) int64 ->
+ *   offset_out (2, classes) = mean_m(mean_n logits) - mean_n logits
+ *   acc_out[4] (fp64)       = accuracies of x1 / x2 uncorrected, x1 / x2 with the offset added
+ * No host synchronisation.  workspace: >= lf_epoch_workspace_bytes(classes), zero-initialised once by the caller.
+ */
+size_t lf_epoch_workspace_bytes(int32_t classes);
+int lf_epoch_offset_correction(const float* logits, const int64_t* labels, int64_t n, int32_t classes, float* offset_out,
+                               double* acc_out, void* workspace, size_t workspace_bytes, void* stream);
+
+
 int lf_step_mid(const LfMidArgs* args, void* stream);
 
 typedef struct LfTensorList {

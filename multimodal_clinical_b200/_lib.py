@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "_lf_fusion.so")
 
 LF_MODE_JLOGITS, LF_MODE_QMF = 0, 1
 LF_PREC_FP32, LF_PREC_TF32, LF_PREC_BF16 = 0, 1, 2
-LF_LOSS_NO_JOINT, LF_LOSS_NO_UNI = 1, 2          # LfHeadsArgs.loss_terms / LfMidArgs.loss_terms bits (QMF loss ablations)
+LF_LOSS_NO_JOINT, LF_LOSS_NO_UNI, LF_LOSS_NO_REG = 1, 2, 4          # LfHeadsArgs.loss_terms / LfMidArgs.loss_terms bits (QMF loss ablations)
 LF_MOD_OGM_GE, LF_MOD_OGM, LF_MOD_NOISE = 0, 1, 2
 LF_STATS_HEADER = 16
 LF_MAX_TENSORS = 64
@@ -120,6 +120,10 @@ SIGNATURES = {
     "lf_comm_ipc_close": (C.c_int, [C.c_void_p]),
     "lf_peer_allreduce": (C.c_int, [C.POINTER(LfPeerReduceArgs), C.c_void_p]),
     "lf_mid_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "lf_pool_mean": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "lf_pool_mean_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "lf_epoch_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "lf_epoch_offset_correction": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lf_step_mid": (C.c_int, [C.POINTER(LfMidArgs), C.c_void_p]),
     "lf_modulate_workspace_bytes": (C.c_size_t, []),
     "lf_ogm_modulate": (C.c_int, [C.POINTER(LfTensorList), C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64,

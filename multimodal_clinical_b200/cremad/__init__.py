@@ -5,6 +5,8 @@ def get_model(args):
         from .joint_model import MultimodalCremadModel
     elif args.model_type == "ogm_ge":
         from .joint_model_ogm_ge import MultimodalCremadModel
+    elif args.model_type == "ensemble_ogm_ge":
+        from .ensemble_model_noised import MultimodalCremadModel
     elif args.model_type == "qmf":
         from .joint_model_qmf import MultimodalCremadModel
     elif args.model_type == "qmf_ablate":

@@ -194,7 +194,7 @@ static int check_heads(const LfHeadsArgs* a, bool backward) {
     set_error("ld_logits %d: must be >= classes, and a padded pitch is only supported on the tensor-pipe path", a->ld_logits);
     return LF_ERR_BAD_ARG;
   }
-  if (a->loss_terms & ~(LF_LOSS_NO_JOINT | LF_LOSS_NO_UNI)) { set_error("bad loss_terms %d", a->loss_terms); return LF_ERR_BAD_ARG; }
+  if (a->loss_terms & ~(LF_LOSS_NO_JOINT | LF_LOSS_NO_UNI | LF_LOSS_NO_REG)) { set_error("bad loss_terms %d", a->loss_terms); return LF_ERR_BAD_ARG; }
   if (a->ld_fused != 0 && a->ld_fused != a->classes && !use_tensor_pipe(a)) { set_error("ld_fused: a padded pitch is only supported on the tensor-pipe path"); return LF_ERR_BAD_ARG; }
   if (a->ld_fused != 0 && a->ld_fused < a->classes) { set_error("ld_fused %d < classes %d", a->ld_fused, a->classes); return LF_ERR_BAD_ARG; }
   if (a->ld_dlogits != 0 && a->ld_dlogits < a->classes) { set_error("ld_dlogits %d < classes %d", a->ld_dlogits, a->classes); return LF_ERR_BAD_ARG; }

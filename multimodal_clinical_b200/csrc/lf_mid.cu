@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_kernel(MidParams p) {
   // ---- exchange (sharded runs): this rank's statistics and per-sample records {idx, conf0, conf1} are stored into
   // slot [parity][rank] of every rank's receive area (NVLink stores; the local copy too, so readers see one layout).
   // No fence, flag or barrier follows: readers validate the words they need against the sentinel (lf_peer.cuh).
-  const bool qmf = a.mode == LF_MODE_QMF;
+  // (QMF heads with LF_LOSS_NO_REG -- the ensemble loss -- have no History / ranking part: they take the light path)
+  const bool qmf = a.mode == LF_MODE_QMF && !(a.loss_terms & LF_LOSS_NO_REG);
   long long epoch = 0;
   const char* rec_base = nullptr;              // local receive area of this epoch's parity
   const long long stats_bytes = ((long long)len * 8 + 15) / 16 * 16;
@@ -274,7 +275,16 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_kernel(MidParams p) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) ema_class(a, c, s_stats[LF_STATS_HEADER + c], s_stats[LF_STATS_HEADER + C + c]);
       if (threadIdx.x == 0) {
         if (a.coeff_out) ogm_coeff_write(a, (float)s_stats[LF_STAT_SCORE_X1], (float)s_stats[LF_STAT_SCORE_X2]);
-        if (a.loss_out) a.loss_out[0] = (float)(s_stats[LF_STAT_CE_JOINT] / (double)Bg);
+        if (a.loss_out) {
+          if (a.mode == LF_MODE_QMF) {         // ensemble: CE(z1) + CE(z2) (+ CE(z_df) unless ablated), each a separate fp32 mean
+            const double inv = 1.0 / (double)Bg;
+            const float uni = (a.loss_terms & LF_LOSS_NO_UNI) ? 0.f : (float)(s_stats[LF_STAT_CE_X1] * inv) + (float)(s_stats[LF_STAT_CE_X2] * inv);
+            const float joint = (a.loss_terms & LF_LOSS_NO_JOINT) ? 0.f : (float)(s_stats[LF_STAT_CE_JOINT] * inv);
+            a.loss_out[0] = joint + uni;
+          } else {
+            a.loss_out[0] = (float)(s_stats[LF_STAT_CE_JOINT] / (double)Bg);
+          }
+        }
         if (a.use_peer) a.comm.epoch[0] = epoch;
       }
     }
@@ -592,7 +602,7 @@ extern "C" size_t lf_mid_workspace_bytes(int32_t batch_global) {
 }
 
 extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
-  if (a && a->use_peer && a->mode == LF_MODE_QMF &&
+  if (a && a->use_peer && a->mode == LF_MODE_QMF && !(a->loss_terms & LF_LOSS_NO_REG) &&
       (a->off_idx < (int64_t)8 * (LF_STATS_HEADER + 2 * a->classes) || a->off_conf < a->off_idx + (int64_t)8 * a->batch_local ||
        a->payload_bytes < ((int64_t)8 * (LF_STATS_HEADER + 2 * a->classes) + 15) / 16 * 16 + (int64_t)16 * a->batch_local)) {
     set_error("lf_step_mid: payload layout [stats | idx | conf] does not fit payload_bytes");
@@ -603,7 +613,7 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
     set_error("lf_step_mid: bad peer-exchange arguments");
     return LF_ERR_BAD_ARG;
   }
-  if (a && a->stats_rows && ((a->n_ranks != 1 && !a->use_peer) || a->n_stats_rows < 1 || a->mode != LF_MODE_QMF)) {
+  if (a && a->stats_rows && ((a->n_ranks != 1 && (!a->use_peer || (a->loss_terms & LF_LOSS_NO_REG))) || a->n_stats_rows < 1 || a->mode != LF_MODE_QMF)) {
     set_error("lf_step_mid: stats_rows (QMF) needs one rank or the peer exchange (the column sums are exchanged in the kernel)");
     return LF_ERR_BAD_ARG;
   }
@@ -613,7 +623,8 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
     return LF_ERR_BAD_ARG;
   }
   if (a->update_ema && (!a->ema_x || !a->ema_offset)) { set_error("lf_step_mid: update_ema needs ema_x / ema_offset"); return LF_ERR_BAD_ARG; }
-  const bool qmf = a->mode == LF_MODE_QMF;
+  if (a->loss_terms & ~(LF_LOSS_NO_JOINT | LF_LOSS_NO_UNI | LF_LOSS_NO_REG)) { set_error("lf_step_mid: bad loss_terms %d", a->loss_terms); return LF_ERR_BAD_ARG; }
+  const bool qmf = a->mode == LF_MODE_QMF && !(a->loss_terms & LF_LOSS_NO_REG);
   if (qmf) {
     if ((!a->use_peer && (!a->idx_parts || !a->conf_parts)) || !a->correctness || !a->confidence || !a->last_writer || !a->workspace ||
         a->n_data < 1 || a->step_base < 0) { set_error("lf_step_mid: QMF mode needs idx/conf/History/workspace"); return LF_ERR_BAD_ARG; }
@@ -622,7 +633,7 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
       return LF_ERR_BAD_ARG;
     }
     if (a->workspace_bytes < lf_mid_workspace_bytes(a->batch_global)) { set_error("lf_step_mid: workspace too small"); return LF_ERR_WORKSPACE; }
-  } else if (a->mode != LF_MODE_JLOGITS) { set_error("lf_step_mid: bad mode %d", a->mode); return LF_ERR_BAD_ARG; }
+  } else if (a->mode != LF_MODE_JLOGITS && a->mode != LF_MODE_QMF) { set_error("lf_step_mid: bad mode %d", a->mode); return LF_ERR_BAD_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
   MidParams p;
   p.a = *a;

@@ -33,7 +33,7 @@ class MultimodalFoodModel(OGMGEBaseModel):
         self.model.fused.ogm_alpha = self.ogm_alpha
 
     def configure_optimizers(self):
-        optimizer = torch.optim.SGD(self.parameters(), lr=self.args.learning_rate, momentum=0.9, weight_decay=1.0e-4)
+        optimizer = self._sgd()
         if self.args.use_scheduler:
             scheduler = {'scheduler': StepLR(optimizer, step_size=50, gamma=0.5), 'interval': 'epoch', 'frequency': 1}
             return [optimizer], [scheduler]

@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ._lib import STAT
 from .step import LateFusionStep, StepOutput
 
 
@@ -35,6 +36,13 @@ class _FusedStep(torch.autograd.Function):
         head.last_step = out
         ctx.out = out if grad_mode else None
         ctx.dtypes = (f1.dtype, f2.dtype)
+        ctx.ensemble = head.mode == "ensemble"
+        if ctx.ensemble:
+            # one CE per modality (cremad/ensemble_model_noised.py:52-53): batch means of the per-modality CE sums
+            ce = (out.stats[STAT["CE_X1"]:STAT["CE_X2"] + 1] / float(out.batch_global)).float()
+            res = (out.logits[0], out.logits[1], ce[0], ce[1])
+            ctx.mark_non_differentiable(*res[:2])
+            return res
         res = (out.logits[0], out.logits[1], out.avg_logits, out.loss)
         if out.logits_df is not None:
             res = res + (out.logits_df,)
@@ -46,34 +54,36 @@ class _FusedStep(torch.autograd.Function):
         out: StepOutput = ctx.out
         if out is None:
             raise _lib.LfError("backward through a fused step that ran with gradients disabled")
-        g = grads[3]                                    # d(total)/d(loss), a 0-d tensor
+        # d(total)/d(loss), a 0-d tensor; the ensemble head has one loss per modality, each reaching only its own head
+        gm = (grads[2], grads[3]) if ctx.ensemble else (grads[3], grads[3])
 
-        def scaled(t, dtype=None):
+        def scaled(t, dtype=None, m=0):
             if t is None:
                 return None
-            t = t * g
+            t = t * gm[m]
             return t if dtype is None or t.dtype == dtype else t.to(dtype)
 
         need = ctx.needs_input_grad
         return (None,
                 scaled(out.dfeat[0], ctx.dtypes[0]) if need[1] else None,
-                scaled(out.dfeat[1], ctx.dtypes[1]) if need[2] else None,
+                scaled(out.dfeat[1], ctx.dtypes[1], 1) if need[2] else None,
                 scaled(out.dweight[0]) if need[3] else None, scaled(out.dbias[0]) if need[4] else None,
-                scaled(out.dweight[1]) if need[5] else None, scaled(out.dbias[1]) if need[6] else None,
+                scaled(out.dweight[1], None, 1) if need[5] else None, scaled(out.dbias[1], None, 1) if need[6] else None,
                 None, None)
 
 
 class FusedLateFusionHead(nn.Module):
     """Parameter-free module that owns the device state of the fused step (EMA, QMF History, scratch).
 
-    mode: "jlogits" (mean fusion + CE; also what the OGM-GE models use) or "qmf".
+    mode: "jlogits" (mean fusion + CE; also what the OGM-GE models use), "qmf", or "ensemble" (one CE per modality,
+    cremad/ensemble_model_noised.py: forward returns (x1_logits, x2_logits, x1_loss, x2_loss)).
     """
 
     def __init__(self, num_classes: int, mode: str = "jlogits", n_data: Optional[int] = None,
                  precision: str = "auto", ema_smoothing: float = 0.05, loss_terms: int = 0,
                  process_group=None, sharded: bool = False):
         super().__init__()
-        if mode not in ("jlogits", "ogm_ge", "qmf"):
+        if mode not in ("jlogits", "ogm_ge", "qmf", "ensemble"):
             raise NotImplementedError(f"fused head mode {mode!r}")
         if precision not in ("auto", "fp32", "tf32", "bf16"):
             raise ValueError(f"head precision {precision!r}")
@@ -100,6 +110,8 @@ class FusedLateFusionHead(nn.Module):
         self._grad_enabled = True
         self._ema = None
         self._qmf_state = None
+        self._in_step_sgd = None                     # (lr, momentum, weight_decay) once an optimizer asked for it
+        self._in_step_done = {}
 
     def bind_ema(self, ema) -> None:
         """Share the calibration state with the LightningModule's ``utils.EMA.EMA`` (utils/BaseModel.py:30)."""
@@ -134,6 +146,39 @@ class FusedLateFusionHead(nn.Module):
             return "tf32"
         return "fp32"
 
+    # ------------------------------------------------------------------ SGD inside the step (utils/fused_sgd.py)
+    def enable_in_step_sgd(self, lr: float, momentum: float, weight_decay: float, lr_source=None) -> bool:
+        """Ask the fused step to apply torch.optim.SGD(lr, momentum, weight_decay) to the head tensors itself.  Returns
+        False when that cannot be right: under a DDP wrapper (sharded=False while torch.distributed has several ranks)
+        the gradients are only reduced after ``backward()``."""
+        import torch.distributed as dist
+        if not self.sharded and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return False
+        self._in_step_sgd = (float(lr), float(momentum), float(weight_decay))
+        self._lr_source = lr_source                  # callable -> current lr (the optimizer's param group, moved by StepLR)
+        for eng in self._engines.values():
+            self._apply_in_step_sgd(eng)
+        return True
+
+    def _apply_in_step_sgd(self, eng) -> None:
+        if self._in_step_sgd is None:
+            return
+        try:
+            eng.enable_sgd(*self._in_step_sgd)
+        except _lib.LfError:
+            pass                                     # exact-fp32 / narrow heads: the optimizer keeps updating them
+
+    def set_in_step_lr(self, lr: float) -> None:
+        if self._in_step_sgd is not None and float(lr) != self._in_step_sgd[0]:
+            self._in_step_sgd = (float(lr),) + self._in_step_sgd[1:]
+            for eng in self._engines.values():
+                if eng._sgd is not None:
+                    eng.set_lr(lr)
+
+    def in_step_updated(self) -> dict:
+        """{id(parameter): momentum buffer} for the head tensors the LAST fused step updated itself."""
+        return self._in_step_done
+
     def _shared_state(self):
         if self._ema is None:
             from .utils.EMA import EMA
@@ -154,6 +199,7 @@ class FusedLateFusionHead(nn.Module):
                                  ema=self._ema, loss_terms=self.loss_terms, process_group=self.process_group,
                                  sharded=self.sharded)
             eng.fresh_outputs = True
+            self._apply_in_step_sgd(eng)
             self._engines[key] = eng
         self._engine = eng
         return eng
@@ -172,8 +218,15 @@ class FusedLateFusionHead(nn.Module):
             raise ValueError("QMF head needs the dataset indices of the batch (idx)")
         # the reference's eval steps still compute the loss (and, QMF, mutate the History) but never touch
         # the EMA and need no gradients (utils/BaseModel.py:133-160, 1009-1040)
-        self._get_engine(f1.device, self.resolve_precision(f1))
+        eng = self._get_engine(f1.device, self.resolve_precision(f1))
+        if self._in_step_sgd is not None and getattr(self, "_lr_source", None) is not None:
+            self.set_in_step_lr(self._lr_source())   # device-resident hyper-parameter: a write only when StepLR moved it
         self._grad_enabled = torch.is_grad_enabled()
         self.update_ema = self.training and self._grad_enabled
-        return _FusedStep.apply(self, f1, f2, lin1.weight, lin1.bias, lin2.weight, lin2.bias, label,
-                                idx.view(-1) if idx is not None else None)
+        res = _FusedStep.apply(self, f1, f2, lin1.weight, lin1.bias, lin2.weight, lin2.bias, label,
+                               idx.view(-1) if idx is not None else None)
+        self._in_step_done = {}
+        if eng._sgd is not None and self._grad_enabled and eng._sgd.get("mom") is not None:
+            params = (lin1.weight, lin1.bias, lin2.weight, lin2.bias)
+            self._in_step_done = {id(p): m for p, m in zip(params, eng._sgd["mom"])}
+        return res

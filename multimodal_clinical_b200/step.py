@@ -91,7 +91,11 @@ class LateFusionStep:
         if not torch.cuda.is_available():
             raise _lib.LfError("LateFusionStep needs a CUDA device (sm_100a); there is no CPU fallback")
         self.C = int(num_classes)
-        self.mode = {"jlogits": LF_MODE_JLOGITS, "ogm_ge": LF_MODE_JLOGITS, "qmf": LF_MODE_QMF}[mode]
+        # "ensemble": one CE per modality (cremad/ensemble_model_noised.py:52-53) = the QMF kernels' unimodal terms
+        # without the joint term, the ranking regulariser and the History
+        self.mode = {"jlogits": LF_MODE_JLOGITS, "ogm_ge": LF_MODE_JLOGITS, "qmf": LF_MODE_QMF, "ensemble": LF_MODE_QMF}[mode]
+        if mode == "ensemble":
+            loss_terms = int(loss_terms) | _lib.LF_LOSS_NO_JOINT | _lib.LF_LOSS_NO_REG
         self.precision = {"fp32": LF_PREC_FP32, "tf32": LF_PREC_TF32, "bf16": LF_PREC_BF16}[precision]
         self.bf16 = self.precision == LF_PREC_BF16
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -111,7 +115,8 @@ class LateFusionStep:
         self.coeff = torch.ones(2, device=dev)
         self.loss = torch.zeros(1, device=dev)
         self.n_data = None
-        if self.mode == LF_MODE_QMF:
+        self.has_history = self.mode == LF_MODE_QMF and not (self.loss_terms & _lib.LF_LOSS_NO_REG)
+        if self.has_history:
             if n_data is None:
                 raise ValueError("QMF mode needs n_data (args.num_samples)")
             self.n_data = int(n_data)
@@ -213,7 +218,7 @@ class LateFusionStep:
             # one flat buffer [dW1 | db1 | dW2 | db2 | cal1 cal2] so the gradient exchange is ONE all-reduce
             n = Cn * D
             b["grad_flat"] = torch.empty((2 * (n + Cn) + 2 + 3) // 4 * 4, device=dev)[:2 * (n + Cn) + 2]   # 16-B padded slot
-            b["qmf_g"] = torch.empty(2, B, device=dev) if qmf else None
+            b["qmf_g"] = torch.zeros(2, B, device=dev) if qmf else None      # stays zero for the ensemble loss (no ranking term)
             self._bufs = b
             self._ws_key = key
         if self.fresh_outputs:
@@ -325,7 +330,9 @@ class LateFusionStep:
         # this rank's contribution to the one exchange before the backward pass:
         # [partial statistics (16+2C) f64 | idx (B) i64 | conf (2,B) f32], 8-byte aligned pieces
         pay, p_stats, p_idx, p_conf = self._payload(B, qmf)
-        if qmf:
+        hist = self.has_history
+        idx_in_place = True
+        if hist:
             if idx is None:
                 raise ValueError("QMF step needs the dataset indices of the batch (idx)")
             idx = idx.reshape(-1)
@@ -333,7 +340,7 @@ class LateFusionStep:
             # (peer exchange): no staging copy kernel in the step.  Only the NCCL all-gather needs them in the payload.
             idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
             self._idx_keep = idx
-            idx_in_place = self.world == 1 or (self.comm_mode != "nccl" and B % 2 == 0 and idx.data_ptr() % 16 == 0)
+            idx_in_place = self.world == 1 or self.comm_mode != "nccl"
             if not idx_in_place:
                 p_idx.copy_(idx)
 
@@ -385,7 +392,7 @@ class LateFusionStep:
             a.sgd = C.pointer(sgd)
 
         rows_out = (C.c_uint64 * 2)(0, 0)
-        if self.world == 1 or (peer is not None and qmf):
+        if self.world == 1 or (peer is not None and hist):
             # lf_step_mid sums the forward's per-CTA rows itself (sharded: and exchanges the column sums over peer memory)
             a.stats_rows_out = rows_out
         check(lib.lf_heads_forward(C.byref(a), st), "lf_heads_forward")
@@ -399,10 +406,10 @@ class LateFusionStep:
             mid.off_idx, mid.off_conf = self._off_idx, self._off_conf
             peer.fill(mid.comm)
             gathered = pay
-            if qmf and idx_in_place:
+            if hist and idx_in_place:
                 mid.payload_idx_src = idx.data_ptr()
         else:
-            if qmf and idx_in_place and self.world > 1:
+            if hist and idx_in_place and self.world > 1:
                 p_idx.copy_(idx)                                  # fell back to NCCL after all (no peer mapping)
             gathered = parallel.gather_payload(pay, self.pg)      # (world, payload bytes); identity on one GPU
         mid.mode, mid.classes, mid.batch_global, mid.n_ranks = self.mode, Cn, Bg, self.world
@@ -411,7 +418,7 @@ class LateFusionStep:
         mid.stats_parts, mid.stats_stride = base, stride // 8
         if rows_out[0]:
             mid.stats_rows, mid.n_stats_rows = rows_out[0], rows_out[1]
-        if qmf:
+        if hist:
             qs = self.qmf_state
             mid.idx_parts, mid.idx_stride = (idx.data_ptr() if self.world == 1 else base + self._off_idx), stride // 8
             mid.conf_parts, mid.conf_stride = base + self._off_conf, stride // 4
@@ -426,7 +433,7 @@ class LateFusionStep:
             mid.alpha, mid.coeff_out = float(ogm_alpha), _ptr(self.coeff)
         mid.loss_out = _ptr(self.loss)
         mid.loss_terms = self.loss_terms
-        if fuse_ar and qmf:
+        if fuse_ar and hist:
             # ranking terms of this rank's slice only; the partial sums ride in the gradient all-reduce
             if getattr(self, "_reg_partial", None) is None:
                 self._reg_partial = torch.zeros(4, device=self.device)
@@ -446,7 +453,7 @@ class LateFusionStep:
                 gcomm = _lib.LfPeerComm()
                 peer.fill(gcomm)
                 a.grad_comm = C.pointer(gcomm)
-                if qmf:
+                if hist:
                     a.reg_partial, a.loss_out = _ptr(self._reg_partial), _ptr(self.loss)
                 check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
             else:

@@ -25,7 +25,35 @@ from .._lib import STAT
 from ..existing_algos.OGM_GE import ogm_ge
 from ..heads import FusedLateFusionHead
 from .EMA import EMA
+from .fused_sgd import SGDWithFusedHeads
 from .lightning_compat import pl
+
+
+_epoch_ws = {}
+
+
+def epoch_offset_correction(logits: torch.Tensor, labels: torch.Tensor):
+    """Epoch-end unimodal offset correction (utils/BaseModel.py:168-185) on the device: logits (N, 2, C), labels (N) ->
+    (offset (2, C), accuracies [x1 uncal, x2 uncal, x1 corrected, x2 corrected] as a 4-element fp32 device tensor)."""
+    import ctypes as C
+    from .. import _lib
+    if not logits.is_cuda:
+        raise _lib.LfError("epoch_offset_correction runs on CUDA only; got a CPU tensor")
+    lib = _lib.load()
+    z = logits.detach().float().contiguous()
+    y = labels.to(device=z.device, dtype=torch.int64).contiguous()
+    n, m, c = z.shape
+    if m != 2:
+        raise NotImplementedError("two modalities")
+    key = (z.device.index, c)
+    if key not in _epoch_ws:
+        _epoch_ws[key] = torch.zeros(lib.lf_epoch_workspace_bytes(c), dtype=torch.uint8, device=z.device)
+    ws = _epoch_ws[key]
+    offset = torch.empty(2, c, device=z.device)
+    acc = torch.empty(4, dtype=torch.float64, device=z.device)
+    _lib.check(lib.lf_epoch_offset_correction(z.data_ptr(), y.data_ptr(), n, c, offset.data_ptr(), acc.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), torch.cuda.current_stream().cuda_stream), "lf_epoch_offset_correction")
+    return offset, acc.float()
 
 
 def _mean(xs):
@@ -120,17 +148,15 @@ class JointLogitsBaseModel(pl.LightningModule, ABC):
         metrics = self.val_metrics if kind == "val" else self.test_metrics
         labels = torch.cat(metrics[f"{kind}_labels"], dim=0)
         logits = torch.cat(metrics[f"{kind}_logits"], dim=0)          # (N, M, C)
-        m_out = torch.mean(logits, dim=0)
-        offset = torch.mean(m_out, dim=0, keepdim=True) - m_out       # (M, C)
-        corrected = logits + offset
-        acc = lambda z: torch.mean((torch.argmax(z, dim=1) == labels).float())
+        offset, acc = epoch_offset_correction(logits, labels)         # device kernel pair, no host sync
+        self.last_epoch_offset = offset                                # (M, C): mean_m(mean_n logits) - mean_n logits
         kw = dict(on_step=False, on_epoch=True, prog_bar=False, logger=True)
         self.log(f"{kind}_epoch/{kind}_avg_acc", _mean(metrics[f"{kind}_acc"]), **kw)
         self.log(f"{kind}_epoch/{kind}_avg_loss", _mean(metrics[f"{kind}_loss"]), **kw)
-        self.log(f"{kind}_epoch/{kind}_avg_x1_acc_uncal", acc(logits[:, 0, :]), **kw)
-        self.log(f"{kind}_epoch/{kind}_avg_x2_acc_uncal", acc(logits[:, 1, :]), **kw)
-        self.log(f"{kind}_epoch/{kind}_avg_x1_acc", acc(corrected[:, 0, :]), **kw)
-        self.log(f"{kind}_epoch/{kind}_avg_x2_acc", acc(corrected[:, 1, :]), **kw)
+        self.log(f"{kind}_epoch/{kind}_avg_x1_acc_uncal", acc[0], **kw)
+        self.log(f"{kind}_epoch/{kind}_avg_x2_acc_uncal", acc[1], **kw)
+        self.log(f"{kind}_epoch/{kind}_avg_x1_acc", acc[2], **kw)
+        self.log(f"{kind}_epoch/{kind}_avg_x2_acc", acc[3], **kw)
         if with_df:
             self.log(f"{kind}_epoch/{kind}_avg_df_acc", _mean(metrics[f"{kind}_df_acc"]), **kw)
         for k in list(metrics):
@@ -158,12 +184,101 @@ class JointLogitsBaseModel(pl.LightningModule, ABC):
     def on_test_epoch_end(self):
         self._eval_epoch_end("test")
 
+    def _sgd(self):
+        """SGD(lr, momentum 0.9, weight decay 1e-4) over all parameters (utils/BaseModel.py:275-285).  The head tensors are
+        updated inside the fused step where it can take them (utils/fused_sgd.py; ``args.fused_head_sgd = False`` keeps the
+        stock optimizer for everything)."""
+        if getattr(self.args, "fused_head_sgd", True):
+            return SGDWithFusedHeads(self.parameters(), self.model.fused, lr=self.args.learning_rate, momentum=0.9, weight_decay=1.0e-4)
+        return torch.optim.SGD(self.parameters(), lr=self.args.learning_rate, momentum=0.9, weight_decay=1.0e-4)
+
     def configure_optimizers(self):
-        optimizer = torch.optim.SGD(self.parameters(), lr=self.args.learning_rate, momentum=0.9, weight_decay=1.0e-4)
+        optimizer = self._sgd()
         if self.args.use_scheduler:
             scheduler = {'scheduler': StepLR(optimizer, step_size=70, gamma=0.1), 'interval': 'epoch', 'frequency': 1}
             return [optimizer], [scheduler]
         return optimizer
+
+    @abstractmethod
+    def _build_model(self):
+        pass
+
+
+class EnsembleBaseModel(pl.LightningModule, ABC):
+    """Per-modality CE ensemble (utils/BaseModel.py:291-562 of the reference): ``self.model(x1, x2, label)`` returns
+    ``(x1_logits, x2_logits, x1_loss, x2_loss)``; no EMA calibration and no epoch-end offset correction in this family.
+    The accuracies of a step come from the packed statistics of the fused step (no host sync)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.model = self._build_model()
+        if not isinstance(getattr(self.model, "fused", None), FusedLateFusionHead):
+            raise TypeError("self.model must expose a FusedLateFusionHead as `.fused`: the late-fusion step has no "
+                            "eager PyTorch fallback")
+        self.train_metrics = {"train_loss": [], "train_acc": [], "train_x1_acc": [], "train_x2_acc": []}
+        self.val_metrics = {"val_loss": [], "val_acc": [], "val_x1_acc": [], "val_x2_acc": []}
+        self.test_metrics = {"test_loss": [], "test_acc": [], "test_x1_acc": [], "test_x2_acc": []}
+
+    def forward(self, x1, x2, label):
+        return self.model(x1, x2, label)
+
+    def _accs(self):
+        out = self.model.fused.last_step
+        a = (out.stats[STAT["CNT_X1"]:STAT["CNT_JOINT"] + 1] / float(out.batch_global)).float()
+        return a[0], a[1], a[2]                      # x1, x2, joint = argmax of (z1 + z2) / 2
+
+    def _record(self, kind, loss, accs, metrics):
+        x1_acc, x2_acc, joint_acc = accs
+        kw = dict(on_step=True, on_epoch=True, prog_bar=False, logger=True)
+        self.log(f"{kind}_step/{kind}_loss", loss, **kw)
+        self.log(f"{kind}_step/{kind}_acc", joint_acc, **kw)
+        if kind == "train":
+            self.log("train_step/train_x1_acc", x1_acc, **kw)
+            self.log("train_step/train_x2_acc", x2_acc, **kw)
+        metrics[f"{kind}_loss"].append(loss.detach()); metrics[f"{kind}_acc"].append(joint_acc)
+        metrics[f"{kind}_x1_acc"].append(x1_acc); metrics[f"{kind}_x2_acc"].append(x2_acc)
+
+    def training_step(self, batch, batch_idx):
+        x1, x2, label = batch
+        x1_logits, x2_logits, x1_loss, x2_loss = self.model(x1, x2, label)
+        avg_loss = (x1_loss + x2_loss)               # (sic: the base class sums, utils/BaseModel.py:361)
+        self._record("train", avg_loss, self._accs(), self.train_metrics)
+        return avg_loss
+
+    def _eval_step(self, kind, batch):
+        x1, x2, label = batch
+        x1_logits, x2_logits, x1_loss, x2_loss = self.model(x1, x2, label)
+        avg_loss = (x1_loss + x2_loss) / 2
+        self._record(kind, avg_loss, self._accs(), self.val_metrics if kind == "val" else self.test_metrics)
+        return avg_loss
+
+    def _epoch_end(self, kind, metrics):
+        kw = dict(on_step=False, on_epoch=True, prog_bar=False, logger=True)
+        self.log(f"{kind}_epoch/{kind}_avg_loss", _mean(metrics[f"{kind}_loss"]), **kw)
+        self.log(f"{kind}_epoch/{kind}_avg_acc", _mean(metrics[f"{kind}_acc"]), **kw)
+        self.log(f"{kind}_epoch/{kind}_avg_x1_acc", _mean(metrics[f"{kind}_x1_acc"]), **kw)
+        self.log(f"{kind}_epoch/{kind}_avg_x2_acc", _mean(metrics[f"{kind}_x2_acc"]), **kw)
+        for k in metrics:
+            metrics[k].clear()
+
+    def on_train_epoch_end(self) -> None:
+        self._epoch_end("train", self.train_metrics)
+
+    def validation_step(self, batch, batch_idx):
+        return self._eval_step("val", batch)
+
+    def on_validation_epoch_end(self) -> None:
+        self._epoch_end("val", self.val_metrics)
+
+    def test_step(self, batch, batch_idx):
+        return self._eval_step("test", batch)
+
+    def on_test_epoch_end(self):
+        self._epoch_end("test", self.test_metrics)
+
+    _sgd = JointLogitsBaseModel._sgd
+    configure_optimizers = JointLogitsBaseModel.configure_optimizers
 
     @abstractmethod
     def _build_model(self):

@@ -41,3 +41,47 @@ class FusedHeadSGD(torch.optim.Optimizer):
                 a.first_step = int(firsts.pop())
                 check(lib.lf_sgd_heads(C.byref(a), torch.cuda.current_stream().cuda_stream), "lf_sgd_heads")
         return loss
+
+
+class SGDWithFusedHeads(torch.optim.SGD):
+    """``torch.optim.SGD(params, lr, momentum, weight_decay)`` of the reference's ``configure_optimizers``
+    (utils/BaseModel.py:275-285; enrico/joint_model.py:100-110; food101/joint_model_qmf.py:96-106) whose HEAD parameters are
+    updated inside the fused step -- in the tail of the dW kernel, right after their gradients are reduced (and
+    all-reduced on several GPUs) -- instead of by foreach kernels after ``backward()``.
+
+    Every parameter stays in the optimizer's groups (so ``StepLR`` sees one ``lr`` and ``state_dict`` has every
+    ``momentum_buffer``); ``step()`` skips the tensors the last fused step has already updated and runs the stock SGD
+    on the rest (encoders, hidden MLP layers).  Heads fall back to the stock update whenever the step could not take
+    them (exact-fp32 / narrow heads: the in-step update is part of the tensor-pipe dW kernel).  Not for training loops
+    that modify ``.grad`` of the heads between ``backward()`` and ``step()`` (clipping): pass ``fused_head_sgd=False``."""
+
+    def __init__(self, params, head, lr, momentum=0.9, weight_decay=1.0e-4):
+        super().__init__(params, lr=lr, momentum=momentum, weight_decay=weight_decay)
+        self.head = head
+        # the head reads this optimizer's current lr at every forward (StepLR changes it between steps)
+        self.in_step = head.enable_in_step_sgd(lr, momentum, weight_decay, lr_source=lambda: self.param_groups[0]["lr"])
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if not self.in_step:
+            return super().step(closure)
+        head = self.head
+        done = head.in_step_updated()                          # {id(param): momentum buffer} of the step that just ran
+        hidden = []
+        for g in self.param_groups:
+            for p in g["params"]:
+                buf = done.get(id(p))
+                if buf is None:
+                    continue
+                st = self.state[p]
+                mine = st.get("momentum_buffer")
+                if mine is not None and mine is not buf:       # loaded from a checkpoint: hand it to the step, then alias
+                    buf.copy_(mine)
+                st["momentum_buffer"] = buf
+                hidden.append((p, p.grad))
+                p.grad = None                                  # torch's SGD skips parameters without a gradient
+        try:
+            return super().step(closure)
+        finally:
+            for p, gr in hidden:
+                p.grad = gr

@@ -18,6 +18,8 @@ Reference lines followed (paths relative to the reference tree):
   ranking regulariser ............... existing_algos/QMF.py:119-141
   OGM-GE scores / coefficients ...... existing_algos/OGM_GE.py:21-40
   OGM-GE gradient modulation ........ existing_algos/OGM_GE.py:42-57
+  per-modality ensemble ............. cremad/ensemble_model_noised.py:49-55, 97-120
+  epoch-end offset correction ....... utils/BaseModel.py:168-185
   EMA logit offsets ................. utils/EMA.py:29-38, utils/BaseModel.py:82-85
   step metrics ...................... utils/BaseModel.py:78-92, 946-961
 
@@ -286,6 +288,29 @@ def jlogits_step(feats, weights, biases, y, ema_x=None, dtype=torch.float32, fea
     loss = cross_entropy_mean(avg, y)
     out = {"loss": loss, "avg_logits": avg}
     return _finish(out, fs, ws, bs, zs, y, ema_x, feat_grad)
+
+
+def ensemble_step(feats, weights, biases, y, dtype=torch.float32, feat_grad=True) -> Dict:
+    """Per-modality ensemble: x_m_loss = CE(z_m, y), backward of (x1_loss + x2_loss) / 2
+    (cremad/ensemble_model_noised.py:49-55, 97-103, 119-120).  No EMA calibration in this family
+    (utils/BaseModel.py:291-562); the joint accuracy is that of (z1 + z2) / 2."""
+    fs, ws, bs = _leafs(feats, weights, biases, dtype, feat_grad)
+    zs = heads_forward(fs, ws, bs)
+    l1, l2 = cross_entropy_mean(zs[0], y), cross_entropy_mean(zs[1], y)
+    out = {"loss": (l1 + l2) / 2, "avg_logits": (zs[0] + zs[1]) / 2, "loss_x1": l1.detach(), "loss_x2": l2.detach()}
+    return _finish(out, fs, ws, bs, zs, y, None, feat_grad)
+
+
+def epoch_offset_correction(logits: torch.Tensor, labels: torch.Tensor) -> Dict:
+    """Epoch-end unimodal offset correction over all collected logits (N, M, C) (utils/BaseModel.py:168-185):
+    offset = mean_m(mean_n logits) - mean_n logits; accuracies of the raw and of the corrected unimodal logits."""
+    m_out = torch.mean(logits, dim=0)
+    offset = torch.mean(m_out, dim=0, keepdim=True) - m_out
+    corrected = logits + offset
+    N = logits.shape[0]
+    return {"offset": offset,
+            "x1_acc_uncal": correct_count(logits[:, 0, :], labels) / N, "x2_acc_uncal": correct_count(logits[:, 1, :], labels) / N,
+            "x1_acc": correct_count(corrected[:, 0, :], labels) / N, "x2_acc": correct_count(corrected[:, 1, :], labels) / N}
 
 
 LOSS_NO_JOINT, LOSS_NO_UNI = 1, 2     # the LF_LOSS_* bits of include/lf_fusion.h

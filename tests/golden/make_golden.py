@@ -232,6 +232,146 @@ def golden_modulate(name, seed):
     print("wrote", name)
 
 
+def golden_ensemble(name, B, D, C, steps, seed, alpha):
+    """cremad/ensemble_model_noised.FusionNet (one CE per modality) with stub encoders + existing_algos.OGM_GE.ogm_ge
+    (modulation 'OGM'): losses, gradients of (x1_loss + x2_loss) / 2 and the coefficients read back from the grads."""
+    from existing_algos.OGM_GE import ogm_ge
+    import cremad.ensemble_model_noised as me
+    g = torch.Generator().manual_seed(seed)
+    W1, b1 = lin_init(C, D, g)
+    W2, b2 = lin_init(C, D, g)
+
+    def stub(modality):
+        conv = nn.Conv2d(D, D, 1, bias=False)
+        with torch.no_grad():
+            nn.init.dirac_(conv.weight)
+        return nn.Sequential(conv)
+    me.resnet18 = stub
+    net = me.FusionNet(C, nn.CrossEntropyLoss())
+    set_heads(net, W1, b1, W2, b2)
+    rec = {"W1": W1.numpy(), "b1": b1.numpy(), "W2": W2.numpy(), "b2": b2.numpy(),
+           "meta": np.array([B, D, C, 0, steps], dtype=np.int64), "alpha": np.float64(alpha)}
+    for s in range(steps):
+        f1 = torch.randn(B, D, generator=g); f2 = torch.randn(B, D, generator=g)
+        y = torch.randint(0, C, (B,), generator=g, dtype=torch.int64)
+        if s % 2 == 0:
+            f1 = f1 + 0.3 * W1[y] * np.sqrt(D)
+        else:
+            f2 = f2 + 0.3 * W2[y] * np.sqrt(D)
+        a = f1.clone().view(B, D, 1, 1).requires_grad_(True)
+        v = f2.clone().view(B, D, 1, 1).requires_grad_(True)
+        net.zero_grad()
+        z1, z2, l1, l2 = net(a, v, y)
+        ((l1 + l2) / 2).backward()                                       # ensemble_model_noised.py:103, 119-120
+        g1 = net.x1_model[0].weight.grad.clone(); g2 = net.x2_model[0].weight.grad.clone()
+        ogm_ge(net, z1, z2, y, alpha=alpha, modulation="OGM")
+        k1 = (net.x1_model[0].weight.grad.flatten() @ g1.flatten()) / (g1.flatten() @ g1.flatten())
+        k2 = (net.x2_model[0].weight.grad.flatten() @ g2.flatten()) / (g2.flatten() @ g2.flatten())
+        avg = (z1 + z2) / 2
+        r = {"f1": f1, "f2": f2, "y": y, "z1": z1, "z2": z2, "loss_x1": l1, "loss_x2": l2,
+             "dW1": net.x1_classifier.weight.grad, "db1": net.x1_classifier.bias.grad,
+             "dW2": net.x2_classifier.weight.grad, "db2": net.x2_classifier.bias.grad,
+             "df1": a.grad.view(B, D), "df2": v.grad.view(B, D)}
+        for k, t in r.items():
+            rec[f"s{s}_{k}"] = t.detach().numpy().copy()
+        rec[f"s{s}_coeff"] = np.array([float(k1), float(k2)])
+        f = lambda z: float(torch.mean((torch.argmax(z, dim=1) == y).float()))
+        rec[f"s{s}_acc_x1"] = np.float64(f(z1.detach())); rec[f"s{s}_acc_x2"] = np.float64(f(z2.detach()))
+        rec[f"s{s}_acc_joint"] = np.float64(f(avg.detach()))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print("wrote", name, "losses(last) =", float(l1.detach()), float(l2.detach()))
+
+
+def golden_epoch_end(name, n_batches, B, C, seed):
+    """utils/BaseModel.JointLogitsBaseModel.on_validation_epoch_end (:161-202) of the UNMODIFIED reference class: the
+    collected (N, M, C) logits, the labels and every value it logs."""
+    import utils.BaseModel as RB
+
+    class Model(RB.JointLogitsBaseModel):
+        def _build_model(self):
+            return nn.Identity()
+
+    m = Model(argparse.Namespace(num_classes=C, learning_rate=0.1, use_scheduler=False))
+    logged = {}
+    m.log = lambda key, val, **kw: logged.__setitem__(key, float(val))
+    g = torch.Generator().manual_seed(seed)
+    rec = {"meta": np.array([n_batches, B, C], dtype=np.int64)}
+    shift = torch.randn(2, C, generator=g) * 0.7              # per-modality class bias: what the correction removes
+    for i in range(n_batches):
+        nb = B if i < n_batches - 1 else B // 2 + 1            # short last batch
+        y = torch.randint(0, C, (nb,), generator=g, dtype=torch.int64)
+        z = torch.randn(nb, 2, C, generator=g) + shift
+        z[torch.arange(nb), :, y] += 1.0                       # some signal
+        m.val_metrics["val_logits"].append(z.clone())
+        m.val_metrics["val_labels"].append(y.clone())
+        m.val_metrics["val_loss"].append(torch.rand((), generator=g))
+        m.val_metrics["val_acc"].append(torch.rand((), generator=g))
+        rec[f"b{i}_logits"] = z.numpy().copy(); rec[f"b{i}_labels"] = y.numpy().copy()
+        rec[f"b{i}_loss"] = m.val_metrics["val_loss"][-1].numpy().copy(); rec[f"b{i}_acc"] = m.val_metrics["val_acc"][-1].numpy().copy()
+    m.on_validation_epoch_end()
+    for k, v in logged.items():
+        rec["log/" + k] = np.float64(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print("wrote", name, logged)
+
+
+def golden_food101(name, B, C, N, steps, seed):
+    """food101/joint_model_qmf.FusionNet of the reference (:28-81): SigLIP stubbed by a module that returns the given
+    768-d embeddings, the two 768 -> 512 -> 512 -> C MLP heads in eval() mode (Dropout off), the
+    QMF loss; gradients on EVERY MLP parameter and on the embeddings, the History after each step."""
+    import food101.joint_model_qmf as fq
+
+    class FakeSiglip(nn.Module):
+        @classmethod
+        def from_pretrained(cls, *a, **k):
+            return cls()
+
+        def forward(self, x1, x2):
+            return {"text_embeds": x1, "image_embeds": x2}
+    fq.AutoModel = FakeSiglip
+    net = fq.FusionNet(argparse.Namespace(num_classes=C, num_samples=N), nn.CrossEntropyLoss())
+    net.eval()
+    food101_fill(net, seed)
+    g = torch.Generator().manual_seed(seed)
+    rec = {"meta": np.array([B, 768, C, N, steps, seed], dtype=np.int64)}
+    for s in range(steps):
+        e1 = torch.randn(B, 768, generator=g).requires_grad_(True)
+        e2 = torch.randn(B, 768, generator=g).requires_grad_(True)
+        y = torch.randint(0, C, (B,), generator=g, dtype=torch.int64)
+        idx = (torch.arange(B, dtype=torch.int64) + s * B) % N          # unshuffled loader (food101/run_training.py:39-45)
+        net.zero_grad()
+        z1, z2, avg, loss, zdf = net(e1, e2, y, idx)
+        loss.backward()
+        r = {"e1": e1, "e2": e2, "y": y, "idx": idx, "z1": z1, "z2": z2, "avg": avg, "zdf": zdf, "loss": loss,
+             "de1": e1.grad, "de2": e2.grad}
+        for k, t in r.items():
+            rec[f"s{s}_{k}"] = t.detach().numpy().copy()
+        for n, p in net.named_parameters():
+            if p.grad is None:
+                continue
+            if p.grad.numel() <= 60000:                                  # heads (mlp.6) and every bias: in full
+                rec[f"s{s}_grad/" + n] = p.grad.numpy().copy()
+            else:                                                        # hidden weights: two seeded random projections
+                gr = torch.Generator().manual_seed(1000 + s)
+                rec[f"s{s}_gradR/" + n] = (p.grad @ torch.randn(p.grad.shape[1], 4, generator=gr)).numpy().copy()
+                rec[f"s{s}_gradL/" + n] = (torch.randn(4, p.grad.shape[0], generator=gr) @ p.grad).numpy().copy()
+        rec[f"s{s}_corr"] = np.stack([h.correctness for h in net.qmf.history]).copy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print("wrote", name, "loss(last) =", float(loss.detach()))
+
+
+def food101_fill(net, seed):
+    """Deterministic parameters for the Food101 MLPs (nn.Linear's default range), regenerated the same way by the test
+    instead of being stored: values drawn from a seeded CPU generator, parameters visited in sorted name order."""
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in sorted(net.named_parameters()):
+            if not (n.startswith("x1_model.") or n.startswith("x2_model.")):
+                continue
+            bound = 1.0 / np.sqrt(p.shape[-1] if p.dim() > 1 else {0: 768, 3: 512, 6: 512}[int(n.split(".")[2])])
+            p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * bound)
+
+
 if __name__ == "__main__":
     install_shims()
     torch.manual_seed(5)
@@ -255,3 +395,11 @@ if __name__ == "__main__":
     # K1: Enrico jlogits, B=32 D=512 C=20 (frozen encoders: no dfeat)
     golden_ogm("jlogits_enrico_b32", B=32, D=512, C=20, steps=2, seed=19, alpha=0.1, enrico=True)
     golden_modulate("ogm_modulate_small", seed=23)
+    # the per-modality ensemble with OGM-GE (model_type ensemble_ogm_ge)
+    golden_ensemble("ensemble_ogm_b48", B=48, D=512, C=6, steps=3, seed=47, alpha=0.8)
+    golden_ensemble("ensemble_wide_c101", B=40, D=128, C=101, steps=2, seed=53, alpha=0.8)
+    # epoch-end unimodal offset correction of the reference's own LightningModule (utils/BaseModel.py:161-202)
+    golden_epoch_end("epoch_end_c6", n_batches=5, B=64, C=6, seed=59)
+    golden_epoch_end("epoch_end_c101", n_batches=3, B=96, C=101, seed=61)
+    # the Food101 module itself (K4's model): MLP heads on SigLIP embeddings, QMF loss
+    golden_food101("food101_module_b32", B=32, C=101, N=256, steps=2, seed=67)

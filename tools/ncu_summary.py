@@ -16,7 +16,9 @@ with open(out + "_ncu_full_summary.csv", "w", newline="") as f:
     wr.writerow([h[i] for i in idx]); wr.writerow([rows[1][i] for i in idx])
     for r in rows[2:]:
         wr.writerow([r[i] for i in idx])
-names = {"tc_fwd_qmf_kernel": "tc_forward_qmf", "rows_forward_vec_kernel<1": "rows_forward_qmf", "rows_forward_vec_kernel<0": "rows_forward_jlogits",
+names = {"tc_fwd_qmf_kernel": "tc_forward_qmf", "tc_bwd_qmf_kernel": "tc_backward_qmf", "modulate_stats_kernel": "modulate_stats",
+         "modulate_apply_kernel": "modulate_apply", "narrow_kernel<0, 0": "narrow_step_jlogits", "narrow_kernel<1, 1": "narrow_forward_qmf",
+         "narrow_kernel<1, 2": "narrow_backward_qmf", "pool_mean_kernel": "pool_mean", "pool_mean_bwd_kernel": "pool_mean_bwd", "rows_forward_vec_kernel<1": "rows_forward_qmf", "rows_forward_vec_kernel<0": "rows_forward_jlogits",
          "rows_backward_vec_kernel<1": "rows_backward_qmf", "rows_backward_vec_kernel<0": "rows_calibrated",
          "mid_kernel": "step_mid", "finalize_grads_kernel": "finalize_grads", "finalize_stats_kernel": "finalize_stats",
          "rows_forward_reg_kernel<1": "rows_forward_qmf", "rows_forward_reg_kernel<0": "rows_forward_jlogits",
@@ -32,6 +34,10 @@ for r in rows[2:]:
         label = order[len([1 for k in traffic if k in order]) % len(order)]
     if label is None and "tc_heads_forward" in n:
         label = "tc_heads_forward"
+    if label is None and "lf::" in n:
+        import re
+        m = re.search(r"lf::(\w+)", n)
+        label = m.group(1) if m else None
     if label and label not in traffic:
         traffic[label] = int(float(r[ri]) * unit[rows[1][ri]] + float(r[wi]) * unit[rows[1][wi]])
 path = os.path.join(os.path.dirname(out), "traffic.json")
