@@ -49,6 +49,11 @@ bool pdl_enabled() {
   return on;
 }
 
+bool l2_hints_enabled() {
+  static const bool on = getenv("LF_NO_L2_HINTS") == nullptr;
+  return on;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -442,6 +447,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     // the reduction of the split-K partials, db, the calibrated counts (and the optional all-reduce / SGD step) run in the kernel's tail
     const bool tail = dw_tail_plan(a, &splits, &d.block_n);
     d.splits = splits; d.split_stride = (long long)cd; d.balance_m = 0; d.name = "tc_dweight";
+    d.l2_last_use = l2_hints_enabled() ? 3 : 0;          // F and dz are read for the last time in the step
     const bool peer = tail && a->grad_comm && a->batch_global != a->batch;
     if (a->grad_comm && a->batch_global != a->batch && !peer) {
       set_error("grad_comm given but this shape cannot fuse the all-reduce (ask lf_heads_backward_fuses_allreduce first)");

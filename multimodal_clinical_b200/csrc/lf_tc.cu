@@ -349,6 +349,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;                                // ring position / phase, carried across items
+      const uint64_t pol_first = l2_policy_evict_first();
       const int a_boxes = TC_BLOCK_M / p.mn_box, b_boxes = p.block_n / p.mn_box;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const Item w = decode_item(p, item);
@@ -360,18 +361,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           uint8_t* sb = sa + a_bytes;
           mbar_expect_tx(&full_bar[s], (p.a_mn_major ? a_bytes : (uint32_t)p.tile_m * TC_BLOCK_K * 4) + b_bytes);
           const int k0 = w.k_begin + kb * p.kb_elems;
+          const bool ha = (p.l2_last_use & 1) != 0, hb = (p.l2_last_use & 2) != 0;
           if (!p.a_mn_major) {
-            tma_load_2d(mapA, &full_bar[s], sa, k0, w.m0);                      // [32 k x 128 rows]
+            if (ha) tma_load_2d_hint(mapA, &full_bar[s], sa, k0, w.m0, pol_first);
+            else tma_load_2d(mapA, &full_bar[s], sa, k0, w.m0);                 // [32 k x 128 rows]
           } else {
 #pragma unroll
-            for (int i = 0; i < a_boxes; ++i)                                   // [mn_box m x kb_elems k] boxes of 128-B rows
-              tma_load_2d(mapA, &full_bar[s], sa + i * p.mn_box_bytes, w.m0 + p.mn_box * i, k0);
+            for (int i = 0; i < a_boxes; ++i) {                                 // [mn_box m x kb_elems k] boxes of 128-B rows
+              if (ha) tma_load_2d_hint(mapA, &full_bar[s], sa + i * p.mn_box_bytes, w.m0 + p.mn_box * i, k0, pol_first);
+              else tma_load_2d(mapA, &full_bar[s], sa + i * p.mn_box_bytes, w.m0 + p.mn_box * i, k0);
+            }
           }
           if (!p.b_mn_major) {
-            tma_load_2d(mapB, &full_bar[s], sb, k0, w.n0);                      // [32 k x block_n rows]
+            if (hb) tma_load_2d_hint(mapB, &full_bar[s], sb, k0, w.n0, pol_first);
+            else tma_load_2d(mapB, &full_bar[s], sb, k0, w.n0);                 // [32 k x block_n rows]
           } else {
-            for (int i = 0; i < b_boxes; ++i)
-              tma_load_2d(mapB, &full_bar[s], sb + i * p.mn_box_bytes, w.n0 + p.mn_box * i, k0);
+            for (int i = 0; i < b_boxes; ++i) {
+              if (hb) tma_load_2d_hint(mapB, &full_bar[s], sb + i * p.mn_box_bytes, w.n0 + p.mn_box * i, k0, pol_first);
+              else tma_load_2d(mapB, &full_bar[s], sb + i * p.mn_box_bytes, w.n0 + p.mn_box * i, k0);
+            }
           }
           if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
         }
@@ -588,6 +596,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   kps = div_up(kps, p.kb_elems) * p.kb_elems;
   p.k_per_split = kps;
   p.a_mn_major = d.a_mn_major; p.b_mn_major = d.b_mn_major;
+  p.l2_last_use = d.l2_last_use;
   for (int b = 0; b < 2; ++b) { p.out[b] = d.out[b < d.nbatch ? b : 0]; p.bias[b] = d.bias[b < d.nbatch ? b : 0]; }
   p.ld_out = d.ld_out; p.split_stride = d.split_stride;
   // TMA-store epilogue: 16-byte output pitch; the 128-byte store chunks must tile the N tile exactly unless it is

@@ -58,6 +58,7 @@ struct TcGemmParams {
   int mn_box;              // MN elements per MN-major TMA box (128 B): 32 / 64
   int mn_box_bytes;        // bytes of one MN-major box: 128 B x kb_elems rows
   unsigned mn_step, mn_lbo, mn_sbo, mn_lt;   // MN-major UMMA descriptor: bytes per instruction, LBO, SBO, layout type
+  int l2_last_use;         // bit 0 / 1: operand A / B is read for the last time in the step -> loads tagged evict_first
   int tile_m;              // rows per M tile (<= 128): A box rows; smaller tiles balance the item count over the SMs
   int m_tiles, n_tiles, total_items;
   void* out[2];
@@ -87,6 +88,7 @@ struct TcGemmDesc {
   int elem = 4;            // 4 = fp32 operands (TF32 MMA), 2 = bf16 operands
   int out_elem = 4;        // 4 = fp32 output, 2 = bf16 output (TMA-store epilogue only)
   int max_epi_halves = 2;  // 1: never add the second group of epilogue warps (the CTA then leaves room for a concurrent kernel)
+  int l2_last_use = 0;     // bit 0: A, bit 1: B are dead after this GEMM (L2 evict_first hint on their loads)
   int balance_m = 0;           // 1: pick tile_m so that the number of work items is a multiple of the SM count (K-major A, plain-store epilogue only)
   TcTail tail = {};            // tail.on: fused reduction of the split-K partials (needs all CTAs co-resident: grid <= 148)
   const char* name;

@@ -43,6 +43,7 @@ struct TcFwdParams {
   int stages, elem, kb_elems, num_kb, m_tiles;
   int tile_m;              // samples per M tile (<= 128, multiple of 8): chosen so that the tiles fill whole waves of CTAs
   int nb_total;            // partial rows the finalize kernel sums; rows beyond the grid are zeroed here
+  int l2_hints;            // 1: features evict_last, avg / z_df stores streaming (lf_tc_ptx.cuh)
   unsigned long long* trace;   // LF_FWD_TRACE=1: [grid][8] %globaltimer stamps of the roles (printed once, see tc_heads_forward_qmf)
   const float* bias[2];
   float* z[2];
@@ -101,6 +102,7 @@ __device__ __forceinline__ void mask16(float (&v)[16], int c0, int C) {
 // arithmetic, bounded the first versions of this kernel).  The chunk is transposed through a 2 KB per-warp staging
 // tile (16-byte pieces XOR-swizzled by the row so both directions are conflict-free) and written as 8 rows x 64
 // contiguous bytes per instruction.
+template <bool STREAM = false>
 __device__ __forceinline__ void store16_coalesced(float* stg, float* __restrict__ base, int ld, int row0, int B, int c0,
                                                   const float (&v)[16], int lane) {
   float4* mine = reinterpret_cast<float4*>(stg + lane * 16);
@@ -113,7 +115,10 @@ __device__ __forceinline__ void store16_coalesced(float* stg, float* __restrict_
     const int r = (lane >> 2) + 8 * k;
     const float4 t = reinterpret_cast<const float4*>(stg + r * 16)[pc ^ ((r >> 1) & 3)];
     const int row = row0 + r;
-    if (row < B && col < ld) *reinterpret_cast<float4*>(base + (size_t)row * ld + col) = t;
+    if (row < B && col < ld) {
+      if (STREAM) __stcs(reinterpret_cast<float4*>(base + (size_t)row * ld + col), t);       // never read again in the step
+      else *reinterpret_cast<float4*>(base + (size_t)row * ld + col) = t;
+    }
   }
   __syncwarp();
 }
@@ -188,6 +193,7 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
+      const uint64_t pol_last = l2_policy_evict_last();
       bool first = true;
       // (tried: cp.async.bulk.prefetch.tensor of the feature boxes one / two tiles ahead into L2 -- the main loop got
       // 10 % slower, 29 vs 26 us to the last load)
@@ -200,7 +206,8 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(&full_bar[s], (uint32_t)p.tile_m * 128u + b_bytes);
-            tma_load_2d(mapA, &full_bar[s], sa, kb * p.kb_elems, m0);            // [128 B of K x tile_m samples]
+            if (p.l2_hints) tma_load_2d_hint(mapA, &full_bar[s], sa, kb * p.kb_elems, m0, pol_last);
+            else tma_load_2d(mapA, &full_bar[s], sa, kb * p.kb_elems, m0);       // [128 B of K x tile_m samples]
             tma_load_2d(mapW, &full_bar[s], sa + a_bytes, kb * p.kb_elems, 0);   // [128 B of K x block_n classes]
             if (tr && first) { tr[2] = gtimer(); first = false; }
             if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
@@ -302,7 +309,8 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           float av[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) av[i] = (v1[i] + v2[i]) / 2.f;
-          store16_coalesced(stg, p.avg, p.ld_f, row0, row_end, c0, av, lane);
+          if (p.l2_hints) store16_coalesced<true>(stg, p.avg, p.ld_f, row0, row_end, c0, av, lane);
+          else store16_coalesced(stg, p.avg, p.ld_f, row0, row_end, c0, av, lane);
           mask16(av, c0, C);
           max_arg16(av, c0, ma, ia);
         }
@@ -356,7 +364,8 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         add_bias16(v1, sbias + c0); add_bias16(v2, sbias + 128 + c0);
 #pragma unroll
         for (int i = 0; i < 16; ++i) vd[i] = v1[i] * c1 + v2[i] * c2;
-        store16_coalesced(stg, p.zdf, p.ld_f, row0, row_end, c0, vd, lane);
+        if (p.l2_hints) store16_coalesced<true>(stg, p.zdf, p.ld_f, row0, row_end, c0, vd, lane);
+        else store16_coalesced(stg, p.zdf, p.ld_f, row0, row_end, c0, vd, lane);
         mask16(vd, c0, C);
         const float od = md;
         max_arg16(vd, c0, md, idf);
@@ -515,6 +524,7 @@ int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2],
                          cudaStream_t s) {
   TcFwdParams p;
   p.stats = stats; p.sync = stats ? sync : nullptr;
+  p.l2_hints = l2_hints_enabled() ? 1 : 0;
   p.B = B; p.C = C; p.D = D; p.ld_z = ld_z; p.ld_f = ld_f;
   p.block_n = div_up(C, 16) * 16;
   p.elem = elem == 2 ? 2 : 4;
