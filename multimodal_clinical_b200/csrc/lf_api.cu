@@ -49,10 +49,13 @@ bool pdl_enabled() {
   return on;
 }
 
-bool l2_hints_enabled() {
-  static const bool on = getenv("LF_NO_L2_HINTS") == nullptr;
-  return on;
+// bit 0: features evict_last in the fused forward; 1: avg / z_df streaming stores; 2: dF evict_first stores;
+// 3: the dW GEMM's operands evict_first.  LF_NO_L2_HINTS=1 = none, LF_L2_HINTS=<mask> for experiments.
+int l2_hints_mask() {
+  static const int mask = getenv("LF_NO_L2_HINTS") ? 0 : (getenv("LF_L2_HINTS") ? atoi(getenv("LF_L2_HINTS")) : 15);
+  return mask;
 }
+bool l2_hints_enabled() { return l2_hints_mask() != 0; }
 
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -447,7 +450,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     // the reduction of the split-K partials, db, the calibrated counts (and the optional all-reduce / SGD step) run in the kernel's tail
     const bool tail = dw_tail_plan(a, &splits, &d.block_n);
     d.splits = splits; d.split_stride = (long long)cd; d.balance_m = 0; d.name = "tc_dweight";
-    d.l2_last_use = l2_hints_enabled() ? 3 : 0;          // F and dz are read for the last time in the step
+    d.l2_last_use = (l2_hints_mask() & 8) ? 3 : 0;       // F and dz are read for the last time in the step
     const bool peer = tail && a->grad_comm && a->batch_global != a->batch;
     if (a->grad_comm && a->batch_global != a->batch && !peer) {
       set_error("grad_comm given but this shape cannot fuse the all-reduce (ask lf_heads_backward_fuses_allreduce first)");

@@ -67,6 +67,7 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_enabled();
+int l2_hints_mask();
 bool l2_hints_enabled();     // L2 eviction-priority hints of the tensor-pipe step (lf_tc_ptx.cuh); LF_NO_L2_HINTS=1 turns them off
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {

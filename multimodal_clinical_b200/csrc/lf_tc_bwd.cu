@@ -59,7 +59,7 @@ struct TcBwdParams {
   float* dbpart;            // [grid][2][C]
   float* calpart;           // [grid][2]
   float w_joint, w_uni;
-  int l2_hints;             // 1: dF stores and the z reads are tagged evict_first (lf_tc_ptx.cuh)
+  int l2_hints;             // 1: dF stores are tagged evict_first (lf_tc_ptx.cuh)
   unsigned long long* trace;   // LF_BWD_TRACE=1: [grid][16] %globaltimer stamps of the roles
 };
 
@@ -295,7 +295,7 @@ tc_bwd_qmf_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_consta
       for (int k = 0; k < NK; ++k) {
         const int qc = l + G * k;
         v1[k] = make_float4(0.f, 0.f, 0.f, 0.f); v2[k] = v1[k];
-        if (qc < nq) { v1[k] = __ldcs(z1p + qc); v2[k] = __ldcs(z2p + qc); }      // last read of z in the step: streaming
+        if (qc < nq) { v1[k] = __ldg(z1p + qc); v2[k] = __ldg(z2p + qc); }
       }
       const int y = (int)p.label[b];
       const float c1 = p.conf[b], c2 = p.conf[B + b];
@@ -449,7 +449,7 @@ int tc_backward_qmf(const RowsArgs& a, const void* const w16[2], void* const dfe
   for (int m = 0; m < 2; ++m) p.z[m] = a.z[m];
   p.conf = a.conf; p.rowstat = a.rowstat; p.qmf_g = a.qmf_g; p.ema_off = a.ema_off; p.label = a.label;
   p.dbpart = a.dbpart; p.calpart = a.calpart; p.w_joint = a.w_joint; p.w_uni = a.w_uni;
-  p.l2_hints = l2_hints_enabled() ? 1 : 0;
+  p.l2_hints = (l2_hints_mask() & 4) ? 1 : 0;
   static unsigned long long* trace_buf = nullptr;
   static int trace_calls = 0;
   p.trace = nullptr;

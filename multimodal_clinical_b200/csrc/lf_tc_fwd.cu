@@ -43,7 +43,7 @@ struct TcFwdParams {
   int stages, elem, kb_elems, num_kb, m_tiles;
   int tile_m;              // samples per M tile (<= 128, multiple of 8): chosen so that the tiles fill whole waves of CTAs
   int nb_total;            // partial rows the finalize kernel sums; rows beyond the grid are zeroed here
-  int l2_hints;            // 1: features evict_last, avg / z_df stores streaming (lf_tc_ptx.cuh)
+  int l2_hints;            // bit 0: features evict_last, bit 1: avg / z_df stores streaming (lf_tc_ptx.cuh)
   unsigned long long* trace;   // LF_FWD_TRACE=1: [grid][8] %globaltimer stamps of the roles (printed once, see tc_heads_forward_qmf)
   const float* bias[2];
   float* z[2];
@@ -206,7 +206,7 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(&full_bar[s], (uint32_t)p.tile_m * 128u + b_bytes);
-            if (p.l2_hints) tma_load_2d_hint(mapA, &full_bar[s], sa, kb * p.kb_elems, m0, pol_last);
+            if (p.l2_hints & 1) tma_load_2d_hint(mapA, &full_bar[s], sa, kb * p.kb_elems, m0, pol_last);
             else tma_load_2d(mapA, &full_bar[s], sa, kb * p.kb_elems, m0);       // [128 B of K x tile_m samples]
             tma_load_2d(mapW, &full_bar[s], sa + a_bytes, kb * p.kb_elems, 0);   // [128 B of K x block_n classes]
             if (tr && first) { tr[2] = gtimer(); first = false; }
@@ -309,7 +309,7 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           float av[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) av[i] = (v1[i] + v2[i]) / 2.f;
-          if (p.l2_hints) store16_coalesced<true>(stg, p.avg, p.ld_f, row0, row_end, c0, av, lane);
+          if (p.l2_hints & 2) store16_coalesced<true>(stg, p.avg, p.ld_f, row0, row_end, c0, av, lane);
           else store16_coalesced(stg, p.avg, p.ld_f, row0, row_end, c0, av, lane);
           mask16(av, c0, C);
           max_arg16(av, c0, ma, ia);
@@ -364,7 +364,7 @@ tc_fwd_qmf_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         add_bias16(v1, sbias + c0); add_bias16(v2, sbias + 128 + c0);
 #pragma unroll
         for (int i = 0; i < 16; ++i) vd[i] = v1[i] * c1 + v2[i] * c2;
-        if (p.l2_hints) store16_coalesced<true>(stg, p.zdf, p.ld_f, row0, row_end, c0, vd, lane);
+        if (p.l2_hints & 2) store16_coalesced<true>(stg, p.zdf, p.ld_f, row0, row_end, c0, vd, lane);
         else store16_coalesced(stg, p.zdf, p.ld_f, row0, row_end, c0, vd, lane);
         mask16(vd, c0, C);
         const float od = md;
@@ -524,7 +524,7 @@ int tc_heads_forward_qmf(const void* const feat[2], const void* const weight[2],
                          cudaStream_t s) {
   TcFwdParams p;
   p.stats = stats; p.sync = stats ? sync : nullptr;
-  p.l2_hints = l2_hints_enabled() ? 1 : 0;
+  p.l2_hints = l2_hints_mask() & 3;
   p.B = B; p.C = C; p.D = D; p.ld_z = ld_z; p.ld_f = ld_f;
   p.block_n = div_up(C, 16) * 16;
   p.elem = elem == 2 ? 2 : 4;
