@@ -229,6 +229,8 @@ def run_reference(args, w, rank, world):
                                        f"samples/s does not depend on the batch) of the oracle port on {cores} host threads"},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    # the LITERAL reference modules beside the vectorised port (the port is the harder baseline and stays the `value`)
+    line["cpu_baseline"]["literal_reference"] = literal_reference(w)
     print(json.dumps(line), flush=True)
 
 
@@ -241,6 +243,22 @@ def workload_config(w, args, world):
             "l2": ("inputs rotate over buffer sets totalling > 2x the 126 MB L2"
                    if 2 * w["B"] * w["D"] * (2 if args.precision == "bf16" else 4) * 8 >= 2 * L2_BYTES
                    else "256 MB L2 flush between steps, outside the per-step CUDA-event brackets")}
+
+
+def literal_reference(w, budget_s=8.0):
+    """The UNMODIFIED reference modules (staged under oracle/_ref by oracle/vendor_ref.py) on the host cores, at a bounded
+    batch: QMF.reg_loss materialises (B,B) matrices, so its cost per sample grows with B."""
+    try:
+        from oracle import literal
+        if not literal.available():
+            return {"unavailable": "oracle/_ref is not staged (run oracle/vendor_ref.py where /root/reference exists)"}
+        Bs = min(w["B"], 8192 if w["mode"] == "qmf" else 32768)
+        v, n, dt = literal.time_step(w["mode"], Bs, w["D"], w["C"], w["N"], w["alpha"], budget_s=budget_s)
+        return {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": f"{n} steps of B={Bs} through the reference's own FusionNet.forward / backward / EMA.update (identity encoders) "
+                          f"in {dt:.1f} s; quadratic in B for QMF, so the full batch would be slower per sample"}
+    except Exception as e:                                     # never let the baseline take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
 def cpu_baseline(w, budget_s=20.0):
@@ -265,7 +283,8 @@ def cpu_baseline(w, budget_s=20.0):
             break
     cores = torch.get_num_threads()
     return {"value": w["B"] * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{n} full-batch steps (B={w['B']}) of oracle/late_fusion.py (torch CPU fp32) in {dt:.1f} s"}
+            "sample": f"{n} full-batch steps (B={w['B']}) of oracle/late_fusion.py (torch CPU fp32) in {dt:.1f} s",
+            "literal_reference": literal_reference(w)}
 
 
 # ------------------------------------------------------------------------------------------------
