@@ -48,7 +48,6 @@ def _install():
             sy.Idx = object
             sys.modules["sympy"] = sy
     sys.path.insert(0, vendor_ref.DST)
-    torch.Tensor.cuda = lambda self, *a, **k: self      # CPU run of QMF.py:63,66
     _installed = True
 
 
@@ -57,6 +56,15 @@ def time_step(mode: str, B: int, D: int, C: int, N, alpha, budget_s: float = 15.
     -> (samples/s, steps, seconds).  The reference is quadratic in B (QMF.reg_loss builds (B,B) matrices, ogm_ge's
     score loop is O(B^2 C) Python): callers pass a bounded B and say so."""
     _install()
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self      # CPU run of QMF.py:63,66; restored below (the caller may use a GPU later)
+    try:
+        return _time_step(mode, B, D, C, N, alpha, budget_s, max_steps)
+    finally:
+        torch.Tensor.cuda = real_cuda
+
+
+def _time_step(mode, B, D, C, N, alpha, budget_s, max_steps):
     from utils.EMA import EMA
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(7)
