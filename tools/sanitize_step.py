@@ -16,6 +16,28 @@ for mode, B, D, Cn, N, prec in cases:
                    inp["y"].cuda(), idx=inp["idx"].cuda() if N else None, ogm_alpha=0.5 if not N else None)
     torch.cuda.synchronize()
     print(mode, B, D, Cn, prec, "loss", float(o.loss), flush=True)
+# round-2 paths: in-step SGD (dW tail), ensemble loss, a QMF global batch larger than the step_mid grid, pooling, epoch-end kernels
+inp = O.make_inputs(300, 768, 101, seed=2, n_data=700)
+e = LateFusionStep(101, mode="qmf", n_data=700, device="cuda:0", precision="bf16")
+e.enable_sgd(lr=1e-2)
+W = [inp["W1"].cuda(), inp["W2"].cuda()]; b = [inp["b1"].cuda(), inp["b2"].cuda()]
+for s in range(2):
+    o = e.step([inp["f1"].cuda(), inp["f2"].cuda()], W, b, inp["y"].cuda(), idx=inp["idx"].cuda())
+torch.cuda.synchronize(); print("in-step sgd loss", float(o.loss), flush=True)
+inp = O.make_inputs(70, 512, 6, seed=3)
+e = LateFusionStep(6, mode="ensemble", device="cuda:0")
+o = e.step([inp["f1"].cuda(), inp["f2"].cuda()], [inp["W1"].cuda(), inp["W2"].cuda()], [inp["b1"].cuda(), inp["b2"].cuda()], inp["y"].cuda(), ogm_alpha=0.5)
+torch.cuda.synchronize(); print("ensemble loss", float(o.loss), flush=True)
+inp = O.make_inputs(1500, 64, 6, seed=4, n_data=100)          # N small -> one-CTA step_mid grid, 3 batch positions per thread
+e = LateFusionStep(6, mode="qmf", n_data=100, device="cuda:0")
+o = e.step([inp["f1"].cuda(), inp["f2"].cuda()], [inp["W1"].cuda(), inp["W2"].cuda()], [inp["b1"].cuda(), inp["b2"].cuda()], inp["y"].cuda(), idx=inp["idx"].cuda())
+torch.cuda.synchronize(); print("looping step_mid loss", float(o.loss), flush=True)
+from multimodal_clinical_b200.cremad._pool import pool_features
+a = torch.randn(3, 130, 7, 7, device="cuda", requires_grad=True); v = torch.randn(9, 130, 7, 7, device="cuda", requires_grad=True)
+pa, pv = pool_features(a, v); (pa.sum() + pv.sum()).backward()
+from multimodal_clinical_b200.utils.BaseModel import epoch_offset_correction
+off, acc = epoch_offset_correction(torch.randn(333, 2, 11, device="cuda"), torch.randint(0, 11, (333,), device="cuda"))
+torch.cuda.synchronize(); print("pool / epoch ok", acc.tolist(), flush=True)
 g = [torch.randn(64, 3, 7, 7, device="cuda"), torch.randn(128, 64, 3, 3, device="cuda"), torch.randn(5, 5, 1, 1, device="cuda")]
 e = LateFusionStep(6, mode="jlogits", device="cuda:0")
 e.modulate(g, which=0, modulation="OGM_GE", seed=1, offset=0)
