@@ -163,6 +163,35 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def pin_to_gpu_numa_node(index):
+    """Bind this rank's host threads (and, by first touch, the pinned staging buffers it allocates afterwards) to the NUMA
+    node its GPU hangs off: with every rank on node 0 the host-fed (e2e) runs at 8 GPUs were bounded by one socket's
+    memory bandwidth (round 1: 61 M samples/s at 8 GPUs against 72 M at 4).  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = bus.lower()
+        if len(dev.split(":")[0]) == 8:                      # 00000000:1b:00.0 -> 0000:1b:00.0
+            dev = dev[4:]
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"numa node {node}: no allowed cpus"
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node} ({len(allowed)} cpus)"
+    except Exception as e:
+        return f"unpinned ({type(e).__name__})"
+
+
 def make_batches(w, n_sets, device, seed):
     g = torch.Generator().manual_seed(seed)
     sets = []
@@ -342,6 +371,7 @@ def main():
     # on a GPU meanwhile and the host cores are not shared with the timed region
     cpu_line = cpu_baseline(w) if (rank == 0 and not args.no_cpu_baseline) else None
 
+    numa = pin_to_gpu_numa_node(local) if world > 1 else "single process"
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
@@ -539,7 +569,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
                 "data": "synthetic", "config": workload_config(w, args, world),
-                "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "host_affinity": numa},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
                 "step_roofline": {"alg_bytes_per_sample": step_alg_bytes_per_sample(w, fe), "achieved": step_gbs,
                                   "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak},
