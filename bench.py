@@ -326,7 +326,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "bf16"],
                     help="auto: bf16 (the reference's own bf16-mixed mode: bf16 features, fp32 accumulation) for wide heads "
-                         "(C >= 32), exact fp32 FMA for narrow heads; tf32 = fp32 features consumed as TF32")
+                         "(C >= 32), exact fp32 FMA for narrow heads; tf32 = fp32 features consumed as TF32; fp32 on wide heads = 3xTF32 on the tensor pipe")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-sgd", action="store_true",
@@ -384,7 +384,7 @@ def main():
     W, b = head_params(w)
     W = [x.to(dev) for x in W]; b = [x.to(dev) for x in b]
     # SGD on the heads inside the step: in the tail of the dW kernel, after the gradient all-reduce on several GPUs
-    fused_sgd = (not args.no_sgd) and args.precision != "fp32" and w["C"] >= 32
+    fused_sgd = (not args.no_sgd) and w["C"] >= 32
     args.fused_sgd = fused_sgd
     parity = None
     if not args.no_parity_check:

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 10
+#define LF_ABI_VERSION 11
 
 /* error codes */
 #define LF_OK 0
@@ -394,6 +394,11 @@ int32_t lf_profile_report(char* buf, int32_t buf_bytes);
 int lf_debug_tc_gemm(const float* A, const float* B, const float* bias, float* out, int32_t M, int32_t N,
                      int32_t K, int32_t lda, int32_t ldb, int32_t ld_out, int32_t a_mn_major,
                      int32_t b_mn_major, int32_t block_n, int32_t splits, int64_t split_stride, void* stream);
+/* Same hook through the 3xTF32 split (hi/lo tf32 halves formed in shared memory, three MMAs per k-step): the kernel
+ * behind LF_PREC_FP32 on wide heads (ABI v11).  Parity class 1e-5. */
+int lf_debug_tc_gemm_x3(const float* A, const float* B, const float* bias, float* out, int32_t M, int32_t N,
+                        int32_t K, int32_t lda, int32_t ldb, int32_t ld_out, int32_t a_mn_major,
+                        int32_t b_mn_major, int32_t block_n, int32_t splits, int64_t split_stride, void* stream);
 
 /*
  * Stand-alone pieces of the reference's algorithm API, for callers that use existing_algos/ directly

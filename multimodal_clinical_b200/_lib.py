@@ -138,6 +138,8 @@ SIGNATURES = {
     "lf_profile_report": (C.c_int32, [C.c_char_p, C.c_int32]),
     "lf_debug_tc_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 10 +
                          [C.c_int64, C.c_void_p]),
+    "lf_debug_tc_gemm_x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 10 +
+                         [C.c_int64, C.c_void_p]),
     "lf_debug_tc_gemm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 10 + [C.c_int64, C.c_int32, C.c_void_p]),
     "lf_last_error": (C.c_char_p, []),
     "lf_abi_version": (C.c_int32, []),

@@ -133,7 +133,12 @@ static float* rowstat_ptr(void* base, int B, int D, int C) {
 }
 
 // The tensor pipe only pays for wide heads (C = 6/20 is HBM-bound on FMA).
-static bool use_tensor_pipe(const LfHeadsArgs* a) { return a->precision != LF_PREC_FP32 && a->classes >= 32; }
+// LF_PREC_FP32 on wide heads takes the same kernels through the 3xTF32 operand split (fp32-grade products, parity class
+// 1e-5) when the dL/dlogits scratch has the TMA row pitch; with the legacy dense pitch it stays on the FMA GEMMs.
+static bool use_x3(const LfHeadsArgs* a) {
+  return a->precision == LF_PREC_FP32 && a->classes >= 32 && a->ld_dlogits != 0 && a->ld_dlogits % 4 == 0 && !getenv("LF_NO_X3");
+}
+static bool use_tensor_pipe(const LfHeadsArgs* a) { return (a->precision != LF_PREC_FP32 && a->classes >= 32) || use_x3(a); }
 static bool is_bf16(const LfHeadsArgs* a) { return a->precision == LF_PREC_BF16; }
 // Narrow heads (C <= 32, HBM-bound on FMA): one fused kernel per pass over the features (lf_narrow.cu).
 static bool use_narrow(const LfHeadsArgs* a) {
@@ -329,7 +334,7 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
     }
     {
       const int ldz = a->ld_logits > 0 ? a->ld_logits : a->classes, ldf = a->ld_fused > 0 ? a->ld_fused : a->classes;
-      if (tc_fwd_supported(a->mode, a->batch, a->dim, a->classes, ldz, ldf, d.elem)) {
+      if (!use_x3(a) && tc_fwd_supported(a->mode, a->batch, a->dim, a->classes, ldz, ldf, d.elem)) {
         // QMF, 32 <= C <= 128: the row math runs in the GEMM's epilogue (one thread per sample straight from TMEM)
         int grid = 0;
         const void* fp[2] = {a->feat[0], a->feat[1]};
@@ -349,7 +354,7 @@ extern "C" int lf_heads_forward(const LfHeadsArgs* a, void* stream) {
     d.lda = a->dim; d.ldb = a->dim; d.ld_out = a->ld_logits > 0 ? a->ld_logits : a->classes;
     d.a_mn_major = 0; d.b_mn_major = 0; d.block_n = tc_block_n(a->classes);
     if (a->classes > d.block_n) d.block_n = div_up(d.block_n, 32) * 32;     // several N tiles: whole 128-byte store chunks
-    d.splits = 1; d.split_stride = 0; d.balance_m = 1; d.name = "tc_logits";
+    d.splits = 1; d.split_stride = 0; d.balance_m = 1; d.name = "tc_logits"; d.x3 = use_x3(a);
     rc = tc_gemm(d, s);
   } else {
     rc = gemm_logits(g, 2, s);
@@ -421,7 +426,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
       d.M = a->batch; d.N = a->dim; d.K = a->classes;
       d.lda = ldz; d.ldb = a->dim; d.ld_out = a->dim;
       d.a_mn_major = 0; d.b_mn_major = 1; d.block_n = div_up(tc_block_n(a->dim), 64) * 64;
-      d.splits = 1; d.split_stride = 0; d.balance_m = 0; d.name = "tc_dfeat";
+      d.splits = 1; d.split_stride = 0; d.balance_m = 0; d.name = "tc_dfeat"; d.x3 = use_x3(a);
       // sharded runs (phase 2) overlap dfeat with the peer all-reduce on a side stream: keep the CTA small enough
       // (192 threads) for the all-reduce CTAs to be co-resident, or the exchange waits for dfeat to drain
       d.max_epi_halves = phase == 2 ? 1 : 2;
@@ -449,7 +454,7 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     d.a_mn_major = 1; d.b_mn_major = 1;
     // the reduction of the split-K partials, db, the calibrated counts (and the optional all-reduce / SGD step) run in the kernel's tail
     const bool tail = dw_tail_plan(a, &splits, &d.block_n);
-    d.splits = splits; d.split_stride = (long long)cd; d.balance_m = 0; d.name = "tc_dweight";
+    d.splits = splits; d.split_stride = (long long)cd; d.balance_m = 0; d.name = "tc_dweight"; d.x3 = use_x3(a);
     d.l2_last_use = (l2_hints_mask() & 8) ? 3 : 0;       // F and dz are read for the last time in the step
     const bool peer = tail && a->grad_comm && a->batch_global != a->batch;
     if (a->grad_comm && a->batch_global != a->batch && !peer) {

@@ -22,6 +22,11 @@
 //             shared->global), so the store of tile i overlaps the loads and MMAs of tile i+1.
 //             Outputs whose row pitch is not a multiple of 16 B (logits, C = 309) take a transposing path
 //             with 128-byte coalesced stores instead.
+// Exact-fp32 tier (TcGemmParams::x3, LF_PREC_FP32 on wide heads): 3xTF32.  Four converter warps sit between the TMA
+// producer and the MMA issuer: they split every fp32 word of a landed stage into hi = tf32(x) (written back in place) and
+// lo = tf32(x - hi) (a second copy of the stage with the same swizzled layout -- the split is element-wise, so it is
+// layout-agnostic and serves K-major and MN-major operands alike), and the issuer runs lo*hi + hi*lo + hi*hi per k-step
+// into the same fp32 accumulator.  The dropped lo*lo term and the rounding of lo are ~2^-23 of a product.
 // Ragged edges: TMA zero-fills out-of-bounds loads and clips stores, so C = 101/309 and K = 101/309 need
 // no padding copies.  Parity class: 2e-2 (tests/test_tc_gemm_gpu.py, tests/test_parity_gpu.py).
 #include <cuda.h>
@@ -34,10 +39,12 @@
 
 namespace lf {
 
-constexpr int TC_THREADS = 320;                          // producer warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kX3ChunkK = 512;                           // 3xTF32: longest K accumulated in TMEM before the tile is flushed (see TcGemmParams::chunks)
+constexpr int kConvThreads = 256;                        // 3xTF32: eight converter warps
+constexpr int TC_THREADS = 448;                          // producer warp, MMA warp, 2 x 4 epilogue warps; x3: 4 epilogue + 8 converter warps
 // staging: two [128 rows x 128 B] store boxes per epilogue half (TcGemmParams::epi_halves = 1 or 2)
 
-struct Item { int batch, split, m0, n0, k_begin, num_kb, k_end; };
+struct Item { int batch, split, m0, n0, k_begin, num_kb, k_end, chunk; };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
   unsigned v;
@@ -258,10 +265,11 @@ __device__ __forceinline__ Item decode_item(const TcGemmParams& p, int item) {
   Item it;
   const int n_t = item % p.n_tiles; int r = item / p.n_tiles;
   const int m_t = r % p.m_tiles; r /= p.m_tiles;
-  it.split = r % p.splits; it.batch = r / p.splits;
+  it.split = r % p.splits; r /= p.splits;
+  it.batch = r % p.nbatch; it.chunk = r / p.nbatch;     // chunks > 1: grid == items per chunk, so a CTA walks one tile's chunks
   it.m0 = m_t * p.tile_m; it.n0 = n_t * p.block_n;
-  it.k_begin = it.split * p.k_per_split;
-  it.k_end = min(p.K, it.k_begin + p.k_per_split);
+  it.k_begin = it.split * p.k_per_split + it.chunk * p.k_per_chunk;
+  it.k_end = min(min(p.K, (it.split + 1) * p.k_per_split), it.k_begin + p.k_per_chunk);
   it.num_kb = it.k_end > it.k_begin ? (it.k_end - it.k_begin + p.kb_elems - 1) / p.kb_elems : 0;
   return it;
 }
@@ -274,10 +282,12 @@ __device__ __forceinline__ Item decode_item(const TcGemmParams& p, int item) {
 //   MN-major: rows are k; fp32: 128B swizzle with 32-byte atoms, 4 k-rows per atom (SBO 512), 32-element MN
 //   chunks 4096 B apart (LBO), 1024 B per instruction; bf16: plain 128B swizzle, 8 k-rows per atom (SBO 1024),
 //   64-element MN chunks 8192 B apart, 2048 B per instruction.
-template <bool TF32>
+template <bool TF32, bool X3>
 __device__ __forceinline__ void mma_issue_loop(const TcGemmParams& p, uint8_t* smem, uint32_t stage_bytes, uint32_t a_bytes,
                                                uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tmem_full_bar,
                                                uint64_t* tmem_empty_bar, uint32_t tmem_base) {
+  // X3: full_bar is the converters' barrier; the lo copies of both operands sit half a stage above the hi ones
+  const uint64_t lo_off = (uint64_t)((stage_bytes / 2) >> 4);
   const int stages = p.stages;
   const uint32_t idesc = TF32 ? make_idesc_tf32(TC_BLOCK_M, p.block_n, p.a_mn_major, p.b_mn_major)
                               : make_idesc_bf16(TC_BLOCK_M, p.block_n, p.a_mn_major, p.b_mn_major);
@@ -300,7 +310,11 @@ __device__ __forceinline__ void mma_issue_loop(const TcGemmParams& p, uint8_t* s
       uint64_t da = descA0 + (uint64_t)(sa >> 4), db = descB0 + (uint64_t)((sa + a_bytes) >> 4);
       const int ksteps = krem >= p.kb_elems ? 4 : (krem + p.umma_k - 1) / p.umma_k;       // 32 B of K per instruction
       for (int k = 0; k < ksteps; ++k, da += stepA, db += stepB) {
-        if (TF32) umma_tf32(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        if (X3) {                                 // small terms first, all three into the same fp32 accumulator
+          umma_tf32(acc, da + lo_off, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_tf32(acc, da, db + lo_off, idesc, 1u);
+          umma_tf32(acc, da, db, idesc, 1u);
+        } else if (TF32) umma_tf32(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         else umma_f16(acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
       }
       umma_commit(&empty_bar[s]);               // frees the stage once the MMAs above have read it
@@ -318,13 +332,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int stages = p.stages;
   const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4;
   const uint32_t b_bytes = (uint32_t)p.block_n * TC_BLOCK_K * 4;
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+  const uint32_t half_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+  const uint32_t stage_bytes = p.x3 ? 2 * half_bytes : half_bytes;   // x3: [A hi | B hi | A lo | B lo]
   uint8_t* staging = smem + (size_t)stages * stage_bytes;            // 1024-aligned (stage_bytes is)
   uint64_t* full_bar = (uint64_t*)(staging + (size_t)2 * p.epi_halves * TC_BLOCK_M * 128);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;                      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                      // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty_bar + 2);
+  uint64_t* conv_bar = tmem_empty_bar + 2;                           // [stages], x3 only: stage split into hi / lo
+  uint32_t* tmem_slot = (uint32_t*)(conv_bar + 8);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (p.tail.trace && threadIdx.x == 0) { unsigned long long x; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(x)); p.tail.trace[(size_t)blockIdx.x * 8] = x; }
@@ -333,7 +349,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapB0);
     if (p.nbatch > 1) { tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB1); }
     if (p.tma_store) { tma_prefetch_desc(&mapO0); if (p.nbatch > 1) tma_prefetch_desc(&mapO1); }
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&conv_bar[s], kConvThreads / 32); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4 * p.epi_halves); }
     fence_barrier_init();
   }
@@ -388,8 +404,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      if (p.elem == 4) mma_issue_loop<true>(p, smem, stage_bytes, a_bytes, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
-      else mma_issue_loop<false>(p, smem, stage_bytes, a_bytes, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+      if (p.x3) mma_issue_loop<true, true>(p, smem, stage_bytes, a_bytes, conv_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+      else if (p.elem == 4) mma_issue_loop<true, false>(p, smem, stage_bytes, a_bytes, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+      else mma_issue_loop<false, false>(p, smem, stage_bytes, a_bytes, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
     }
   } else if (warp < 2 + 4 * p.epi_halves) {
     // ===================== epilogue =====================
@@ -405,6 +422,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       tc_fence_after();
       const uint32_t acc = tmem_base + buf * (uint32_t)p.acc_cols + ((uint32_t)(q * 32) << 16);
       const CUtensorMap* mapO = w.batch == 0 ? &mapO0 : &mapO1;
+      // a later chunk adds onto what the previous one stored: that store (or reduce) has to be complete, not just read
+      if (w.chunk > 0 && et == 0) tma_store_wait_all();
       if (p.tma_store) {
         const int ccols = 128 / p.out_elem;                 // output columns per 128-byte staging row: 32 fp32 / 64 bf16
         for (int c0 = half * ccols; c0 < p.block_n; c0 += p.epi_halves * ccols, ++cc) {
@@ -413,7 +432,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             float v[32];
             tmem_ld16(acc + c0, v);
             tmem_ld16(acc + c0 + 16, v + 16);
-            const float* bias = p.bias[w.batch];
+            const float* bias = w.chunk == 0 ? p.bias[w.batch] : nullptr;
             if (bias) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) { const int col = w.n0 + c0 + i; v[i] += col < p.N ? __ldg(bias + col) : 0.f; }
@@ -442,7 +461,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           fence_proxy_async();
           named_bar_sync(1 + half, 128);
           if (et == 0) {
-            tma_store_3d(mapO, box, w.n0 + c0, w.m0, w.split);
+            if (w.chunk > 0) tma_reduce_add_3d(mapO, box, w.n0 + c0, w.m0, w.split);
+            else tma_store_3d(mapO, box, w.n0 + c0, w.m0, w.split);
             tma_store_commit();
           }
         }
@@ -481,6 +501,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (p.tma_store && et == 0) {
       tma_store_wait_all();
       if (p.tail.on) asm volatile("fence.proxy.async;" ::: "memory");    // async-proxy stores -> generic-proxy readers of the tail
+    }
+  }
+  else if (p.x3) {
+    // ===================== 3xTF32 converters (warps 6-13; x3 runs one epilogue half) =====================
+    const int ct = threadIdx.x - (64 + 128 * p.epi_halves);          // 0..kConvThreads-1
+    const uint32_t n16 = half_bytes >> 4;                            // 16-byte words of [A | B] in one stage
+    uint32_t s = 0, ph = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const Item w = decode_item(p, item);
+      for (int kb = 0; kb < w.num_kb; ++kb) {
+        mbar_wait(&full_bar[s], ph);               // every lane polls: measured faster than one polling lane + __syncwarp here
+        uint4* hi = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes);
+        uint4* lo = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes + half_bytes);
+        // loads of a whole batch first: the tensor core's operand reads keep the shared-memory port busy, so an LDS takes
+        // hundreds of cycles here, and the compiler cannot hoist loads over the (possibly aliasing) stores by itself
+        for (uint32_t i0 = ct; i0 < n16; i0 += kConvThreads * 8) {
+          uint4 x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const uint32_t i = i0 + j * kConvThreads; if (i < n16) x[j] = hi[i]; }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t i = i0 + j * kConvThreads;
+            if (i < n16) {
+              uint4 h, l;
+              split_tf32(x[j].x, h.x, l.x); split_tf32(x[j].y, h.y, l.y); split_tf32(x[j].z, h.z, l.z); split_tf32(x[j].w, h.w, l.w);
+              hi[i] = h; lo[i] = l;
+            }
+          }
+        }
+        fence_proxy_async();                       // generic-proxy writes -> the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_bar[s]);
+        if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
+      }
     }
   }
   tc_fence_before();
@@ -582,6 +636,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   TcGemmParams p;
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.elem = d.elem == 2 ? 2 : 4;
+  p.x3 = (d.x3 && p.elem == 4) ? 1 : 0;
   p.out_elem = d.out_elem == 2 ? 2 : 4;
   p.kb_elems = 128 / p.elem; p.umma_k = 32 / p.elem; p.mn_box = 128 / p.elem;
   p.mn_box_bytes = 128 * p.kb_elems;
@@ -595,6 +650,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   int kps = div_up(d.K, p.splits);
   kps = div_up(kps, p.kb_elems) * p.kb_elems;
   p.k_per_split = kps;
+  p.chunks = 1; p.k_per_chunk = kps;
   p.a_mn_major = d.a_mn_major; p.b_mn_major = d.b_mn_major;
   p.l2_last_use = d.l2_last_use;
   for (int b = 0; b < 2; ++b) { p.out[b] = d.out[b < d.nbatch ? b : 0]; p.bias[b] = d.bias[b < d.nbatch ? b : 0]; }
@@ -623,6 +679,14 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   }
   p.m_tiles = div_up(d.M, p.tile_m);
   p.total_items = p.m_tiles * p.n_tiles * p.splits * d.nbatch;
+  int grid_fixed = 0;
+  if (p.x3 && kps > kX3ChunkK && p.tma_store && p.total_items <= 148) {
+    // 3xTF32 with a long K per work item (the split-K dW GEMM): bound the accumulation chain in TMEM
+    p.chunks = div_up(kps, kX3ChunkK);
+    p.k_per_chunk = div_up(div_up(kps, p.chunks), p.kb_elems) * p.kb_elems;
+    grid_fixed = p.total_items;
+    p.total_items *= p.chunks;
+  }
 
   CUtensorMap mA[2], mB[2], mO[2];
   for (int b = 0; b < d.nbatch; ++b) {
@@ -645,12 +709,13 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
 
   const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4;
   const uint32_t b_bytes = (uint32_t)d.block_n * TC_BLOCK_K * 4;
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+  const uint32_t stage_bytes = (a_bytes + ((b_bytes + 1023) & ~1023u)) * (p.x3 ? 2 : 1);
   // the second epilogue half pays when the epilogue bounds the kernel: short K (tc_dfeat of a <= 128-way head: ten
   // 128 x 256 output tiles per CTA, two k-blocks each); with long K its two extra staging boxes cost a pipeline stage
-  p.epi_halves = (p.tma_store && d.K <= 128 && d.max_epi_halves >= 2) ? 2 : 1;
+  // (x3: warps 6-9 are the converters, so one half)
+  p.epi_halves = (p.tma_store && d.K <= 128 && d.max_epi_halves >= 2 && !p.x3) ? 2 : 1;
   const size_t staging_bytes = (size_t)2 * p.epi_halves * TC_BLOCK_M * 128;
-  const size_t fixed = staging_bytes + 256;
+  const size_t fixed = staging_bytes + 320;
   int stages = 8;
   while (stages > 2 && (size_t)stages * stage_bytes + fixed > 226 * 1024) --stages;
   p.stages = stages;
@@ -660,7 +725,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
     cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     attr_set = true;
   }
-  const int grid = p.total_items < 148 ? p.total_items : 148;
+  const int grid = grid_fixed ? grid_fixed : (p.total_items < 148 ? p.total_items : 148);
   p.tail = d.tail;
   static unsigned long long* trace_buf = nullptr;
   static int trace_calls = 0;
@@ -672,7 +737,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
     // the tail's grid barrier needs every CTA resident at once: a cooperative launch guarantees it (or fails)
     if (!p.tma_store || p.tail.n % 4) { set_error("tc_gemm: the fused dW tail needs the TMA-store epilogue and C*D %% 4 == 0"); return LF_ERR_BAD_ARG; }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 128 * p.epi_halves); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 128 * p.epi_halves + kConvThreads * p.x3); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
@@ -696,7 +761,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
     }
     return check_launch(d.name);
   }
-  LF_LAUNCH(d.name, s, launch_pdl(tc_gemm_kernel, dim3(grid), dim3(64 + 128 * p.epi_halves), smem, s, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p));
+  LF_LAUNCH(d.name, s, launch_pdl(tc_gemm_kernel, dim3(grid), dim3(64 + 128 * p.epi_halves + kConvThreads * p.x3), smem, s, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p));
   return check_launch(d.name);
 }
 
@@ -717,17 +782,33 @@ extern "C" int lf_debug_tc_gemm16(const void* A, const void* B, void* out, int32
   return lf::tc_gemm(d, (cudaStream_t)stream);
 }
 
-extern "C" int lf_debug_tc_gemm(const float* A, const float* B, const float* bias, float* out, int32_t M, int32_t N,
-                                int32_t K, int32_t lda, int32_t ldb, int32_t ld_out, int32_t a_mn_major,
-                                int32_t b_mn_major, int32_t block_n, int32_t splits, int64_t split_stride,
-                                void* stream) {
+static int debug_tc_gemm32(const float* A, const float* B, const float* bias, float* out, int32_t M, int32_t N,
+                           int32_t K, int32_t lda, int32_t ldb, int32_t ld_out, int32_t a_mn_major,
+                           int32_t b_mn_major, int32_t block_n, int32_t splits, int64_t split_stride,
+                           void* stream, int x3) {
   lf::TcGemmDesc d;
+  d.x3 = x3;
   d.nbatch = 1;
   d.A[0] = A; d.B[0] = B; d.bias[0] = bias; d.out[0] = out;
   d.A[1] = A; d.B[1] = B; d.bias[1] = bias; d.out[1] = out;
   d.elem = 4; d.out_elem = 4;
   d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ld_out = ld_out;
   d.a_mn_major = a_mn_major; d.b_mn_major = b_mn_major; d.block_n = block_n;
-  d.splits = splits; d.split_stride = split_stride; d.balance_m = 0; d.name = "tc_gemm_debug";
+  d.splits = splits; d.split_stride = split_stride; d.balance_m = 0; d.name = x3 ? "tc_gemm_x3_debug" : "tc_gemm_debug";
   return lf::tc_gemm(d, (cudaStream_t)stream);
+}
+
+extern "C" int lf_debug_tc_gemm(const float* A, const float* B, const float* bias, float* out, int32_t M, int32_t N,
+                                int32_t K, int32_t lda, int32_t ldb, int32_t ld_out, int32_t a_mn_major,
+                                int32_t b_mn_major, int32_t block_n, int32_t splits, int64_t split_stride,
+                                void* stream) {
+  return debug_tc_gemm32(A, B, bias, out, M, N, K, lda, ldb, ld_out, a_mn_major, b_mn_major, block_n, splits, split_stride, stream, 0);
+}
+
+// Same hook with the 3xTF32 operand split (the exact-fp32 tier of the wide heads).
+extern "C" int lf_debug_tc_gemm_x3(const float* A, const float* B, const float* bias, float* out, int32_t M, int32_t N,
+                                   int32_t K, int32_t lda, int32_t ldb, int32_t ld_out, int32_t a_mn_major,
+                                   int32_t b_mn_major, int32_t block_n, int32_t splits, int64_t split_stride,
+                                   void* stream) {
+  return debug_tc_gemm32(A, B, bias, out, M, N, K, lda, ldb, ld_out, a_mn_major, b_mn_major, block_n, splits, split_stride, stream, 1);
 }

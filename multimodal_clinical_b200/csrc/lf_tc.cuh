@@ -52,6 +52,10 @@ struct TcGemmParams {
   int tma_store;           // epilogue writes through cp.async.bulk.tensor (needs a 16-byte output pitch)
   int epi_halves;          // 1 or 2 groups of four epilogue warps taking alternate 128-byte column chunks
   int elem;                // operand element size: 4 = fp32 consumed as TF32, 2 = bf16
+  int chunks, k_per_chunk; // x3 split-K: each split's K range is accumulated in `chunks` pieces (one work item each, same CTA,
+                           // in order); piece 0 stores its tile, the others add theirs with a TMA reduce -- the tensor core's
+                           // accumulator truncates on every MMA, so a long K chain in TMEM loses ~5e-9 * K relative
+  int x3;                  // fp32 operands split into tf32 hi + lo in shared memory, three MMAs per k-step (exact-fp32 tier)
   int out_elem;            // output element size (TMA-store epilogue): 4 = fp32, 2 = bf16
   int kb_elems;            // K elements per stage (128 B per operand row): 32 / 64
   int umma_k;              // K elements per tcgen05.mma: 8 / 16
@@ -86,6 +90,7 @@ struct TcGemmDesc {
   int splits;
   long long split_stride;
   int elem = 4;            // 4 = fp32 operands (TF32 MMA), 2 = bf16 operands
+  int x3 = 0;              // elem == 4 only: 3xTF32 (hi*hi + hi*lo + lo*hi), fp32-grade products on the tensor pipe
   int out_elem = 4;        // 4 = fp32 output, 2 = bf16 output (TMA-store epilogue only)
   int max_epi_halves = 2;  // 1: never add the second group of epilogue warps (the CTA then leaves room for a concurrent kernel)
   int l2_last_use = 0;     // bit 0: A, bit 1: B are dead after this GEMM (L2 evict_first hint on their loads)

@@ -117,6 +117,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// 3xTF32 operand split: hi = x rounded to tf32 (low 13 mantissa bits zero, so the tensor core's own handling of those
+// bits is irrelevant), lo = (x - hi) rounded to tf32; x - hi is exact in fp32 and |lo| <= 2^-12 |x|.  Non-finite x (or an
+// x that rounds up to Inf) poisons every output it touches with NaN: the Inf * lo(w) terms have either sign.
+// Rounding to tf32 (nearest, ties away) is an integer add of half an ulp to the sign-magnitude pattern and a mask -- two
+// full-rate ALU ops; cvt.rna.tf32.f32 compiles to the same plus a non-finite guard that buys nothing here.
+__device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {
+  hi = (x + 0x1000u) & 0xffffe000u;
+  const float r = __uint_as_float(x) - __uint_as_float(hi);
+  lo = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+}
 // instruction descriptor for kind::f16 with bf16 operands, fp32 accumulate
 __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int a_mn, int b_mn) {
   uint32_t d = 0;
@@ -206,6 +216,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, const void* src, int c0, int c1, int c2, uint64_t policy) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
+}
+// out += box, fp32 round-to-nearest adds performed at the L2 (cp.reduce.async.bulk.tensor)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>

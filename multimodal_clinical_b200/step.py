@@ -13,6 +13,7 @@ No host synchronisation happens inside a step; metrics are read from ``stats`` l
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -157,8 +158,8 @@ class LateFusionStep:
         to ``step`` INSIDE the step: the update runs in the tail of the dW kernel, right after the gradients are
         reduced (after the gradient all-reduce on several GPUs), and also refreshes the bf16 copies of the heads.
         The hyper-parameters live on the device, so a captured graph follows ``set_lr`` (StepLR)."""
-        if self.precision == LF_PREC_FP32 or self.C < 32:
-            raise _lib.LfError("the fused SGD step is part of the tensor-pipe backward (wide heads, tf32 / bf16)")
+        if self.C < 32 or (self.precision == LF_PREC_FP32 and os.environ.get("LF_NO_X3")):
+            raise _lib.LfError("the fused SGD step is part of the tensor-pipe backward (wide heads, C >= 32)")
         self._sgd = {"hyper": torch.tensor([lr, momentum, weight_decay, 0.0], device=self.device), "mom": None, "key": None}
 
     def set_lr(self, lr: float) -> None:
@@ -200,7 +201,9 @@ class LateFusionStep:
             qmf = self.mode == LF_MODE_QMF
             b = {}
             # tensor-pipe path: logits rows padded to 16 B so the GEMM epilogue can TMA-store them; callers get views
-            b["ldl"] = (Cn + 3) // 4 * 4 if (self.precision != LF_PREC_FP32 and Cn >= 32) else Cn
+            # (wide heads in every precision: LF_PREC_FP32 runs the same kernels through the 3xTF32 operand split)
+            no_x3 = self.precision == LF_PREC_FP32 and os.environ.get("LF_NO_X3")     # A/B switch: FMA GEMMs, dense rows
+            b["ldl"] = (Cn + 3) // 4 * 4 if (Cn >= 32 and not no_x3) else Cn
             b["logits_store"] = torch.empty(2, B, b["ldl"], device=dev)
             b["logits"] = b["logits_store"][:, :, :Cn]
             # avg / z_df share the padded pitch up to 256 classes, where the vector row kernels write them with 128-bit

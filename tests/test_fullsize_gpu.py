@@ -149,3 +149,62 @@ def test_k3_full_size_with_ogm_modulation_matches_oracle():
         torch.cuda.synchronize()
         for a, b0 in zip(gr, g0):
             assert_close(a, b0.double() * float(eng.coeff[which]), 1e-6, "OGM scale")
+
+
+def test_k4_fp32_full_size_3xtf32_matches_fp64_oracle():
+    """K4 in the exact tier: LF_PREC_FP32 on a 101-way head runs the tensor-pipe kernels through the 3xTF32 operand split
+    (csrc/lf_tc.cu), with the split-K dW GEMM's accumulation chain bounded by chunked TMA reduce-adds.  Contract: 1e-5."""
+    B, D, C, N = 32768, 768, 101, 65536
+    g = torch.Generator().manual_seed(414)
+    base = O.make_inputs(8, D, C, seed=5)
+    W = [base["W1"], base["W2"]]; b = [base["b1"], base["b2"]]
+    eng = _eng(num_classes=C, mode="qmf", n_data=N, precision="fp32")
+    hist = O.HistoryState(N)
+    ema = torch.zeros(2, C, dtype=torch.float64)
+    Wd = [x.cuda() for x in W]; bd = [x.cuda() for x in b]
+    from multimodal_clinical_b200 import _lib
+    lib = _lib.load()
+    for s in range(2):
+        f = [torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)]
+        y = torch.randint(0, C, (B,), generator=g, dtype=torch.int64)
+        idx = _bench_idx(B, N, g)
+        ref = O.qmf_step(f, W, b, y, idx, hist, ema_x=ema, dtype=torch.float64)
+        ema = ref["ema_x"]
+        if s == 0:
+            lib.lf_profile_enable(1)
+        out = eng.step([x.cuda() for x in f], Wd, bd, y.cuda(), idx=idx.cuda())
+        torch.cuda.synchronize()
+        if s == 0:
+            names = set(_lib.profile_report()); lib.lf_profile_enable(0)
+            assert {"tc_logits", "tc_dfeat", "tc_dweight"} <= names and not any(n.startswith("sgemm") for n in names), names
+        assert_close(out.loss, ref["loss"], TOL_FP32, f"loss step {s}")
+        for m in range(2):
+            assert_close(out.logits[m], ref["logits"][m], TOL_FP32, f"z{m + 1}")
+            assert_close(out.dweight[m], ref["dW"][m], TOL_FP32, f"dW{m + 1} step {s}")
+            assert_close(out.dbias[m], ref["db"][m], TOL_FP32, f"db{m + 1} step {s}")
+            assert_close(out.dfeat[m], ref["dfeat"][m], TOL_FP32, f"df{m + 1} step {s}")
+        assert_close(out.logits_df, ref["logits_df"], TOL_FP32, "zdf")
+        assert_close(eng.ema_x, ref["ema_x"], TOL_FP32, "ema_x")
+        assert_close(eng.correctness, hist.correctness, 1e-6, "history.correctness")
+        _check_counts(out, eng, y.cuda(), qmf=True, slack=2)
+
+
+def test_k5_fp32_full_size_3xtf32_matches_fp64_oracle():
+    B, D, C = 131072, 512, 309
+    g = torch.Generator().manual_seed(515)
+    base = O.make_inputs(8, D, C, seed=5)
+    W = [base["W1"], base["W2"]]; b = [base["b1"], base["b2"]]
+    f = [torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)]
+    y = torch.randint(0, C, (B,), generator=g, dtype=torch.int64)
+    eng = _eng(num_classes=C, mode="jlogits", precision="fp32")
+    ref = O.jlogits_step(f, W, b, y, ema_x=torch.zeros(2, C, dtype=torch.float64), dtype=torch.float64)
+    out = eng.step([x.cuda() for x in f], [x.cuda() for x in W], [x.cuda() for x in b], y.cuda(), ogm_alpha=0.8)
+    torch.cuda.synchronize()
+    assert_close(out.loss, ref["loss"], TOL_FP32, "loss")
+    for m in range(2):
+        assert_close(out.logits[m], ref["logits"][m], TOL_FP32, f"z{m + 1}")
+        assert_close(out.dweight[m], ref["dW"][m], TOL_FP32, f"dW{m + 1}")
+        assert_close(out.dbias[m], ref["db"][m], TOL_FP32, f"db{m + 1}")
+        assert_close(out.dfeat[m], ref["dfeat"][m], TOL_FP32, f"df{m + 1}")
+    assert_close(eng.ema_x, ref["ema_x"], TOL_FP32, "ema_x")
+    _check_counts(out, eng, y.cuda(), qmf=False, slack=4)
