@@ -33,7 +33,8 @@ extern "C" {
 #define LF_MODE_QMF 1     /* L=CE(z_df)+CE(z1)+CE(z2)+L_reg: cremad/joint_model_qmf.py:57-75 */
 
 /* arithmetic of the three head GEMMs */
-#define LF_PREC_FP32 0 /* exact fp32 FMA; parity 1e-5 */
+#define LF_PREC_FP32 0 /* exact fp32; parity 1e-5.  Narrow heads: FMA kernels.  Wide heads (C >= 32) whose ld_dlogits is a non-zero
+                          multiple of 4: the tensor-pipe kernels through the 3xTF32 operand split (ABI v11); else FMA GEMMs */
 #define LF_PREC_TF32 1 /* tcgen05 kind::tf32 tensor pipe (wide heads); parity 2e-2 like the reference's bf16-mixed */
 #define LF_PREC_BF16 2 /* the reference's own mode (Trainer precision "bf16-mixed", utils/run_trainer.py:47): features, dfeat
                           and the dL/dlogits scratch are bf16 in HBM (half the bytes), heads are cast to bf16 per step like
@@ -435,6 +436,37 @@ typedef struct LfSgdArgs {
   int64_t numel[8];
 } LfSgdArgs;
 int lf_sgd_heads(const LfSgdArgs* args, void* stream);
+
+/*
+ * Mean fusion of M = 2..4 narrow heads with PER-MODALITY feature widths, forward and backward in one pass (ABI v11;
+ * SURVEY.md 8f rank 4).  Replaces, after the encoders:
+ *   mustard/joint_model.py:72-83   three heads (LstmClassifier.fc3, 100 -> C), avg = (z1 + z2 + z3) / 3, CE(avg, y)
+ *   avmnist/joint_model.py:128-138 two heads of different widths (48 -> C, 192 -> C), avg = (z1 + z2) / 2, CE(avg, y)
+ * and autograd's backward through them.  Exact fp32 (parity 1e-5), classes <= 32, bit-reproducible.
+ *   stats[0] = sum of the per-sample CE, stats[1] = #(argmax avg == y), stats[2 + m] = #(argmax z_m == y)
+ */
+#define LF_MAX_MODALITIES 4
+typedef struct LfMultiHeadsArgs {
+  int32_t modalities;                       /* M */
+  int32_t batch, classes;
+  int32_t need_dfeat;
+  int32_t dim[LF_MAX_MODALITIES];           /* D_m */
+  const float* feat[LF_MAX_MODALITIES];     /* (B, D_m) row-major, dense */
+  const float* weight[LF_MAX_MODALITIES];   /* (C, D_m) */
+  const float* bias[LF_MAX_MODALITIES];     /* (C) */
+  const int64_t* label;                     /* (B) */
+  float* logits[LF_MAX_MODALITIES];         /* out (B, C) */
+  float* avg_logits;                        /* out (B, C) */
+  float* dweight[LF_MAX_MODALITIES];        /* out (C, D_m) */
+  float* dbias[LF_MAX_MODALITIES];          /* out (C) */
+  float* dfeat[LF_MAX_MODALITIES];          /* out (B, D_m), or NULL when need_dfeat == 0 */
+  float* loss_out;                          /* out: batch-mean CE */
+  double* stats;                            /* out [2 + M] */
+  void* workspace;                          /* >= lf_multi_heads_workspace_bytes(M, C, sum D_m); contents irrelevant */
+  size_t workspace_bytes;
+} LfMultiHeadsArgs;
+size_t lf_multi_heads_workspace_bytes(int32_t modalities, int32_t classes, int32_t dim_total);
+int lf_multi_heads_step(const LfMultiHeadsArgs* args, void* stream);
 
 /* Last error message of the calling thread (host string). */
 const char* lf_last_error(void);

@@ -92,6 +92,15 @@ class LfSgdArgs(C.Structure):
 
 
 LF_QMF_UPDATE_X1, LF_QMF_UPDATE_X2, LF_QMF_REG, LF_QMF_ALL = 1, 2, 4, 7
+LF_MAX_MODALITIES = 4
+_P4 = C.c_void_p * LF_MAX_MODALITIES
+
+
+class LfMultiHeadsArgs(C.Structure):
+    _fields_ = [("modalities", C.c_int32), ("batch", C.c_int32), ("classes", C.c_int32), ("need_dfeat", C.c_int32),
+                ("dim", C.c_int32 * LF_MAX_MODALITIES), ("feat", _P4), ("weight", _P4), ("bias", _P4), ("label", C.c_void_p),
+                ("logits", _P4), ("avg_logits", C.c_void_p), ("dweight", _P4), ("dbias", _P4), ("dfeat", _P4),
+                ("loss_out", C.c_void_p), ("stats", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class LfTensorList(C.Structure):
@@ -133,6 +142,8 @@ SIGNATURES = {
     "lf_ogm_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_size_t, C.c_void_p]),
     "lf_sgd_heads": (C.c_int, [C.POINTER(LfSgdArgs), C.c_void_p]),
+    "lf_multi_heads_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "lf_multi_heads_step": (C.c_int, [C.POINTER(LfMultiHeadsArgs), C.c_void_p]),
     "lf_launch_count": (C.c_int64, []),
     "lf_profile_enable": (None, [C.c_int32]),
     "lf_profile_report": (C.c_int32, [C.c_char_p, C.c_int32]),

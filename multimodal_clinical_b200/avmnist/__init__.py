@@ -1,0 +1,7 @@
+def get_model(args):
+    """Model types of avmnist/run_training.py on the fused path (jlogits: mean fusion of the heads' logits)."""
+    if args.model_type == "jlogits":
+        from .joint_model import MultimodalAVMnistModel
+    else:
+        raise NotImplementedError("Model type not implemented")
+    return MultimodalAVMnistModel(args)

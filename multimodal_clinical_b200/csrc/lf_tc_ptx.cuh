@@ -120,6 +120,8 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 // 3xTF32 operand split: hi = x rounded to tf32 (low 13 mantissa bits zero, so the tensor core's own handling of those
 // bits is irrelevant), lo = (x - hi) rounded to tf32; x - hi is exact in fp32 and |lo| <= 2^-12 |x|.  Non-finite x (or an
 // x that rounds up to Inf) poisons every output it touches with NaN: the Inf * lo(w) terms have either sign.
+// (Measured: the tensor core does ignore the low 13 bits -- feeding the raw word as hi with lo = x - trunc(x) passes the
+// same tests -- but skipping the hi store bought no time, so the split stays independent of that behaviour.)
 // Rounding to tf32 (nearest, ties away) is an integer add of half an ulp to the sign-magnitude pattern and a mask -- two
 // full-rate ALU ops; cvt.rna.tf32.f32 compiles to the same plus a non-finite guard that buys nothing here.
 __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {

@@ -1,4 +1,5 @@
-"""``python -m multimodal_clinical_b200.main --dir {cremad,food101,enrico}`` (main.py of the reference)."""
+"""``python -m multimodal_clinical_b200.main --dir {cremad,food101,enrico,mustard,avmnist}`` (main.py of the reference; the
+last two are stand-alone ``run_training.py`` scripts there and take ``--config <yaml>``)."""
 import argparse
 
 
@@ -12,6 +13,10 @@ def main(argv=None):
         from .food101.run_training import run_training
     elif arg.dir == "enrico":
         from .enrico.run_training import run_training
+    elif arg.dir == "mustard":
+        from .mustard.run_training import run_training
+    elif arg.dir == "avmnist":
+        from .avmnist.run_training import run_training
     else:
         raise NotImplementedError("Please specify a directory to run")
     return run_training(argv)

@@ -25,3 +25,24 @@ class SyntheticPairs(Dataset):
 def splits(n_train, shape1, shape2, num_classes, with_idx, seed=5):
     mk = lambda n, s: SyntheticPairs(n, shape1, shape2, num_classes, with_idx, seed=s)
     return mk(n_train, seed), mk(max(n_train // 4, 8), seed + 1), mk(max(n_train // 4, 8), seed + 2)
+
+
+class SyntheticTuples(Dataset):
+    """(x_1, ..., x_M, label) for the M-modality loaders (mustard: (S, 371), (S, 81), (S, 300); avmnist: (1, 28, 28), (1, 112, 112))."""
+
+    def __init__(self, n, shapes, num_classes, seed=5):
+        g = torch.Generator().manual_seed(seed)
+        self.label = torch.randint(0, num_classes, (n,), generator=g)
+        self.xs = [torch.randn(n, *s, generator=g) + self.label.view(-1, *([1] * len(s))) * (0.1 if m % 2 == 0 else -0.1)
+                   for m, s in enumerate(shapes)]
+
+    def __len__(self):
+        return self.label.numel()
+
+    def __getitem__(self, i):
+        return tuple(x[i] for x in self.xs) + (self.label[i],)
+
+
+def tuple_splits(n_train, shapes, num_classes, seed=5):
+    mk = lambda n, s: SyntheticTuples(n, shapes, num_classes, seed=s)
+    return mk(n_train, seed), mk(max(n_train // 4, 8), seed + 1), mk(max(n_train // 4, 8), seed + 2)

@@ -65,6 +65,16 @@ except Exception:
         def configure_optimizers(self):
             raise NotImplementedError
 
+        # hooks a module may leave out (Lightning's defaults are no-ops too)
+        def on_train_epoch_end(self) -> None:
+            pass
+
+        def on_validation_epoch_end(self) -> None:
+            pass
+
+        def on_test_epoch_end(self) -> None:
+            pass
+
     class LearningRateMonitor:
         def __init__(self, logging_interval: str = "epoch"):
             self.logging_interval = logging_interval

@@ -290,6 +290,24 @@ def jlogits_step(feats, weights, biases, y, ema_x=None, dtype=torch.float32, fea
     return _finish(out, fs, ws, bs, zs, y, ema_x, feat_grad)
 
 
+def mean_fusion_multi_step(feats, weights, biases, y, dtype=torch.float32, feat_grad=True) -> Dict:
+    """Mean fusion of M heads with per-modality feature widths: avg = (z_1 + ... + z_M) / M, L = CE(avg)
+    (mustard/joint_model.py:72-83 with M = 3; avmnist/joint_model.py:128-138 with D = 48 / 192) and the joint accuracy the
+    Lightning modules log (mustard/joint_model.py:134, avmnist/joint_model.py:201)."""
+    fs, ws, bs = _leafs(feats, weights, biases, dtype, feat_grad)
+    zs = heads_forward(fs, ws, bs)
+    acc = zs[0]
+    for z in zs[1:]:
+        acc = acc + z
+    avg = acc / len(zs)
+    loss = cross_entropy_mean(avg, y)
+    loss.backward()
+    B = y.shape[0]
+    return {"loss": loss.detach(), "avg_logits": avg.detach(), "logits": [z.detach() for z in zs],
+            "dW": [w.grad for w in ws], "db": [b.grad for b in bs], "dfeat": [f.grad for f in fs] if feat_grad else [None] * len(fs),
+            "acc_joint": correct_count(avg.detach(), y) / B, "acc_modality": [correct_count(z.detach(), y) / B for z in zs]}
+
+
 def ensemble_step(feats, weights, biases, y, dtype=torch.float32, feat_grad=True) -> Dict:
     """Per-modality ensemble: x_m_loss = CE(z_m, y), backward of (x1_loss + x2_loss) / 2
     (cremad/ensemble_model_noised.py:49-55, 97-103, 119-120).  No EMA calibration in this family

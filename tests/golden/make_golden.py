@@ -372,9 +372,60 @@ def food101_fill(net, seed):
             p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * bound)
 
 
+def golden_multi(name, which, B, seed, only=True):
+    """The reference's three-modality and unequal-width FusionNets, unmodified, encoders included:
+    mustard/joint_model.py (three LstmClassifiers, heads fc3: 100 -> C) and avmnist/joint_model.py (two LeNets,
+    heads 48 -> C and 192 -> C).  Forward pre-hooks on the head modules capture the features that reach them (and retain
+    their gradients), so the fixture holds exactly what the fused heads kernel sees and must return."""
+    import importlib
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    if which == "mustard":
+        mod = importlib.import_module("mustard.joint_model")
+        C = 2
+        net = mod.FusionNet(num_classes=C, loss_fn=nn.CrossEntropyLoss())
+        heads = [net.x1_model.fc3, net.x2_model.fc3, net.x3_model.fc3]
+        xs = [torch.randn(B, 7, d, generator=g) for d in (371, 81, 300)]
+    else:
+        mod = importlib.import_module("avmnist.joint_model")
+        C = 10
+        net = mod.FusionNet(num_classes=C, loss_fn=nn.CrossEntropyLoss())
+        heads = [net.classifier_x1, net.classifier_x2]
+        xs = [torch.randn(B, 1, 28, 28, generator=g), torch.randn(B, 1, 112, 112, generator=g)]
+    y = torch.randint(0, C, (B,), generator=g, dtype=torch.int64)
+    seen = {}
+
+    def grab(m):
+        def hook(module, inp):
+            seen[m] = inp[0]
+            inp[0].retain_grad()
+        return hook
+    for m, h in enumerate(heads):
+        h.register_forward_pre_hook(grab(m))
+    net.train()
+    out = net(*xs, y)
+    zs, avg, loss = out[:-2], out[-2], out[-1]
+    loss.backward()
+    M = len(heads)
+    rec = {"meta": np.array([B, C, M], dtype=np.int64), "y": y.numpy(), "avg": avg.detach().numpy(), "loss": loss.detach().numpy(),
+           "acc_joint": np.float64(torch.mean((torch.argmax(avg, dim=1) == y).float()))}
+    for m in range(M):
+        rec[f"f{m}"] = seen[m].detach().numpy().copy(); rec[f"df{m}"] = seen[m].grad.numpy().copy()
+        rec[f"W{m}"] = heads[m].weight.detach().numpy().copy(); rec[f"b{m}"] = heads[m].bias.detach().numpy().copy()
+        rec[f"dW{m}"] = heads[m].weight.grad.numpy().copy(); rec[f"db{m}"] = heads[m].bias.grad.numpy().copy()
+        rec[f"z{m}"] = zs[m].detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print("wrote", name, "loss =", float(loss.detach()), "feature widths", [int(seen[m].shape[1]) for m in range(M)])
+
+
 if __name__ == "__main__":
     install_shims()
     torch.manual_seed(5)
+    # three modalities (mustard) and unequal feature widths (avmnist): SURVEY.md §8f rank 4
+    golden_multi("multi_mustard_b24", "mustard", B=24, seed=71)
+    golden_multi("multi_avmnist_b40", "avmnist", B=40, seed=73)
+    if "--multi-only" in sys.argv:
+        sys.exit(0)
     # K2: Crema-D QMF, B=64 D=512 C=6, sampling with replacement (duplicates), 4 steps of history
     golden_qmf("qmf_cremad_b64", B=64, D=512, C=6, N=997, steps=3, seed=5)
     # ragged / odd sizes, contiguous idx windows (Food101-style loader), C not a multiple of anything

@@ -54,6 +54,13 @@ def test_struct_layout_matches_c(tmp_path):
             C.sizeof(_lib.LfTensorList), C.sizeof(_lib.LfMidArgs), _lib.LfMidArgs.stats.offset,
             _lib.LfMidArgs.step_base.offset, _lib.LfHeadsArgs.fwd_only.offset]
     assert got == want
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lf_fusion.h"\nint main(){'
+                    'printf("%zu %zu %zu %zu %zu\\n", sizeof(LfMultiHeadsArgs), offsetof(LfMultiHeadsArgs, feat), offsetof(LfMultiHeadsArgs, label),'
+                    'offsetof(LfMultiHeadsArgs, dfeat), offsetof(LfMultiHeadsArgs, workspace_bytes)); return 0;}')
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    M = _lib.LfMultiHeadsArgs
+    assert got == [C.sizeof(M), M.feat.offset, M.label.offset, M.dfeat.offset, M.workspace_bytes.offset]
 
 
 def test_workspace_sizes_are_monotone(lib):

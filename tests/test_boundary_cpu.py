@@ -65,6 +65,28 @@ def test_state_dict_keys_keep_the_reference_names():
         assert k in keys, k
 
 
+def test_multi_modality_modules_keep_the_reference_names_and_refuse_cpu():
+    """mustard (three modalities) / avmnist (unequal widths): parameter names and shapes of the reference's FusionNets
+    (mustard/joint_model.py:9-58, avmnist/joint_model.py:32-110), Adam optimizer, loud failure without a GPU."""
+    from multimodal_clinical_b200.mustard.joint_model import MultimodalMustardModel as MM
+    from multimodal_clinical_b200.avmnist.joint_model import MultimodalAVMnistModel as AM
+    from multimodal_clinical_b200 import mustard, avmnist
+    sd = MM(argparse.Namespace(num_classes=2, learning_rate=5e-4)).state_dict()
+    assert len(sd) == 30 and not any("fused" in k for k in sd)
+    assert tuple(sd["model.x1_model.fc1.weight"].shape) == (384, 371) and tuple(sd["model.x2_model.fc1.weight"].shape) == (384, 81)
+    assert tuple(sd["model.x3_model.fc3.weight"].shape) == (2, 100) and "model.x2_model.lstm.weight_hh_l0" in sd
+    am = AM(argparse.Namespace(num_classes=10, learning_rate=1e-3))
+    sd = am.state_dict()
+    assert len(sd) == 64 and tuple(sd["model.classifier_x1.weight"].shape) == (10, 48) and tuple(sd["model.classifier_x2.weight"].shape) == (10, 192)
+    assert tuple(sd["model.x2_model.convs.5.weight"].shape) == (192, 96, 3, 3) and "model.x1_model.bns.3.running_mean" in sd
+    assert isinstance(am.configure_optimizers(), torch.optim.Adam)
+    with pytest.raises(_lib.LfError):
+        am.model(torch.randn(4, 1, 28, 28), torch.randn(4, 1, 112, 112), torch.zeros(4, dtype=torch.long))
+    for mod in (mustard, avmnist):
+        with pytest.raises(NotImplementedError):
+            mod.get_model(argparse.Namespace(model_type="jprobas"))
+
+
 def test_base_model_public_attributes_and_optimizer():
     from multimodal_clinical_b200.cremad.joint_model_ogm_ge import MultimodalCremadModel
     m = MultimodalCremadModel(_args())
