@@ -468,6 +468,38 @@ typedef struct LfMultiHeadsArgs {
 size_t lf_multi_heads_workspace_bytes(int32_t modalities, int32_t classes, int32_t dim_total);
 int lf_multi_heads_step(const LfMultiHeadsArgs* args, void* stream);
 
+/*
+ * Hidden layers of the Food101 per-modality MLPs (ABI v11): the two modalities' layers of one shape,
+ *   forward   h = dropout_p(relu(x W^T + b))        food101/joint_model_qmf.py:15-20 (nn.Linear, nn.ReLU, nn.Dropout(0.2))
+ *   backward  dP = dh * [h > 0] / (1 - p);  dx = dP W;  dW = dP^T x;  db = sum_rows dP      (autograd of the same)
+ * on the tensor-pipe GEMM kernel (precision: LF_PREC_BF16 = x, h, dh, dpre, dx bf16 with fp32 accumulation, what the
+ * bf16-mixed trainer runs; LF_PREC_TF32 / LF_PREC_FP32 = fp32 tensors, single-pass TF32 / 3xTF32).  Bias, ReLU and the
+ * dropout mask (Philox4x32-10: element e = row * dim_out + col draws word e & 3 of the block with counter (e >> 2, offset)
+ * and key seed; kept when word >= p * 2^32) are applied in the forward GEMM's epilogue; no mask is stored.
+ * training == 0: dropout is the identity (nn.Dropout in eval mode).  dx may be NULL for both layers (frozen input).
+ */
+typedef struct LfHiddenArgs {
+  int32_t batch, dim_in, dim_out;   /* dims multiples of 8 */
+  int32_t precision;                /* LF_PREC_* */
+  int32_t training;
+  float drop_p;
+  uint64_t seed, offset;
+  const void* x[2];                 /* (B, dim_in) */
+  const float* weight[2];           /* (dim_out, dim_in) fp32 master weights */
+  const float* bias[2];             /* (dim_out) */
+  void* h[2];                       /* out (B, dim_out) */
+  const void* dh[2];                /* backward: (B, dim_out) */
+  void* dpre[2];                    /* backward scratch (B, dim_out), same element type as h */
+  void* dx[2];                      /* backward out (B, dim_in) or NULL */
+  float* dweight[2];                /* backward out (dim_out, dim_in) fp32 */
+  float* dbias[2];                  /* backward out (dim_out) fp32 */
+  void* workspace;                  /* >= lf_hidden_workspace_bytes(batch, dim_in, dim_out) */
+  size_t workspace_bytes;
+} LfHiddenArgs;
+size_t lf_hidden_workspace_bytes(int32_t batch, int32_t dim_in, int32_t dim_out);
+int lf_hidden_forward(const LfHiddenArgs* args, void* stream);
+int lf_hidden_backward(const LfHiddenArgs* args, void* stream);
+
 /* Last error message of the calling thread (host string). */
 const char* lf_last_error(void);
 int32_t lf_abi_version(void);

@@ -96,6 +96,13 @@ LF_MAX_MODALITIES = 4
 _P4 = C.c_void_p * LF_MAX_MODALITIES
 
 
+class LfHiddenArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("dim_in", C.c_int32), ("dim_out", C.c_int32), ("precision", C.c_int32),
+                ("training", C.c_int32), ("drop_p", C.c_float), ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("x", _P2), ("weight", _P2), ("bias", _P2), ("h", _P2), ("dh", _P2), ("dpre", _P2), ("dx", _P2),
+                ("dweight", _P2), ("dbias", _P2), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 class LfMultiHeadsArgs(C.Structure):
     _fields_ = [("modalities", C.c_int32), ("batch", C.c_int32), ("classes", C.c_int32), ("need_dfeat", C.c_int32),
                 ("dim", C.c_int32 * LF_MAX_MODALITIES), ("feat", _P4), ("weight", _P4), ("bias", _P4), ("label", C.c_void_p),
@@ -142,6 +149,9 @@ SIGNATURES = {
     "lf_ogm_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_size_t, C.c_void_p]),
     "lf_sgd_heads": (C.c_int, [C.POINTER(LfSgdArgs), C.c_void_p]),
+    "lf_hidden_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "lf_hidden_forward": (C.c_int, [C.POINTER(LfHiddenArgs), C.c_void_p]),
+    "lf_hidden_backward": (C.c_int, [C.POINTER(LfHiddenArgs), C.c_void_p]),
     "lf_multi_heads_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "lf_multi_heads_step": (C.c_int, [C.POINTER(LfMultiHeadsArgs), C.c_void_p]),
     "lf_launch_count": (C.c_int64, []),

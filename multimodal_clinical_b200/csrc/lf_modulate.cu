@@ -7,6 +7,7 @@
 // registers.  HBM-bound: 12 B/param (4 read for std, 4 read + 4 write for the update); the second read
 // hits L2 when an encoder's conv gradients (45 MB for ResNet18) fit the 126 MB L2.
 #include "lf_common.cuh"
+#include "lf_philox.cuh"
 
 namespace lf {
 
@@ -27,20 +28,6 @@ __device__ __forceinline__ int mod_find_tensor(const ModTable& tb, int item) {
     if (tb.chunk0[mid] <= item) lo = mid; else hi = mid - 1;
   }
   return lo;
-}
-
-// ---- Philox4x32-10 (Salmon et al. 2011), counter-based: any element's draw is addressable ----------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const unsigned long long p0 = (unsigned long long)M0 * ctr.x, p1 = (unsigned long long)M1 * ctr.z;   // one IMAD.WIDE each
-    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
-    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0; key.y += W1;
-  }
-  return ctr;
 }
 
 __device__ __forceinline__ float4 normal4(unsigned long long group, unsigned long long seed,

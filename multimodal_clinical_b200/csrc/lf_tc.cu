@@ -34,6 +34,7 @@
 #include <stdlib.h>
 #include "lf_common.cuh"
 #include "lf_peer.cuh"
+#include "lf_philox.cuh"
 #include "lf_tc.cuh"
 #include "lf_tc_ptx.cuh"
 
@@ -261,6 +262,26 @@ __device__ __forceinline__ void gemm_tail(const TcGemmParams& p, float* s_rows) 
   }
 }
 
+// Epilogue activation of the hidden layers: relu, then inverted dropout.  v holds n (multiple of 4) consecutive columns of
+// output row `row` starting at column col0 (multiple of 4).
+template <int N4>
+__device__ __forceinline__ void relu_dropout(float* v, long long row, int col0, const TcGemmParams& p) {
+#pragma unroll
+  for (int i = 0; i < 4 * N4; ++i) v[i] = relu_nan(v[i]);
+  if (p.drop_p > 0.f) {
+    const uint32_t thr = (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967040.f);
+    const unsigned long long g0 = ((unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col0) >> 2;
+#pragma unroll
+    for (int g = 0; g < N4; ++g) {
+      const uint4 r = dropout_words(g0 + g, p.seed, p.rng_offset);
+      v[4 * g + 0] = r.x >= thr ? v[4 * g + 0] * p.drop_scale : 0.f;
+      v[4 * g + 1] = r.y >= thr ? v[4 * g + 1] * p.drop_scale : 0.f;
+      v[4 * g + 2] = r.z >= thr ? v[4 * g + 2] * p.drop_scale : 0.f;
+      v[4 * g + 3] = r.w >= thr ? v[4 * g + 3] * p.drop_scale : 0.f;
+    }
+  }
+}
+
 __device__ __forceinline__ Item decode_item(const TcGemmParams& p, int item) {
   Item it;
   const int n_t = item % p.n_tiles; int r = item / p.n_tiles;
@@ -437,13 +458,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
               for (int i = 0; i < 32; ++i) { const int col = w.n0 + c0 + i; v[i] += col < p.N ? __ldg(bias + col) : 0.f; }
             }
+            if (p.act_relu) relu_dropout<8>(v, (long long)w.m0 + row_in_tile, w.n0 + c0, p);
 #pragma unroll
             for (int i = 0; i < 32; ++i) pk[i] = w.num_kb == 0 ? 0u : __float_as_uint(v[i]);
           } else {
+            const float* bias = w.chunk == 0 ? p.bias[w.batch] : nullptr;
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               float v[16];
               tmem_ld16(acc + c0 + 16 * h, v);
+              if (bias) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { const int col = w.n0 + c0 + 16 * h + i; v[i] += col < p.N ? __ldg(bias + col) : 0.f; }
+              }
+              if (p.act_relu) relu_dropout<4>(v, (long long)w.m0 + row_in_tile, w.n0 + c0 + 16 * h, p);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
@@ -660,8 +688,14 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   const int ccols = 128 / p.out_elem;
   bool aligned = ((d.ld_out * p.out_elem) % 16 == 0) && ((d.split_stride * p.out_elem) % 16 == 0) &&
                  (d.block_n % ccols == 0 || d.N <= d.block_n);
-  for (int b = 0; b < d.nbatch; ++b) aligned = aligned && (((uintptr_t)d.out[b] & 15) == 0) && (d.bias[b] == nullptr || p.out_elem == 4);
+  for (int b = 0; b < d.nbatch; ++b) aligned = aligned && (((uintptr_t)d.out[b] & 15) == 0);
   p.tma_store = aligned ? 1 : 0;
+  p.act_relu = d.act_relu; p.drop_p = d.drop_p; p.drop_scale = d.drop_p > 0.f ? 1.f / (1.f - d.drop_p) : 1.f;
+  p.seed = d.seed; p.rng_offset = d.rng_offset;
+  if (d.act_relu && (!p.tma_store || (d.N & 3) || d.splits > 1 || d.drop_p < 0.f || d.drop_p >= 1.f)) {
+    set_error("tc_gemm: the relu / dropout epilogue needs the TMA-store path, N %% 4 == 0, no split-K and 0 <= p < 1");
+    return LF_ERR_BAD_ARG;
+  }
   if (p.out_elem == 2 && !p.tma_store) { set_error("tc_gemm: bf16 output needs the TMA-store epilogue (16-byte pitch, no bias)"); return LF_ERR_BAD_ARG; }
   p.acc_cols = d.block_n <= 32 ? 32 : d.block_n <= 64 ? 64 : d.block_n <= 128 ? 128 : 256;
   p.tmem_cols = 2 * p.acc_cols;
@@ -680,7 +714,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   p.m_tiles = div_up(d.M, p.tile_m);
   p.total_items = p.m_tiles * p.n_tiles * p.splits * d.nbatch;
   int grid_fixed = 0;
-  if (p.x3 && kps > kX3ChunkK && p.tma_store && p.total_items <= 148) {
+  if (p.x3 && kps > kX3ChunkK && p.tma_store && p.total_items <= 148 && !d.act_relu) {     // (a nonlinear epilogue needs the whole sum)
     // 3xTF32 with a long K per work item (the split-K dW GEMM): bound the accumulation chain in TMEM
     p.chunks = div_up(kps, kX3ChunkK);
     p.k_per_chunk = div_up(div_up(kps, p.chunks), p.kb_elems) * p.kb_elems;

@@ -55,6 +55,10 @@ struct TcGemmParams {
   int chunks, k_per_chunk; // x3 split-K: each split's K range is accumulated in `chunks` pieces (one work item each, same CTA,
                            // in order); piece 0 stores its tile, the others add theirs with a TMA reduce -- the tensor core's
                            // accumulator truncates on every MMA, so a long K chain in TMEM loses ~5e-9 * K relative
+  int act_relu;            // epilogue (TMA-store path): out = dropout(relu(acc + bias)) -- the hidden layers of the Food101 MLPs
+  float drop_p, drop_scale;           // dropout probability (0 = off) and 1 / (1 - p)
+  unsigned long long seed, rng_offset; // Philox4x32-10 key / counter high words; element (row, col) draws word (col & 3) of
+                                       // counter group (row * N + col) / 4, so the mask does not depend on the tiling
   int x3;                  // fp32 operands split into tf32 hi + lo in shared memory, three MMAs per k-step (exact-fp32 tier)
   int out_elem;            // output element size (TMA-store epilogue): 4 = fp32, 2 = bf16
   int kb_elems;            // K elements per stage (128 B per operand row): 32 / 64
@@ -90,6 +94,9 @@ struct TcGemmDesc {
   int splits;
   long long split_stride;
   int elem = 4;            // 4 = fp32 operands (TF32 MMA), 2 = bf16 operands
+  int act_relu = 0;        // TMA-store epilogue: relu after the bias
+  float drop_p = 0.f;      // then inverted dropout with this probability (Philox4x32-10 keyed by seed / rng_offset)
+  unsigned long long seed = 0, rng_offset = 0;
   int x3 = 0;              // elem == 4 only: 3xTF32 (hi*hi + hi*lo + lo*hi), fp32-grade products on the tensor pipe
   int out_elem = 4;        // 4 = fp32 output, 2 = bf16 output (TMA-store epilogue only)
   int max_epi_halves = 2;  // 1: never add the second group of epilogue warps (the CTA then leaves room for a concurrent kernel)

@@ -6,7 +6,7 @@ from torch.optim.lr_scheduler import StepLR
 
 from ..heads import FusedLateFusionHead
 from ..utils.BaseModel import JointLogitsBaseModel
-from ._common import MLP, build_siglip
+from ._common import MLP, build_hidden, build_siglip, hidden_features
 
 
 class FusionNet(nn.Module):
@@ -17,13 +17,13 @@ class FusionNet(nn.Module):
         self.model = build_siglip(args)
         self.x1_model = MLP(input_dim=768, hidden_dim=512, num_classes=num_classes)
         self.x2_model = MLP(input_dim=768, hidden_dim=512, num_classes=num_classes)
+        self.hidden = build_hidden(args)
         self.fused = FusedLateFusionHead(num_classes, mode="jlogits",
                                          precision=getattr(args, "head_precision", "auto"))
 
     def forward(self, x1_data, x2_data, label):
         output = self.model(x1_data, x2_data)
-        h1 = self.x1_model.hidden(output['text_embeds'])
-        h2 = self.x2_model.hidden(output['image_embeds'])
+        h1, h2 = hidden_features(self, output['text_embeds'], output['image_embeds'])
         return self.fused(h1, h2, self.x1_model.classifier, self.x2_model.classifier, label)
 
 

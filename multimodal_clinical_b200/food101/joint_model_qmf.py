@@ -8,7 +8,7 @@ from torch.optim.lr_scheduler import StepLR
 from ..existing_algos.QMF import QMF
 from ..heads import FusedLateFusionHead
 from ..utils.BaseModel import QMFBaseModel
-from ._common import MLP, build_siglip
+from ._common import MLP, build_hidden, build_siglip, hidden_features
 
 
 class FusionNet(nn.Module):
@@ -22,14 +22,14 @@ class FusionNet(nn.Module):
         self.model = build_siglip(args)
         self.x1_model = MLP(input_dim=768, hidden_dim=512, num_classes=self.num_classes)
         self.x2_model = MLP(input_dim=768, hidden_dim=512, num_classes=self.num_classes)
+        self.hidden = build_hidden(args)
         self.fused = FusedLateFusionHead(self.num_classes, mode="qmf", n_data=self.args.num_samples,
                                          precision=getattr(args, "head_precision", "auto"))
         self.fused.bind_qmf(self.qmf)
 
     def forward(self, x1_data, x2_data, label, idx):
         output = self.model(x1_data, x2_data)
-        h1 = self.x1_model.hidden(output['text_embeds'])
-        h2 = self.x2_model.hidden(output['image_embeds'])
+        h1, h2 = hidden_features(self, output['text_embeds'], output['image_embeds'])
         return self.fused(h1, h2, self.x1_model.classifier, self.x2_model.classifier, label, idx)
 
 

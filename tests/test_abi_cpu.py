@@ -61,6 +61,13 @@ def test_struct_layout_matches_c(tmp_path):
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     M = _lib.LfMultiHeadsArgs
     assert got == [C.sizeof(M), M.feat.offset, M.label.offset, M.dfeat.offset, M.workspace_bytes.offset]
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lf_fusion.h"\nint main(){'
+                    'printf("%zu %zu %zu %zu %zu\\n", sizeof(LfHiddenArgs), offsetof(LfHiddenArgs, seed), offsetof(LfHiddenArgs, x),'
+                    'offsetof(LfHiddenArgs, dx), offsetof(LfHiddenArgs, workspace_bytes)); return 0;}')
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    H = _lib.LfHiddenArgs
+    assert got == [C.sizeof(H), H.seed.offset, H.x.offset, H.dx.offset, H.workspace_bytes.offset]
 
 
 def test_workspace_sizes_are_monotone(lib):

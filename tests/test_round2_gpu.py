@@ -154,8 +154,12 @@ def _fill_food101(net, seed):
 
 
 def test_food101_module_matches_reference_golden():
-    """food101/joint_model_qmf.FusionNet of the reference vs ours (same state-dict names, MLP hidden layers in PyTorch, the last
-    Linear + QMF loss in the fused step), exact-fp32 heads: outputs, gradients on every MLP parameter and on the embeddings."""
+    """food101/joint_model_qmf.FusionNet of the reference vs ours (same state-dict names; the MLP's hidden layers on the fused
+    hidden-layer kernels, the last Linear + QMF loss in the fused step), everything in the exact tier: outputs, gradients on
+    every MLP parameter and on the embeddings.  The logits come out of THREE stacked 3xTF32 GEMMs (768 -> 512 -> 512 -> 101),
+    each of which truncates its TMEM accumulator toward zero (~3e-6 at K = 768): 2e-5 for the stack, 1e-5 per layer
+    (tests/test_hidden_gpu.py, tests/test_parity_gpu.py)."""
+    TOL_STACK = 2e-5
     from multimodal_clinical_b200.food101.joint_model_qmf import FusionNet
     g = load_golden("food101_module_b32")
     B, D, C, N, steps, seed = [int(v) for v in g["meta"]]
@@ -172,20 +176,20 @@ def test_food101_module_matches_reference_golden():
         z1, z2, avg, loss, zdf = net(e1, e2, cu(g[p + "y"]), cu(g[p + "idx"]))
         loss.backward()
         torch.cuda.synchronize()
-        assert_close(z1, g[p + "z1"], TOL_FP32, "z1"); assert_close(z2, g[p + "z2"], TOL_FP32, "z2")
-        assert_close(avg, g[p + "avg"], TOL_FP32, "avg"); assert_close(zdf, g[p + "zdf"], TOL_FP32, "zdf")
+        assert_close(z1, g[p + "z1"], TOL_STACK, "z1"); assert_close(z2, g[p + "z2"], TOL_STACK, "z2")
+        assert_close(avg, g[p + "avg"], TOL_STACK, "avg"); assert_close(zdf, g[p + "zdf"], TOL_STACK, "zdf")
         assert_close(loss, g[p + "loss"], TOL_FP32, "loss")
-        assert_close(e1.grad, g[p + "de1"], 2e-5, "d embeddings 1"); assert_close(e2.grad, g[p + "de2"], 2e-5, "d embeddings 2")
+        assert_close(e1.grad, g[p + "de1"], 4e-5, "d embeddings 1"); assert_close(e2.grad, g[p + "de2"], 4e-5, "d embeddings 2")
         for k, ref in g.items():
             if k.startswith(p + "grad/"):
-                assert_close(names[k[len(p) + 5:]].grad, ref, 2e-5, k)
+                assert_close(names[k[len(p) + 5:]].grad, ref, 4e-5, k)
             elif k.startswith(p + "gradR/"):
                 gr = torch.Generator().manual_seed(1000 + s)
                 gp = names[k[len(p) + 6:]].grad.cpu()
                 R = torch.randn(gp.shape[1], 4, generator=gr)
                 L = torch.randn(4, gp.shape[0], generator=gr)
-                assert_close(gp @ R, ref, 2e-5, k)
-                assert_close(L @ gp, g[k.replace("gradR/", "gradL/")], 2e-5, k + " (left)")
+                assert_close(gp @ R, ref, 4e-5, k)
+                assert_close(L @ gp, g[k.replace("gradR/", "gradL/")], 4e-5, k + " (left)")
         assert_close(net.qmf.history[0].correctness, g[p + "corr"][0], 1e-6, "history")
 
 
