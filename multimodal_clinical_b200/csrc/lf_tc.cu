@@ -345,7 +345,10 @@ __device__ __forceinline__ void mma_issue_loop(const TcGemmParams& p, uint8_t* s
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// X3: the 3xTF32 variant (converter warps, 448 threads); ACT: the relu / dropout epilogue of the hidden layers.  Separate
+// instantiations keep the plain kernel at its own register budget and its epilogue loop free of the Philox code.
+template <bool X3, bool ACT>
+__global__ void __launch_bounds__(X3 ? TC_THREADS : 320, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
                const __grid_constant__ CUtensorMap mapO0, const __grid_constant__ CUtensorMap mapO1, TcGemmParams p) {
@@ -354,7 +357,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t a_bytes = TC_BLOCK_M * TC_BLOCK_K * 4;
   const uint32_t b_bytes = (uint32_t)p.block_n * TC_BLOCK_K * 4;
   const uint32_t half_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
-  const uint32_t stage_bytes = p.x3 ? 2 * half_bytes : half_bytes;   // x3: [A hi | B hi | A lo | B lo]
+  const uint32_t stage_bytes = X3 ? 2 * half_bytes : half_bytes;   // x3: [A hi | B hi | A lo | B lo]
   uint8_t* staging = smem + (size_t)stages * stage_bytes;            // 1024-aligned (stage_bytes is)
   uint64_t* full_bar = (uint64_t*)(staging + (size_t)2 * p.epi_halves * TC_BLOCK_M * 128);
   uint64_t* empty_bar = full_bar + stages;
@@ -425,7 +428,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      if (p.x3) mma_issue_loop<true, true>(p, smem, stage_bytes, a_bytes, conv_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
+      if (X3) mma_issue_loop<true, true>(p, smem, stage_bytes, a_bytes, conv_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
       else if (p.elem == 4) mma_issue_loop<true, false>(p, smem, stage_bytes, a_bytes, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
       else mma_issue_loop<false, false>(p, smem, stage_bytes, a_bytes, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base);
     }
@@ -458,7 +461,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
               for (int i = 0; i < 32; ++i) { const int col = w.n0 + c0 + i; v[i] += col < p.N ? __ldg(bias + col) : 0.f; }
             }
-            if (p.act_relu) relu_dropout<8>(v, (long long)w.m0 + row_in_tile, w.n0 + c0, p);
+            if (ACT) relu_dropout<8>(v, (long long)w.m0 + row_in_tile, w.n0 + c0, p);
 #pragma unroll
             for (int i = 0; i < 32; ++i) pk[i] = w.num_kb == 0 ? 0u : __float_as_uint(v[i]);
           } else {
@@ -471,7 +474,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { const int col = w.n0 + c0 + 16 * h + i; v[i] += col < p.N ? __ldg(bias + col) : 0.f; }
               }
-              if (p.act_relu) relu_dropout<4>(v, (long long)w.m0 + row_in_tile, w.n0 + c0 + 16 * h, p);
+              if (ACT) relu_dropout<4>(v, (long long)w.m0 + row_in_tile, w.n0 + c0 + 16 * h, p);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
@@ -531,7 +534,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (p.tail.on) asm volatile("fence.proxy.async;" ::: "memory");    // async-proxy stores -> generic-proxy readers of the tail
     }
   }
-  else if (p.x3) {
+  else if (X3) {
     // ===================== 3xTF32 converters (warps 6-13; x3 runs one epilogue half) =====================
     const int ct = threadIdx.x - (64 + 128 * p.epi_halves);          // 0..kConvThreads-1
     const uint32_t n16 = half_bytes >> 4;                            // 16-byte words of [A | B] in one stage
@@ -754,9 +757,12 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   while (stages > 2 && (size_t)stages * stage_bytes + fixed > 226 * 1024) --stages;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + fixed;
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcGemmParams);
+  static const KernelFn kernels[4] = {tc_gemm_kernel<false, false>, tc_gemm_kernel<false, true>, tc_gemm_kernel<true, false>, tc_gemm_kernel<true, true>};
+  const KernelFn kernel = kernels[2 * p.x3 + (p.act_relu ? 1 : 0)];
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    for (int i = 0; i < 4; ++i) cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     attr_set = true;
   }
   const int grid = grid_fixed ? grid_fixed : (p.total_items < 148 ? p.total_items : 148);
@@ -777,7 +783,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
     attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = getenv("LF_DW_NOCOOP") ? 0 : 1;
     cudaError_t e = cudaSuccess;
-    LF_LAUNCH(d.name, s, (e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p)));
+    LF_LAUNCH(d.name, s, (e = cudaLaunchKernelEx(&cfg, kernel, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p)));
     if (e != cudaSuccess) { set_error("%s: %s", d.name, cudaGetErrorString(e)); return LF_ERR_CUDA; }
     if (p.tail.trace && ++trace_calls == 12) {
       cudaStreamSynchronize(s);
@@ -795,7 +801,7 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
     }
     return check_launch(d.name);
   }
-  LF_LAUNCH(d.name, s, launch_pdl(tc_gemm_kernel, dim3(grid), dim3(64 + 128 * p.epi_halves + kConvThreads * p.x3), smem, s, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p));
+  LF_LAUNCH(d.name, s, launch_pdl(kernel, dim3(grid), dim3(64 + 128 * p.epi_halves + kConvThreads * p.x3), smem, s, mA[0], mB[0], mA[1], mB[1], mO[0], mO[1], p));
   return check_launch(d.name);
 }
 

@@ -86,7 +86,7 @@ class FusedHiddenPair(nn.Module):
     def resolve_precision(self, x: torch.Tensor) -> int:
         if self.precision != "auto":
             return {"fp32": LF_PREC_FP32, "tf32": LF_PREC_TF32, "bf16": LF_PREC_BF16}[self.precision]
-        if x.dtype == torch.bfloat16 or (torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16):
+        if x.dtype == torch.bfloat16 or (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16):
             return LF_PREC_BF16
         return LF_PREC_TF32 if torch.get_float32_matmul_precision() != "highest" else LF_PREC_FP32
 

@@ -372,6 +372,7 @@ def test_food101_module_under_autocast_matches_oracle_on_bf16_rounded_inputs():
     torch.manual_seed(0)
     m = fq.MultimodalFoodModel(_food_args(num_samples=N)).cuda()
     m.train()
+    m.model.hidden = None                       # (not the fused hidden layers either: tests/test_hidden_gpu.py covers those)
     m.model.x1_model.hidden = lambda x: x
     m.model.x2_model.hidden = lambda x: x
     inp = O.make_inputs(B, D, C, seed=77, n_data=N)

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r3t_tests.log
+timeout 200 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r3t_k4_bf16.json 2> gpurun_out/r3t_k4_bf16.err
+timeout 200 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r3t_k4_bf16_b.json 2> gpurun_out/r3t_k4_bf16_b.err
+echo done
