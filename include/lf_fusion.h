@@ -474,8 +474,8 @@ int lf_multi_heads_step(const LfMultiHeadsArgs* args, void* stream);
  *   backward  dP = dh * [h > 0] / (1 - p);  dx = dP W;  dW = dP^T x;  db = sum_rows dP      (autograd of the same)
  * on the tensor-pipe GEMM kernel (precision: LF_PREC_BF16 = x, h, dh, dpre, dx bf16 with fp32 accumulation, what the
  * bf16-mixed trainer runs; LF_PREC_TF32 / LF_PREC_FP32 = fp32 tensors, single-pass TF32 / 3xTF32).  Bias, ReLU and the
- * dropout mask (Philox4x32-10: element e = row * dim_out + col draws word e & 3 of the block with counter (e >> 2, offset)
- * and key seed; kept when word >= p * 2^32) are applied in the forward GEMM's epilogue; no mask is stored.
+ * dropout mask (Philox4x32-10: element e = row * dim_out + col draws 16-bit half e & 7 of the block with counter
+ * (e >> 3, offset) and key seed; kept when the half >= round(p * 65536)) are applied in the forward GEMM's epilogue; no mask is stored.
  * training == 0: dropout is the identity (nn.Dropout in eval mode).  dx may be NULL for both layers (frozen input).
  */
 typedef struct LfHiddenArgs {

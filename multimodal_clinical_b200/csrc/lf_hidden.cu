@@ -27,41 +27,75 @@ template <class T> __device__ __forceinline__ void hid_st(T* p, float v);
 template <> __device__ __forceinline__ void hid_st<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void hid_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-// dP = dH * [H > 0] * scale; per-CTA column sums of dP (fp32, rows in order) into dbpart[modality][block][Dout].
-// One CTA = kHidRowsPerCta rows x all columns; a thread owns columns tid, tid + 256, ... so a row is read coalesced.
+// dP = dH * [H > 0] * scale; per-CTA column sums of dP (fp32) into dbpart[modality][block][Dout].
+// One CTA = kHidRowsPerCta rows x all columns.  Vector path (Dout / VEC threads per row divide the CTA): a thread moves 16
+// bytes of a row per access and keeps the sums of its VEC columns over the rows of its row group; the row groups are then
+// added in order through shared memory.  Scalar path for other widths: a thread owns whole columns.
+template <class T> struct HidVec;
+template <> struct HidVec<float> { static constexpr int n = 4; };
+template <> struct HidVec<__nv_bfloat16> { static constexpr int n = 8; };
+
 template <class T>
 __global__ void __launch_bounds__(256) hidden_dpre_kernel(const T* __restrict__ dh0, const T* __restrict__ dh1, const T* __restrict__ h0,
                                                           const T* __restrict__ h1, T* __restrict__ dp0, T* __restrict__ dp1,
-                                                          float* __restrict__ dbpart, int B, int Dout, int ldp, float scale, int nblocks) {
+                                                          float* __restrict__ dbpart, int B, int Dout, float scale, int nblocks) {
+  constexpr int VEC = HidVec<T>::n;
+  __shared__ float colsum[256 * VEC];
   const int m = blockIdx.y, blk = blockIdx.x;
   const T* dh = m ? dh1 : dh0; const T* h = m ? h1 : h0; T* dp = m ? dp1 : dp0;
   const int r0 = blk * kHidRowsPerCta, r1 = min(B, r0 + kHidRowsPerCta);
-  for (int c = threadIdx.x; c < ldp; c += 256) {
-    float s = 0.f;
-    if (c < Dout) {
-#pragma unroll 8
-      for (int r = r0; r < r1; ++r) {
-        const float hv = hid_ld(h + (size_t)r * Dout + c), g = hid_ld(dh + (size_t)r * Dout + c);
-        T out;
-        hid_st(&out, hv > 0.f ? g * scale : 0.f);
-        dp[(size_t)r * ldp + c] = out;
-        s += hid_ld(&out);                               // the column sum of what the GEMMs will read (bf16-rounded in bf16 mode)
+  float* dst = dbpart + ((size_t)m * nblocks + blk) * Dout;
+  const int tpr = Dout / VEC;                                    // threads per row
+  if (Dout % VEC == 0 && tpr <= 256 && 256 % tpr == 0) {
+    const int q = threadIdx.x % tpr, rg = threadIdx.x / tpr, R = 256 / tpr;
+    float s[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) s[e] = 0.f;
+#pragma unroll 4
+    for (int r = r0 + rg; r < r1; r += R) {
+      const uint4 hv = *reinterpret_cast<const uint4*>(h + (size_t)r * Dout + q * VEC);
+      const uint4 gv = *reinterpret_cast<const uint4*>(dh + (size_t)r * Dout + q * VEC);
+      uint4 ov;
+      const T* hp = reinterpret_cast<const T*>(&hv); const T* gp = reinterpret_cast<const T*>(&gv); T* op = reinterpret_cast<T*>(&ov);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        hid_st(op + e, hid_ld(hp + e) > 0.f ? hid_ld(gp + e) * scale : 0.f);
+        s[e] += hid_ld(op + e);                                  // what the GEMMs will read (bf16-rounded in bf16 mode)
       }
-    } else {
-      for (int r = r0; r < r1; ++r) hid_st(dp + (size_t)r * ldp + c, 0.f);
+      *reinterpret_cast<uint4*>(dp + (size_t)r * Dout + q * VEC) = ov;
     }
-    if (c < Dout) dbpart[((size_t)m * nblocks + blk) * Dout + c] = s;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) colsum[(rg * tpr + q) * VEC + e] = s[e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < Dout; c += 256) {
+      float t = 0.f;
+      for (int g = 0; g < R; ++g) t += colsum[g * Dout + c];
+      dst[c] = t;
+    }
+    return;
+  }
+  for (int c = threadIdx.x; c < Dout; c += 256) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      T out;
+      hid_st(&out, hid_ld(h + (size_t)r * Dout + c) > 0.f ? hid_ld(dh + (size_t)r * Dout + c) * scale : 0.f);
+      dp[(size_t)r * Dout + c] = out;
+      s += hid_ld(&out);
+    }
+    dst[c] = s;
   }
 }
 
+// db = the block partials added per column: one warp per column, lane l takes blocks l, l + 32, ... in order, fixed butterfly
 __global__ void __launch_bounds__(256) hidden_db_kernel(const float* __restrict__ dbpart, float* __restrict__ db0, float* __restrict__ db1,
                                                         int Dout, int nblocks) {
-  const int m = blockIdx.y;
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
   float* db = m ? db1 : db0;
-  for (int c = blockIdx.x * 256 + threadIdx.x; c < Dout; c += gridDim.x * 256) {
+  for (int c = blockIdx.x * 8 + (threadIdx.x >> 5); c < Dout; c += gridDim.x * 8) {
     float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += dbpart[((size_t)m * nblocks + b) * Dout + c];
-    db[c] = s;
+    for (int b = lane; b < nblocks; b += 32) s += dbpart[((size_t)m * nblocks + b) * Dout + c];
+    s = warp_sum(s);
+    if (lane == 0) db[c] = s;
   }
 }
 
@@ -141,15 +175,15 @@ extern "C" int lf_hidden_backward(const LfHiddenArgs* a, void* stream) {
   if (bf16) {
     LF_LAUNCH("hidden_dpre", s, (hidden_dpre_kernel<__nv_bfloat16><<<dim3(nblocks, 2), 256, 0, s>>>(
         (const __nv_bfloat16*)a->dh[0], (const __nv_bfloat16*)a->dh[1], (const __nv_bfloat16*)a->h[0], (const __nv_bfloat16*)a->h[1],
-        (__nv_bfloat16*)a->dpre[0], (__nv_bfloat16*)a->dpre[1], w.dbpart, B, Dout, Dout, scale, nblocks)));
+        (__nv_bfloat16*)a->dpre[0], (__nv_bfloat16*)a->dpre[1], w.dbpart, B, Dout, scale, nblocks)));
   } else {
     LF_LAUNCH("hidden_dpre", s, (hidden_dpre_kernel<float><<<dim3(nblocks, 2), 256, 0, s>>>(
         (const float*)a->dh[0], (const float*)a->dh[1], (const float*)a->h[0], (const float*)a->h[1], (float*)a->dpre[0], (float*)a->dpre[1],
-        w.dbpart, B, Dout, Dout, scale, nblocks)));
+        w.dbpart, B, Dout, scale, nblocks)));
   }
   rc = check_launch("hidden_dpre_kernel");
   if (rc) return rc;
-  LF_LAUNCH("hidden_db", s, (hidden_db_kernel<<<dim3(div_up(Dout, 256), 2), 256, 0, s>>>(w.dbpart, a->dbias[0], a->dbias[1], Dout, nblocks)));
+  LF_LAUNCH("hidden_db", s, (hidden_db_kernel<<<dim3(min(296, div_up(Dout, 8)), 2), 256, 0, s>>>(w.dbpart, a->dbias[0], a->dbias[1], Dout, nblocks)));
   rc = check_launch("hidden_db_kernel");
   if (rc) return rc;
   // ---- dX = dP W   (A = dP K-major, B = W (Dout x Din) row-major = MN-major)

@@ -8,7 +8,7 @@
 // has no grid-wide dependency, so forward AND backward are ONE pass over the features: a CTA walks tiles of S samples;
 // per tile the features of all modalities are staged side by side in shared memory ([S][sum D_m]), the heads are resident
 // in shared memory for the whole kernel, and four phases run on the tile:
-//   A  coalesced loads of the tile                          B  one thread per (sample, modality, class) dot product
+//   A  coalesced loads of the tile                          B  one thread per (sample, modality): all C dot products together
 //   C  one thread per sample: mean, softmax, CE, argmaxes, dz
 //   D  one thread per feature column: df (written once, coalesced) and the dW column, accumulated in a shared-memory
 //      column the thread owns (no atomics); db by one thread per class
@@ -47,23 +47,27 @@ __device__ __forceinline__ int modality_of(const MultiParams& p, int j) {
 
 template <int CPAD>
 __global__ void __launch_bounds__(kMultiThreads) multi_heads_kernel(MultiParams p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int C = p.C, M = p.M, S = p.S, Dtot = p.Dtot, ldw = p.ldw;
-  float* Ws = sm;                               // [C][ldw]   heads side by side; ldw odd: class rows on different banks
-  float* dWs = Ws + (size_t)C * ldw;            // [C][Dtot]  this CTA's dW, column j owned by thread j % blockDim
-  float* fs = dWs + (size_t)C * Dtot;           // [S][ldw]   feature tile
+  float* Wt = sm;                               // [Dtot][CPAD]  heads side by side, TRANSPOSED: the C weights of a feature are one
+                                                //               16-byte-aligned row, read with broadcast LDS.128
+  float* dzs = Wt + (size_t)Dtot * CPAD;        // [S][CPAD]     avg, then dz (same reason for the pitch)
+  float* dWs = dzs + (size_t)S * CPAD;          // [C][Dtot]     this CTA's dW, column j owned by one thread
+  float* fs = dWs + (size_t)C * Dtot;           // [S][ldw]      feature tile; ldw odd: samples on different banks
   float* zs = fs + (size_t)S * ldw;             // [S][M*C]
-  float* dzs = zs + (size_t)S * M * C;          // [S][C]     avg, then dz
-  float* bs = dzs + (size_t)S * C;              // [M*C]
+  float* bs = zs + (size_t)S * M * C;           // [M*C]
   double* red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(bs + M * C) + 7) & ~(uintptr_t)7);   // [S][2 + M] end-of-kernel reduction
   const int tid = threadIdx.x;
 
+  for (int i = tid; i < Dtot * CPAD; i += kMultiThreads) Wt[i] = 0.f;
+  __syncthreads();
   for (int m = 0; m < M; ++m) {
     const int Dm = p.D[m], o = p.off[m];
-    for (int i = tid; i < C * Dm; i += kMultiThreads) { const int c = i / Dm, d = i - c * Dm; Ws[c * ldw + o + d] = p.W[m][i]; }
+    for (int i = tid; i < C * Dm; i += kMultiThreads) { const int c = i / Dm, d = i - c * Dm; Wt[(o + d) * CPAD + c] = p.W[m][i]; }
     for (int c = tid; c < C; c += kMultiThreads) bs[m * C + c] = p.bias[m][c];
   }
   for (int i = tid; i < C * Dtot; i += kMultiThreads) dWs[i] = 0.f;
+  for (int i = tid; i < S * CPAD; i += kMultiThreads) dzs[i] = 0.f;      // the pad columns stay zero
   double ce = 0.0;                               // thread s < S: sums over the samples it owned
   int hits_joint = 0, hits_m[LF_MAX_MODALITIES] = {0, 0, 0, 0};
   float db_acc = 0.f;                            // thread c < C
@@ -89,22 +93,35 @@ __global__ void __launch_bounds__(kMultiThreads) multi_heads_kernel(MultiParams 
       }
     }
     __syncthreads();
-    // ---- B: logits, one (sample, modality, class) per thread and trip
-    for (int i = tid; i < rows * M * C; i += kMultiThreads) {
-      const int c = i % C; const int t = i / C; const int m = t % M, s = t / M;
+    // ---- B: logits.  One (modality, sample) per thread, modality-major so that a warp shares the weight rows it reads;
+    // all C dot products of the pair advance together: per feature one LDS of f and CPAD / 4 broadcast LDS.128 of weights
+    for (int i = tid; i < rows * M; i += kMultiThreads) {
+      const int m = i / rows, s = i - m * rows;
       const float* fr = fs + s * ldw + p.off[m];
-      const float* wr = Ws + c * ldw + p.off[m];
-      float z = 0.f;
-      for (int d = 0; d < p.D[m]; ++d) z = fmaf(fr[d], wr[d], z);
-      z += bs[m * C + c];
-      zs[(s * M + m) * C + c] = z;
-      p.logits[m][(size_t)(row0 + s) * C + c] = z;
+      const float4* wr = reinterpret_cast<const float4*>(Wt + (size_t)p.off[m] * CPAD);
+      float acc[CPAD];
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) acc[c] = 0.f;
+      for (int d = 0; d < p.D[m]; ++d) {
+        const float fv = fr[d];
+#pragma unroll
+        for (int q = 0; q < CPAD / 4; ++q) {
+          const float4 w4 = wr[d * (CPAD / 4) + q];
+          acc[4 * q + 0] = fmaf(fv, w4.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(fv, w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(fv, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(fv, w4.w, acc[4 * q + 3]);
+        }
+      }
+      float* zr = zs + (s * M + m) * C;
+      float* out = p.logits[m] + (size_t)(row0 + s) * C;
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c)
+        if (c < C) { const float z = acc[c] + bs[m * C + c]; zr[c] = z; out[c] = z; }
     }
     __syncthreads();
     // ---- C: row math, one sample per thread
     for (int s = tid; s < rows; s += kMultiThreads) {
       const float* zr = zs + s * M * C;
-      float* ar = dzs + s * C;
+      float* ar = dzs + s * CPAD;
       const long long y = (long long)p.label[row0 + s];
       float mx = -INFINITY; int arg = 0;
       for (int c = 0; c < C; ++c) {
@@ -136,21 +153,30 @@ __global__ void __launch_bounds__(kMultiThreads) multi_heads_kernel(MultiParams 
       const int Dm = p.D[m], d = j - p.off[m];
       float w[CPAD], acc[CPAD];
 #pragma unroll
-      for (int c = 0; c < CPAD; ++c) { w[c] = c < C ? Ws[c * ldw + j] : 0.f; acc[c] = 0.f; }
+      for (int q = 0; q < CPAD / 4; ++q) {
+        const float4 w4 = reinterpret_cast<const float4*>(Wt + (size_t)j * CPAD)[q];
+        w[4 * q] = w4.x; w[4 * q + 1] = w4.y; w[4 * q + 2] = w4.z; w[4 * q + 3] = w4.w;
+      }
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) acc[c] = 0.f;
       float* out = p.dfeat[m] + (size_t)row0 * Dm + d;
       for (int s = 0; s < rows; ++s) {
         const float fv = fs[s * ldw + j];
-        const float* dz = dzs + s * C;
+        const float4* dz4 = reinterpret_cast<const float4*>(dzs + s * CPAD);
         float g = 0.f;
 #pragma unroll
-        for (int c = 0; c < CPAD; ++c)
-          if (c < C) { const float v = dz[c]; g = fmaf(v, w[c], g); acc[c] = fmaf(v, fv, acc[c]); }
+        for (int q = 0; q < CPAD / 4; ++q) {                    // pad columns of dz and w are zero
+          const float4 v = dz4[q];
+          g = fmaf(v.x, w[4 * q], g); g = fmaf(v.y, w[4 * q + 1], g); g = fmaf(v.z, w[4 * q + 2], g); g = fmaf(v.w, w[4 * q + 3], g);
+          acc[4 * q] = fmaf(v.x, fv, acc[4 * q]); acc[4 * q + 1] = fmaf(v.y, fv, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v.z, fv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v.w, fv, acc[4 * q + 3]);
+        }
         if (p.need_dfeat) out[(size_t)s * Dm] = g;
       }
 #pragma unroll
       for (int c = 0; c < CPAD; ++c) if (c < C) dWs[c * Dtot + j] += acc[c];
     }
-    if (tid < C) for (int s = 0; s < rows; ++s) db_acc += dzs[s * C + tid];
+    if (tid < C) for (int s = 0; s < rows; ++s) db_acc += dzs[s * CPAD + tid];
     __syncthreads();
   }
   // ---- this CTA's partials
@@ -170,39 +196,46 @@ __global__ void __launch_bounds__(kMultiThreads) multi_heads_kernel(MultiParams 
   }
 }
 
-// Sums of the per-CTA partials in CTA order: dW (scattered back to the per-modality tensors), db (the same vector for
-// every head: dz does not depend on the modality), statistics and the batch-mean loss.
+// Sums of the per-CTA partials: dW (scattered back to the per-modality tensors), db (the same vector for every head: dz
+// does not depend on the modality), statistics and the batch-mean loss.  One WARP per output: lane l adds partials l,
+// l + 32, ... in order and a fixed butterfly adds the lanes -- the same order on every launch, and ~nparts / 32 dependent
+// loads per lane instead of nparts (the first version's one thread per output took 50 us for 592 partials).
 __global__ void __launch_bounds__(256) multi_finalize_kernel(MultiParams p, int nparts, float* dweight0, float* dweight1, float* dweight2,
                                                             float* dweight3, float* dbias0, float* dbias1, float* dbias2, float* dbias3,
                                                             double* stats, float* loss_out) {
   float* dweight[LF_MAX_MODALITIES] = {dweight0, dweight1, dweight2, dweight3};
   float* dbias[LF_MAX_MODALITIES] = {dbias0, dbias1, dbias2, dbias3};
-  const int n = p.C * p.Dtot;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int g = 0; g < nparts; ++g) s += p.dw_part[(size_t)g * n + i];
-    const int c = i / p.Dtot, j = i - c * p.Dtot;
-    const int m = modality_of(p, j);
-    dweight[m][(size_t)c * p.D[m] + (j - p.off[m])] = s;
-  }
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+  const int n = p.C * p.Dtot, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+  const int extra = p.C + 2 + p.M;                     // db entries and statistics follow the dW elements
+  for (int i = warp; i < n + extra; i += nwarps) {
+    if (i < n) {
       float s = 0.f;
-      for (int g = 0; g < nparts; ++g) s += p.db_part[(size_t)g * p.C + c];
-      for (int m = 0; m < p.M; ++m) dbias[m][c] = s;
-    }
-    if (threadIdx.x < 2 + p.M) {
+      for (int g = lane; g < nparts; g += 32) s += p.dw_part[(size_t)g * n + i];
+      s = warp_sum(s);
+      const int c = i / p.Dtot, j = i - c * p.Dtot;
+      const int m = modality_of(p, j);
+      if (lane == 0) dweight[m][(size_t)c * p.D[m] + (j - p.off[m])] = s;
+    } else if (i < n + p.C) {
+      const int c = i - n;
+      float s = 0.f;
+      for (int g = lane; g < nparts; g += 32) s += p.db_part[(size_t)g * p.C + c];
+      s = warp_sum(s);
+      if (lane == 0) for (int m = 0; m < p.M; ++m) dbias[m][c] = s;
+    } else {
+      const int k = i - n - p.C;
       double s = 0.0;
-      for (int g = 0; g < nparts; ++g) s += p.st_part[(size_t)g * (2 + p.M) + threadIdx.x];
-      stats[threadIdx.x] = s;
-      if (threadIdx.x == 0) loss_out[0] = (float)(s / (double)p.B);
+      for (int g = lane; g < nparts; g += 32) s += p.st_part[(size_t)g * (2 + p.M) + k];
+      s = warp_sum(s);
+      if (lane == 0) { stats[k] = s; if (k == 0) loss_out[0] = (float)(s / (double)p.B); }
     }
   }
 }
 
+static int multi_cpad(int C) { return C <= 4 ? 4 : C <= 8 ? 8 : C <= 16 ? 16 : 32; }
 static size_t multi_smem_bytes(int M, int C, int Dtot, int S) {
-  const int ldw = Dtot | 1;
-  size_t f = (size_t)C * ldw + (size_t)C * Dtot + (size_t)S * ldw + (size_t)S * M * C + (size_t)S * C + (size_t)M * C;
+  const int ldw = Dtot | 1, cpad = multi_cpad(C);
+  size_t f = (size_t)Dtot * cpad + (size_t)S * cpad + (size_t)C * Dtot + (size_t)S * ldw + (size_t)S * M * C + (size_t)M * C;
   return f * sizeof(float) + 8 + (size_t)S * (2 + M) * sizeof(double);
 }
 
@@ -288,7 +321,7 @@ extern "C" int lf_multi_heads_step(const LfMultiHeadsArgs* a, void* stream) {
   else launch(multi_heads_kernel<32>);
   rc = check_launch("multi_heads_kernel");
   if (rc) return rc;
-  const int fgrid = min(148, div_up((long long)p.C * Dtot, 256));
+  const int fgrid = min(592, div_up((long long)p.C * Dtot + p.C + 2 + p.M, 8));
   float* dw[LF_MAX_MODALITIES]; float* db[LF_MAX_MODALITIES];
   for (int m = 0; m < LF_MAX_MODALITIES; ++m) { const int k = m < a->modalities ? m : 0; dw[m] = a->dweight[k]; db[m] = a->dbias[k]; }
   LF_LAUNCH("multi_heads_finalize", s, (multi_finalize_kernel<<<fgrid, 256, 0, s>>>(p, grid, dw[0], dw[1], dw[2], dw[3], db[0], db[1], db[2], db[3],

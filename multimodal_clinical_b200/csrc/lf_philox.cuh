@@ -19,8 +19,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-// Keep-mask bits of the dropout epilogue: element e (= row * N + col) of a tensor draws word (e & 3) of the Philox block
-// whose counter is (e >> 2, rng_offset); an element is KEPT when its word >= p * 2^32.
+// Random words of the dropout epilogue (lf_tc.cu::relu_dropout): element e (= row * N + col) of a tensor draws the 16-bit
+// half (e & 7) of the Philox block whose counter is (e >> 3, rng_offset); it is KEPT when the half >= round(p * 65536).
 __device__ __forceinline__ uint4 dropout_words(unsigned long long group, unsigned long long seed, unsigned long long offset) {
   return philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));

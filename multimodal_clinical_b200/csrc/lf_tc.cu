@@ -262,22 +262,25 @@ __device__ __forceinline__ void gemm_tail(const TcGemmParams& p, float* s_rows) 
   }
 }
 
-// Epilogue activation of the hidden layers: relu, then inverted dropout.  v holds n (multiple of 4) consecutive columns of
-// output row `row` starting at column col0 (multiple of 4).
-template <int N4>
+// Epilogue activation of the hidden layers: relu, then inverted dropout.  v holds 8 * N8 consecutive columns of output row
+// `row` starting at column col0 (multiple of 8).  Element e = row * N + col draws 16 bits -- half (e & 7) of the Philox block
+// with counter (e >> 3, rng_offset) -- and is kept when they are >= round(p * 65536): one Philox call per eight elements.
+template <int N8>
 __device__ __forceinline__ void relu_dropout(float* v, long long row, int col0, const TcGemmParams& p) {
 #pragma unroll
-  for (int i = 0; i < 4 * N4; ++i) v[i] = relu_nan(v[i]);
+  for (int i = 0; i < 8 * N8; ++i) v[i] = relu_nan(v[i]);
   if (p.drop_p > 0.f) {
-    const uint32_t thr = (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967040.f);
-    const unsigned long long g0 = ((unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col0) >> 2;
+    const uint32_t thr = (uint32_t)(p.drop_p * 65536.f + 0.5f);
+    const unsigned long long g0 = ((unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col0) >> 3;
 #pragma unroll
-    for (int g = 0; g < N4; ++g) {
+    for (int g = 0; g < N8; ++g) {
       const uint4 r = dropout_words(g0 + g, p.seed, p.rng_offset);
-      v[4 * g + 0] = r.x >= thr ? v[4 * g + 0] * p.drop_scale : 0.f;
-      v[4 * g + 1] = r.y >= thr ? v[4 * g + 1] * p.drop_scale : 0.f;
-      v[4 * g + 2] = r.z >= thr ? v[4 * g + 2] * p.drop_scale : 0.f;
-      v[4 * g + 3] = r.w >= thr ? v[4 * g + 3] * p.drop_scale : 0.f;
+      const uint32_t wds[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[8 * g + 2 * k] = (wds[k] & 0xffffu) >= thr ? v[8 * g + 2 * k] * p.drop_scale : 0.f;
+        v[8 * g + 2 * k + 1] = (wds[k] >> 16) >= thr ? v[8 * g + 2 * k + 1] * p.drop_scale : 0.f;
+      }
     }
   }
 }
@@ -461,7 +464,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
               for (int i = 0; i < 32; ++i) { const int col = w.n0 + c0 + i; v[i] += col < p.N ? __ldg(bias + col) : 0.f; }
             }
-            if (ACT) relu_dropout<8>(v, (long long)w.m0 + row_in_tile, w.n0 + c0, p);
+            if (ACT) relu_dropout<4>(v, (long long)w.m0 + row_in_tile, w.n0 + c0, p);
 #pragma unroll
             for (int i = 0; i < 32; ++i) pk[i] = w.num_kb == 0 ? 0u : __float_as_uint(v[i]);
           } else {
@@ -474,7 +477,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { const int col = w.n0 + c0 + 16 * h + i; v[i] += col < p.N ? __ldg(bias + col) : 0.f; }
               }
-              if (ACT) relu_dropout<4>(v, (long long)w.m0 + row_in_tile, w.n0 + c0 + 16 * h, p);
+              if (ACT) relu_dropout<2>(v, (long long)w.m0 + row_in_tile, w.n0 + c0 + 16 * h, p);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
@@ -695,8 +698,8 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   p.tma_store = aligned ? 1 : 0;
   p.act_relu = d.act_relu; p.drop_p = d.drop_p; p.drop_scale = d.drop_p > 0.f ? 1.f / (1.f - d.drop_p) : 1.f;
   p.seed = d.seed; p.rng_offset = d.rng_offset;
-  if (d.act_relu && (!p.tma_store || (d.N & 3) || d.splits > 1 || d.drop_p < 0.f || d.drop_p >= 1.f)) {
-    set_error("tc_gemm: the relu / dropout epilogue needs the TMA-store path, N %% 4 == 0, no split-K and 0 <= p < 1");
+  if (d.act_relu && (!p.tma_store || (d.N & 7) || d.splits > 1 || d.drop_p < 0.f || d.drop_p >= 1.f)) {
+    set_error("tc_gemm: the relu / dropout epilogue needs the TMA-store path, N %% 8 == 0, no split-K and 0 <= p < 1");
     return LF_ERR_BAD_ARG;
   }
   if (p.out_elem == 2 && !p.tma_store) { set_error("tc_gemm: bf16 output needs the TMA-store epilogue (16-byte pitch, no bias)"); return LF_ERR_BAD_ARG; }
@@ -750,7 +753,8 @@ int tc_gemm(const TcGemmDesc& d, cudaStream_t s) {
   // the second epilogue half pays when the epilogue bounds the kernel: short K (tc_dfeat of a <= 128-way head: ten
   // 128 x 256 output tiles per CTA, two k-blocks each); with long K its two extra staging boxes cost a pipeline stage
   // (x3: warps 6-9 are the converters, so one half)
-  p.epi_halves = (p.tma_store && d.K <= 128 && d.max_epi_halves >= 2 && !p.x3) ? 2 : 1;
+  // (the activation epilogue -- Philox per eight outputs -- is the longer side of an item even at K = 768: two halves too)
+  p.epi_halves = (p.tma_store && (d.K <= 128 || d.act_relu) && d.max_epi_halves >= 2 && !p.x3) ? 2 : 1;
   const size_t staging_bytes = (size_t)2 * p.epi_halves * TC_BLOCK_M * 128;
   const size_t fixed = staging_bytes + 320;
   int stages = 8;

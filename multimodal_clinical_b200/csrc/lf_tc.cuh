@@ -57,8 +57,8 @@ struct TcGemmParams {
                            // accumulator truncates on every MMA, so a long K chain in TMEM loses ~5e-9 * K relative
   int act_relu;            // epilogue (TMA-store path): out = dropout(relu(acc + bias)) -- the hidden layers of the Food101 MLPs
   float drop_p, drop_scale;           // dropout probability (0 = off) and 1 / (1 - p)
-  unsigned long long seed, rng_offset; // Philox4x32-10 key / counter high words; element (row, col) draws word (col & 3) of
-                                       // counter group (row * N + col) / 4, so the mask does not depend on the tiling
+  unsigned long long seed, rng_offset; // Philox4x32-10 key / counter high words; element (row, col) draws 16-bit half
+                                       // (e & 7) of counter group e >> 3, e = row * N + col: the mask does not depend on the tiling
   int x3;                  // fp32 operands split into tf32 hi + lo in shared memory, three MMAs per k-step (exact-fp32 tier)
   int out_elem;            // output element size (TMA-store epilogue): 4 = fp32, 2 = bf16
   int kb_elems;            // K elements per stage (128 B per operand row): 32 / 64
