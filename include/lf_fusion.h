@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LF_ABI_VERSION 11
+#define LF_ABI_VERSION 12
 
 /* error codes */
 #define LF_OK 0
@@ -118,7 +118,12 @@ typedef struct LfHeadsArgs {
                              Lets the narrow-head path (C <= 32) fuse forward and backward into one pass otherwise. */
   int32_t bwd_phase;      /* lf_heads_backward: 0 = everything; 1 = dL/dz, dW, db, calibrated counts (all but dfeat);
                              2 = dfeat only (after a phase-1 call).  Lets the caller start the gradient exchange of
-                             dW/db on a second stream while dfeat, which no other rank needs, is still being written. */
+                             dW/db on a second stream while dfeat, which no other rank needs, is still being written.
+                             3 = the row kernel only (QMF: dL/dz + db partials; both modes: calibrated counts, which need
+                             this step's EMA offsets); 4 = dW GEMM + finalisation only (after 3, and 2 if dfeat is wanted).
+                             With mean fusion dL/dz is final after the forward (cremad/joint_model_ogm_ge.py:54-56 has no
+                             grid-wide term), so a caller may run lf_step_mid + phase 3 on a second stream beside phase 2
+                             and join before phase 4.  Only where lf_heads_backward_splits_rows() says so. */
   int32_t ld_logits;      /* row pitch (elements) of logits[0], logits[1]; 0 = classes (dense).  A multiple of 4 lets the
                              tensor-pipe GEMM write them with TMA stores (1236-byte rows of a dense C = 309 cannot be). */
   int32_t ld_fused;       /* row pitch (elements) of avg_logits and logits_df; 0 = classes (dense).  A multiple of 4 (with 16-byte
@@ -147,6 +152,10 @@ typedef struct LfHeadsArgs {
 /* 1 when lf_heads_backward(args) would run the gradient all-reduce inside the dW kernel (tensor-pipe heads whose dW
    tiles fit one wave), i.e. when LfHeadsArgs.grad_comm is honoured; 0: the caller exchanges dweight / dbias itself. */
 int lf_heads_backward_fuses_allreduce(const LfHeadsArgs* args);
+
+/* 1 when lf_heads_backward accepts bwd_phase 3 / 4 for these arguments (every shape whose dL/dz comes from the stand-alone
+   row kernels: wide heads outside the fused QMF backward, exact-fp32 fallbacks); 0 for narrow heads and the fused backward. */
+int lf_heads_backward_splits_rows(const LfHeadsArgs* args);
 
 /* Floats per rank slot LfPeerComm.recv_grad must provide for that fused all-reduce ([dW1|dW2|db1|db2|cal x2|reg], 16-byte padded). */
 size_t lf_grad_exchange_floats(int32_t dim, int32_t classes);

@@ -121,6 +121,7 @@ SIGNATURES = {
     "lf_heads_forward": (C.c_int, [C.POINTER(LfHeadsArgs), C.c_void_p]),
     "lf_heads_backward": (C.c_int, [C.POINTER(LfHeadsArgs), C.c_void_p]),
     "lf_heads_backward_fuses_allreduce": (C.c_int, [C.POINTER(LfHeadsArgs)]),
+    "lf_heads_backward_splits_rows": (C.c_int, [C.POINTER(LfHeadsArgs)]),
     "lf_grad_exchange_floats": (C.c_size_t, [C.c_int32, C.c_int32]),
     "lf_cast_heads_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lf_loss_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

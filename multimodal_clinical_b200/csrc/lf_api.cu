@@ -369,7 +369,11 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   HeadsWorkspace w = carve_heads_workspace(a->workspace, a->batch, a->dim, a->classes);
   const int phase = a->bwd_phase;
-  if (phase < 0 || phase > 2) { set_error("bad bwd_phase %d", phase); return LF_ERR_BAD_ARG; }
+  if (phase < 0 || phase > 4) { set_error("bad bwd_phase %d", phase); return LF_ERR_BAD_ARG; }
+  if (phase >= 3 && !lf_heads_backward_splits_rows(a)) {
+    set_error("bwd_phase %d: this shape forms dL/dz inside a fused kernel (ask lf_heads_backward_splits_rows first)", phase);
+    return LF_ERR_UNSUPPORTED;
+  }
   if (use_narrow(a)) {
     if (phase == 2) return LF_OK;                 // dfeat is produced inside the fused narrow kernel
     const size_t cdn = (size_t)a->classes * a->dim;
@@ -403,13 +407,14 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
     void* df[2] = {a->dfeat[0], a->dfeat[1]};
     rc = tc_backward_qmf(rows_args(a, w), w16, df, a->dim, &nb_parts, s);
     if (rc) return rc;
-  } else if (phase != 2) {
+  } else if (phase != 2 && phase != 4) {
     rc = rows_backward(rows_args(a, w), a->mode, s);
     if (rc) return rc;
   }
+  if (phase == 3) return LF_OK;
   const float* dz[2] = {a->dlogits[0], a->mode == LF_MODE_QMF ? a->dlogits[1] : a->dlogits[0]};
   GemmArgs g;
-  if (a->need_dfeat && phase != 1 && !fused_bwd) {
+  if (a->need_dfeat && phase != 1 && phase != 4 && !fused_bwd) {
     memset(&g, 0, sizeof(g));
     for (int m = 0; m < 2; ++m) { g.A[m] = dz[m]; g.B[m] = a->weight[m]; g.bias[m] = nullptr; g.C[m] = a->dfeat[m]; }
     g.M = a->batch; g.N = a->dim; g.K = a->classes;
@@ -510,6 +515,18 @@ extern "C" int lf_heads_backward(const LfHeadsArgs* a, void* stream) {
   if (rc) return rc;
   return finalize_db_cal(w.db_partials, nb_db, a->classes, w.cal_partials, nb_parts, a->dbias[0], a->dbias[1],
                          a->stats, s);
+}
+
+// bwd_phase 3 / 4: the row kernel (dL/dz of QMF heads, calibrated counts) and the dW GEMM as separate calls, so that a
+// caller whose dL/dz is already final after the forward pass (mean fusion) can run lf_step_mid + the calibrated-count pass
+// on a second stream beside the dfeat GEMM.  Not for shapes that form dL/dz inside a fused kernel.
+extern "C" int lf_heads_backward_splits_rows(const LfHeadsArgs* a) {
+  if (!a || a->dim < 4 || a->classes < 1 || a->batch < 1) return 0;
+  if (use_narrow(a)) return 0;
+  const int ldz = a->ld_dlogits > 0 ? a->ld_dlogits : a->classes;
+  if (use_tensor_pipe(a) && tc_bwd_supported(a->mode, a->precision, a->batch, a->dim, a->classes,
+                                              a->ld_logits > 0 ? a->ld_logits : a->classes, ldz, a->need_dfeat)) return 0;
+  return 1;
 }
 
 extern "C" int lf_heads_backward_fuses_allreduce(const LfHeadsArgs* a) {

@@ -151,6 +151,10 @@ class LateFusionStep:
         self._w16_key = None
         self._sgd = None
         self._capturing = False
+        # mean fusion on wide heads: lf_step_mid + the calibrated-count pass beside the dfeat GEMM (see step());
+        # LF_NO_CAL_OVERLAP=1 keeps the single-stream order for A/B runs
+        self.cal_overlap = not os.environ.get("LF_NO_CAL_OVERLAP")
+        self._side = None
 
     # ------------------------------------------------------------------ fused SGD on the heads
     def enable_sgd(self, lr: float, momentum: float = 0.9, weight_decay: float = 1.0e-4) -> None:
@@ -401,6 +405,21 @@ class LateFusionStep:
         check(lib.lf_heads_forward(C.byref(a), st), "lf_heads_forward")
         if peer is not None:
             peer.check()                                          # pinned host flag: no synchronisation
+        # Mean fusion (cremad/joint_model_ogm_ge.py:54-56): dL/dz is final after the forward pass, so the dfeat GEMM does
+        # not depend on lf_step_mid; only the calibrated counts need this step's EMA offsets.  lf_step_mid and the
+        # calibrated-count pass (a second read of the logits: 324 MB at the VGGSound shape) then run on a second stream
+        # BESIDE the dfeat GEMM, which leaves half of the HBM bandwidth and most registers of an SM unused, and join
+        # before the dW GEMM, whose tail consumes the counts.
+        overlap = (backward and self.cal_overlap and self.mode == LF_MODE_JLOGITS and (self.world == 1 or fuse_ar)
+                   and bool(lib.lf_heads_backward_splits_rows(C.byref(a))))
+        main_stream = side = None
+        if overlap:
+            main_stream = torch.cuda.current_stream()
+            side = self._side_stream()
+            side.wait_stream(main_stream)
+            mid_st = side.cuda_stream
+        else:
+            mid_st = st
         stride = pay.numel()
         mid = LfMidArgs()
         if peer is not None:
@@ -441,16 +460,14 @@ class LateFusionStep:
             if getattr(self, "_reg_partial", None) is None:
                 self._reg_partial = torch.zeros(4, device=self.device)
             mid.reg_partial_out = _ptr(self._reg_partial)
-        check(lib.lf_step_mid(C.byref(mid), st), "lf_step_mid")
+        check(lib.lf_step_mid(C.byref(mid), mid_st), "lf_step_mid")
         if update_ema:
             self.ema_counter += 1
             if self.ema is not None:
                 self.ema.counter += 1
         if backward:
             a.stats = _ptr(self.stats)                            # calibrated counts join the GLOBAL statistics
-            if self.world == 1:
-                check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
-            elif fuse_ar:
+            if fuse_ar:
                 # ONE launch sequence: the all-reduce of [dW|db|calibrated counts|ranking-loss partial] (and the SGD step)
                 # run in the tail of the dW kernel over peer memory
                 gcomm = _lib.LfPeerComm()
@@ -458,6 +475,15 @@ class LateFusionStep:
                 a.grad_comm = C.pointer(gcomm)
                 if hist:
                     a.reg_partial, a.loss_out = _ptr(self._reg_partial), _ptr(self.loss)
+            if overlap:
+                a.bwd_phase = 3                                   # calibrated counts, behind lf_step_mid on the second stream
+                check(lib.lf_heads_backward(C.byref(a), mid_st), "lf_heads_backward")
+                a.bwd_phase = 2                                   # dfeat GEMM on the main stream, beside them
+                check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
+                main_stream.wait_stream(side)
+                a.bwd_phase = 4                                   # dW GEMM + tail (reduction, db, counts, [all-reduce], SGD)
+                check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
+            elif self.world == 1 or fuse_ar:
                 check(lib.lf_heads_backward(C.byref(a), st), "lf_heads_backward")
             else:
                 # dW / db first, then their exchange on a side stream while dfeat (which no other rank needs) is

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, n), f"{n} declared in include/lf_fusion.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.lf_abi_version() == 11
+    assert lib.lf_abi_version() == 12
 
 
 def test_struct_layout_matches_c(tmp_path):
