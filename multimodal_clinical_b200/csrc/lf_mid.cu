@@ -15,6 +15,8 @@
 //   [C  min / max over the whole History | History.confidence of the winners | correctness gathers of this rank's pairs]
 //                                                                                            -- barrier 2 --
 //   [D  ranking terms, dL/dconf of this rank's slice; the last CTA to finish assembles the loss]
+// Heads without a History (mean fusion, the ensemble loss) take mid_light_kernel at the end of this file: one CTA, an
+// ordinary launch.
 // Sharded runs start with the exchange of [statistics | idx | conf] over NVLink peer memory (lf_peer.cuh: plain stores
 // into the peers' receive slots, readers validate against a sentinel: no fence, flag or barrier).
 //
@@ -190,7 +192,6 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_kernel(MidParams p) {
   const int tid = cta * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarp = (int)blockDim.x / 32;
   const int C = a.classes, len = LF_STATS_HEADER + 2 * C, Bg = a.batch_global, N = a.n_data;
-  extern __shared__ double s_stats[];                 // mean fusion only: [len] global statistics
   __shared__ MidShared sh;
   __shared__ double slo[2][kMidThreads / 32], shi[2][kMidThreads / 32];
   __shared__ double s_rows[kMidRows][kMidCols], s_col[kMidCols];
@@ -203,8 +204,7 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_kernel(MidParams p) {
   // ---- exchange (sharded runs): this rank's statistics and per-sample records {idx, conf0, conf1} are stored into
   // slot [parity][rank] of every rank's receive area (NVLink stores; the local copy too, so readers see one layout).
   // No fence, flag or barrier follows: readers validate the words they need against the sentinel (lf_peer.cuh).
-  // (QMF heads with LF_LOSS_NO_REG -- the ensemble loss -- have no History / ranking part: they take the light path)
-  const bool qmf = a.mode == LF_MODE_QMF && !(a.loss_terms & LF_LOSS_NO_REG);
+  // (mean fusion, and QMF heads with LF_LOSS_NO_REG -- the ensemble loss -- have no History / ranking part: mid_light_kernel)
   long long epoch = 0;
   const char* rec_base = nullptr;              // local receive area of this epoch's parity
   const long long stats_bytes = ((long long)len * 8 + 15) / 16 * 16;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_kernel(MidParams p) {
 #pragma unroll 1
       for (int r = 0; r < a.n_ranks; ++r) reinterpret_cast<double*>((char*)a.comm.recv_payload[r] + slot)[c] = v;
     }
-    if (qmf) {
+    {
       const int64_t* isrc = a.payload_idx_src ? a.payload_idx_src : (const int64_t*)((const char*)a.payload_local + a.off_idx);
       const float* csrc = (const float*)((const char*)a.payload_local + a.off_conf);
 #pragma unroll 1
@@ -258,38 +258,6 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_kernel(MidParams p) {
 #pragma unroll 1
     for (size_t i = tid; i < n16; i += nthr) q[i] = ones;
   };
-
-  if (!qmf) {
-    // ---- mean fusion (one CTA): global statistics in rank order, EMA, OGM-GE coefficients, loss
-    for (int i = threadIdx.x; i < len; i += blockDim.x) {
-      double s = 0.0;
-      for (int r = 0; r < nrow; ++r) s += stat_at(r, i);
-      s_stats[i] = s;
-    }
-    __syncthreads();
-    if (rec_base && ncta == 1) rearm();     // (one CTA: every read of the slots is behind the barrier above)
-    if (cta == 0) {
-      for (int i = threadIdx.x; i < len; i += blockDim.x)
-        if (i != LF_STAT_CNT_X1_CAL && i != LF_STAT_CNT_X2_CAL) a.stats[i] = s_stats[i];
-      if (a.update_ema)
-        for (int c = threadIdx.x; c < C; c += blockDim.x) ema_class(a, c, s_stats[LF_STATS_HEADER + c], s_stats[LF_STATS_HEADER + C + c]);
-      if (threadIdx.x == 0) {
-        if (a.coeff_out) ogm_coeff_write(a, (float)s_stats[LF_STAT_SCORE_X1], (float)s_stats[LF_STAT_SCORE_X2]);
-        if (a.loss_out) {
-          if (a.mode == LF_MODE_QMF) {         // ensemble: CE(z1) + CE(z2) (+ CE(z_df) unless ablated), each a separate fp32 mean
-            const double inv = 1.0 / (double)Bg;
-            const float uni = (a.loss_terms & LF_LOSS_NO_UNI) ? 0.f : (float)(s_stats[LF_STAT_CE_X1] * inv) + (float)(s_stats[LF_STAT_CE_X2] * inv);
-            const float joint = (a.loss_terms & LF_LOSS_NO_JOINT) ? 0.f : (float)(s_stats[LF_STAT_CE_JOINT] * inv);
-            a.loss_out[0] = joint + uni;
-          } else {
-            a.loss_out[0] = (float)(s_stats[LF_STAT_CE_JOINT] / (double)Bg);
-          }
-        }
-        if (a.use_peer) a.comm.epoch[0] = epoch;
-      }
-    }
-    return;
-  }
 
   // =========================================== QMF ===========================================
   __shared__ Gathered sg;
@@ -592,6 +560,81 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_kernel(MidParams p) {
   stamp(6);
 }
 
+// ---- mean fusion, and the ensemble loss (QMF heads without History / ranking term): global statistics in rank order,
+// EMA, OGM-GE coefficients, loss.  One CTA, no grid barrier -> an ordinary (non-cooperative) launch, and 128 bytes of
+// shared memory: the step runs this kernel and the calibrated-count pass on a second stream BESIDE the dfeat GEMM
+// (LfHeadsArgs.bwd_phase 3), whose CTAs leave ~2.7 KB of every SM's shared memory free.  A thread sums the column(s)
+// it needs itself (the class threads sum their partner column a second time) instead of staging all sums.
+__global__ void __launch_bounds__(256, 1) mid_light_kernel(MidParams p) {
+  const LfMidArgs& a = p.a;
+  const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
+  const int C = a.classes, len = LF_STATS_HEADER + 2 * C, Bg = a.batch_global;
+  __shared__ double s_hdr[LF_STATS_HEADER];
+  long long epoch = 0;
+  const char* rec_base = nullptr;
+  if (a.use_peer) {
+    // this rank's finished statistics into slot [parity][rank] of every rank's receive area (lf_peer.cuh: plain stores,
+    // the readers validate every word against the sentinel)
+    epoch = a.comm.epoch[0] + 1;
+    const int parity = (int)(epoch & 1);
+    const size_t slot = ((size_t)parity * a.n_ranks + a.rank) * (size_t)a.payload_bytes;
+    const double* st_src = (const double*)a.payload_local;
+    for (int c = tid; c < len; c += nthr) {
+      const double v = clean_f64(st_src[c]);
+#pragma unroll 1
+      for (int r = 0; r < a.n_ranks; ++r) reinterpret_cast<double*>((char*)a.comm.recv_payload[r] + slot)[c] = v;
+    }
+    rec_base = (const char*)a.comm.recv_payload[a.rank] + (size_t)parity * a.n_ranks * a.payload_bytes;
+  }
+  const int nrow = a.stats_rows ? (int)a.n_stats_rows : a.n_ranks;
+  auto col_sum = [&](int c) -> double {                // statistic c summed over the rows / ranks in order
+    double s = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < nrow; ++r) {
+      double v;
+      if (a.stats_rows) v = (double)a.stats_rows[(size_t)r * len + c];
+      else if (!rec_base) v = a.stats_parts[(size_t)r * a.stats_stride + c];
+      else {
+        const void* q = rec_base + (size_t)r * a.payload_bytes + (size_t)c * 8;
+        unsigned long long w = ld_volatile_u64(q);
+        PeerSpin spin;
+        while (w == kSentinel64) { spin.wait(a.comm.error); w = ld_volatile_u64(q); }
+        v = __longlong_as_double((long long)w);
+      }
+      s += v;
+    }
+    return s;
+  };
+  for (int i = tid; i < len; i += nthr) {
+    const double s = col_sum(i);
+    if (i < LF_STATS_HEADER) s_hdr[i] = s;
+    if (i != LF_STAT_CNT_X1_CAL && i != LF_STAT_CNT_X2_CAL) a.stats[i] = s;
+    if (a.update_ema && i >= LF_STATS_HEADER && i < LF_STATS_HEADER + C) ema_class(a, i - LF_STATS_HEADER, s, col_sum(i + C));
+  }
+  __syncthreads();                                     // every read of the receive slots is behind this barrier
+  if (rec_base) {
+    const size_t n16 = (size_t)a.n_ranks * a.payload_bytes / 16;
+    uint4* q = reinterpret_cast<uint4*>(const_cast<char*>(rec_base));
+    const uint4 ones = make_uint4(kSentinel32, kSentinel32, kSentinel32, kSentinel32);
+#pragma unroll 1
+    for (size_t i = tid; i < n16; i += nthr) q[i] = ones;
+  }
+  if (tid == 0) {
+    if (a.coeff_out) ogm_coeff_write(a, (float)s_hdr[LF_STAT_SCORE_X1], (float)s_hdr[LF_STAT_SCORE_X2]);
+    if (a.loss_out) {
+      if (a.mode == LF_MODE_QMF) {         // ensemble: CE(z1) + CE(z2) (+ CE(z_df) unless ablated), each a separate fp32 mean
+        const double inv = 1.0 / (double)Bg;
+        const float uni = (a.loss_terms & LF_LOSS_NO_UNI) ? 0.f : (float)(s_hdr[LF_STAT_CE_X1] * inv) + (float)(s_hdr[LF_STAT_CE_X2] * inv);
+        const float joint = (a.loss_terms & LF_LOSS_NO_JOINT) ? 0.f : (float)(s_hdr[LF_STAT_CE_JOINT] * inv);
+        a.loss_out[0] = joint + uni;
+      } else {
+        a.loss_out[0] = (float)(s_hdr[LF_STAT_CE_JOINT] / (double)Bg);
+      }
+    }
+    if (a.use_peer) a.comm.epoch[0] = epoch;
+  }
+}
+
 }  // namespace lf
 
 using namespace lf;
@@ -640,7 +683,11 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
   p.minmax = qmf ? (double*)a->workspace : nullptr;
   p.regpart = qmf ? (float*)((char*)a->workspace + 8192) : nullptr;         // minmax: <= 256 x 4 doubles = 8192 B
   p.done = qmf ? (unsigned*)((char*)a->workspace + 8192 + 1024) : nullptr;  // regpart: <= 256 floats
-  const size_t smem = qmf ? 0 : sizeof(double) * (LF_STATS_HEADER + 2 * (size_t)a->classes);
+  p.trace = nullptr;
+  if (!qmf) {
+    LF_LAUNCH("step_mid", s, (mid_light_kernel<<<1, 256, 0, s>>>(p)));
+    return check_launch("lf_step_mid");
+  }
   cudaLaunchConfig_t cfg = {};
   // QMF: one batch position per thread where the grid allows it (the History sweep and larger global batches loop)
   int ncta = 1;
@@ -652,8 +699,8 @@ extern "C" int lf_step_mid(const LfMidArgs* a, void* stream) {
     if (ncta < 1) ncta = 1;
   }
   cfg.gridDim = dim3(ncta, 1, 1);
-  cfg.blockDim = dim3(qmf ? kMidThreads : 256, 1, 1);
-  cfg.dynamicSmemBytes = smem;
+  cfg.blockDim = dim3(kMidThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;      // co-residency of the grid (its barriers spin)

@@ -154,6 +154,7 @@ class LateFusionStep:
         # mean fusion on wide heads: lf_step_mid + the calibrated-count pass beside the dfeat GEMM (see step());
         # LF_NO_CAL_OVERLAP=1 keeps the single-stream order for A/B runs
         self.cal_overlap = not os.environ.get("LF_NO_CAL_OVERLAP")
+        self.cal_overlap_min_classes = 129
         self._side = None
 
     # ------------------------------------------------------------------ fused SGD on the heads
@@ -410,7 +411,10 @@ class LateFusionStep:
         # calibrated-count pass (a second read of the logits: 324 MB at the VGGSound shape) then run on a second stream
         # BESIDE the dfeat GEMM, which leaves half of the HBM bandwidth and most registers of an SM unused, and join
         # before the dW GEMM, whose tail consumes the counts.
-        overlap = (backward and self.cal_overlap and self.mode == LF_MODE_JLOGITS and (self.world == 1 or fuse_ar)
+        # (up to 128 classes the dfeat GEMM is epilogue-bound and wants its second group of epilogue warps, which leaves
+        # no registers for a co-resident CTA, and the count pass is ~10 us: measured 131 us serial vs 136 us at C = 101)
+        overlap = (backward and self.cal_overlap and Cn >= self.cal_overlap_min_classes
+                   and self.mode == LF_MODE_JLOGITS and (self.world == 1 or fuse_ar)
                    and bool(lib.lf_heads_backward_splits_rows(C.byref(a))))
         main_stream = side = None
         if overlap:

@@ -16,6 +16,7 @@ def _run(overlap, prec, B, D, Cn, steps=3, graph=False, sgd=False):
     from multimodal_clinical_b200.step import LateFusionStep
     eng = LateFusionStep(Cn, mode="jlogits", device="cuda:0", precision=prec)
     eng.cal_overlap = overlap
+    eng.cal_overlap_min_classes = 0        # (by default only heads wider than 128 classes take the two-stream order)
     inp = O.make_inputs(B, D, Cn, seed=11)
     W = [inp["W1"].cuda(), inp["W2"].cuda()]
     b = [inp["b1"].cuda(), inp["b2"].cuda()]
