@@ -264,6 +264,14 @@ def run_reference(args, w, rank, world):
 
 
 def workload_config(w, args, world):
+    cfg = _workload_config(w, args, world)
+    if w["mode"] != "qmf" and w["C"] > 128:
+        # mean fusion on wide heads: lf_step_mid + the calibrated-count pass run beside the dfeat GEMM (step.py)
+        cfg["streams"] = "single stream (LF_NO_CAL_OVERLAP)" if os.environ.get("LF_NO_CAL_OVERLAP") else "two (step_mid + calibrated counts beside tc_dfeat)"
+    return cfg
+
+
+def _workload_config(w, args, world):
     return {"workload": f"{args.workload}: {w['desc']}", "head": w["mode"], "batch_per_gpu": w["B"],
             "global_batch": w["B"] * world, "feature_dim": w["D"], "classes": w["C"], "history_len": w["N"],
             "precision": args.precision, "parallelism": f"dp{world}", "scaling": args.scaling, "cuda_graph": not args.no_graph,
