@@ -265,7 +265,7 @@ def run_reference(args, w, rank, world):
 
 def workload_config(w, args, world):
     cfg = _workload_config(w, args, world)
-    if w["mode"] != "qmf" and w["C"] > 128:
+    if w["mode"] != "qmf" and w["C"] > 128 and world == 1:
         # mean fusion on wide heads: lf_step_mid + the calibrated-count pass run beside the dfeat GEMM (step.py)
         cfg["streams"] = "single stream (LF_NO_CAL_OVERLAP)" if os.environ.get("LF_NO_CAL_OVERLAP") else "two (step_mid + calibrated counts beside tc_dfeat)"
     return cfg

@@ -409,12 +409,14 @@ class LateFusionStep:
         # Mean fusion (cremad/joint_model_ogm_ge.py:54-56): dL/dz is final after the forward pass, so the dfeat GEMM does
         # not depend on lf_step_mid; only the calibrated counts need this step's EMA offsets.  lf_step_mid and the
         # calibrated-count pass (a second read of the logits: 324 MB at the VGGSound shape) then run on a second stream
-        # BESIDE the dfeat GEMM, which leaves half of the HBM bandwidth and most registers of an SM unused, and join
-        # before the dW GEMM, whose tail consumes the counts.
+        # BESIDE the dfeat GEMM, whose CTAs leave 39 K registers per SM and part of the HBM bandwidth unused, and join before
+        # the dW GEMM, whose tail consumes the counts (K5: 0.579 -> 0.557 ms; the pair is HBM-bound).
         # (up to 128 classes the dfeat GEMM is epilogue-bound and wants its second group of epilogue warps, which leaves
         # no registers for a co-resident CTA, and the count pass is ~10 us: measured 131 us serial vs 136 us at C = 101)
+        # One GPU only: on a sharded step lf_step_mid polls the peers' statistics, and spinning beside the GEMM cost more than
+        # the overlap gave (two GPUs, K5: 0.663 ms against 0.614 ms single-stream).
         overlap = (backward and self.cal_overlap and Cn >= self.cal_overlap_min_classes
-                   and self.mode == LF_MODE_JLOGITS and (self.world == 1 or fuse_ar)
+                   and self.mode == LF_MODE_JLOGITS and self.world == 1
                    and bool(lib.lf_heads_backward_splits_rows(C.byref(a))))
         main_stream = side = None
         if overlap:
@@ -437,7 +439,9 @@ class LateFusionStep:
         else:
             if hist and idx_in_place and self.world > 1:
                 p_idx.copy_(idx)                                  # fell back to NCCL after all (no peer mapping)
-            gathered = parallel.gather_payload(pay, self.pg)      # (world, payload bytes); identity on one GPU
+            # (world, payload bytes).  An engine that treats its batch as the whole batch (one GPU, or sharded=False under a
+            # DDP wrapper) consumes its own payload: it must not look at the process group, whose rank 0 holds other data
+            gathered = parallel.gather_payload(pay, self.pg) if self.world > 1 else pay
         mid.mode, mid.classes, mid.batch_global, mid.n_ranks = self.mode, Cn, Bg, self.world
         mid.batch_local, mid.rank, mid.n_data, mid.update_ema = B, self.rank, self.n_data or 0, int(update_ema)
         base = gathered.data_ptr()

@@ -83,11 +83,16 @@ def sharded_vs_single(w, precision, dev, rank, world, sgd=False, steps=2, seed=4
     for s in range(steps):
         f1, f2, y, idx = _global_batch(w, Bg, dev, seed, bf16, s)
         o1 = eng_1.step([f1, f2], W1, b1, y, idx=idx, need_dfeat=w["dfeat"], ogm_alpha=w["alpha"])
+        if os.environ.get("LF_PARITY_SYNC"):
+            torch.cuda.synchronize()
         os_ = eng_s.step([f1[sl], f2[sl]], Ws, bs, y[sl], idx=idx[sl] if idx is not None else None, need_dfeat=w["dfeat"],
                          ogm_alpha=w["alpha"])
         torch.cuda.synchronize()
         eng_s.check_peer()
         upd("loss", abs(float(os_.loss) - float(o1.loss)) / max(abs(float(o1.loss)), 1e-30))
+        if os.environ.get("LF_PARITY_VERBOSE"):
+            print(f"[rank {rank}] step {s}: loss single {float(o1.loss):.6g} sharded {float(os_.loss):.6g}  header single "
+                  f"{[round(float(v), 3) for v in o1.stats[:5]]} sharded {[round(float(v), 3) for v in os_.stats[:5]]}", flush=True)
         for m in range(2):
             upd("logits", _rel(os_.logits[m], o1.logits[m][sl]))
             upd("dweight", _rel(os_.dweight[m], o1.dweight[m]))
@@ -178,23 +183,63 @@ def sharded_vs_oracle(w, precision, dev, rank, world, B_small=512, seed=777):
     return err
 
 
+def unsharded_in_group_vs_oracle(w, precision, dev, rank, world, B_small=384, seed=991):
+    """The DDP layout (FusedLateFusionHead under a DDP wrapper): ``sharded=False`` engines inside an initialised process
+    group, every rank with a DIFFERENT batch.  Each must behave like a lone GPU on its own batch -- loss, statistics, EMA and
+    (QMF) the ranking gradients from its own data, never from another rank's -- checked against the CPU oracle on every rank."""
+    from multimodal_clinical_b200.step import LateFusionStep
+    from oracle import late_fusion as O
+    ws = dict(w, B=B_small, N=(4099 if w["N"] else None))
+    bf16 = precision == "bf16"
+    eng = LateFusionStep(ws["C"], mode=ws["mode"], n_data=ws["N"], device=dev, precision=precision, sharded=False)
+    W, b = _heads(ws, dev)
+    rnd = (lambda x: x.bfloat16().float()) if bf16 else (lambda x: x.float())
+    Wc, bc = [rnd(x).cpu() for x in W], [x.cpu() for x in b]
+    hist = O.HistoryState(ws["N"]) if ws["N"] else None
+    ema = torch.zeros(2, ws["C"], dtype=torch.float64)
+    err = {}
+    for s in range(2):
+        f1, f2, y, idx = _global_batch(ws, B_small, dev, seed + 31 * rank, bf16, s)       # rank-specific data
+        out = eng.step([f1, f2], W, b, y, idx=idx, need_dfeat=True, ogm_alpha=ws["alpha"])
+        torch.cuda.synchronize()
+        fc = [f1.float().cpu(), f2.float().cpu()]
+        if ws["mode"] == "qmf":
+            ref = O.qmf_step(fc, Wc, bc, y.cpu(), idx.cpu(), hist, ema_x=ema, dtype=torch.float64)
+        else:
+            ref = O.jlogits_step(fc, Wc, bc, y.cpu(), ema_x=ema, dtype=torch.float64)
+        ema = ref["ema_x"]
+        e = {"loss": abs(float(out.loss) - float(ref["loss"])) / abs(float(ref["loss"])),
+             "dweight": _rel(out.dweight[1].cpu(), ref["dW"][1]), "dfeat": _rel(out.dfeat[0].float().cpu(), ref["dfeat"][0]),
+             "ema_x": _rel(eng.ema_x.cpu(), ref["ema_x"])}
+        for k, v in e.items():
+            err[k] = max(err.get(k, 0.0), v if v == v else float("inf"))
+    if world > 1:
+        keys = sorted(err)
+        t = torch.tensor([err[k] for k in keys], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        err = dict(zip(keys, t.tolist()))
+    return err
+
+
 def run(w, precision, dev, rank, world, sgd):
     """Both checks -> the ``parity_check`` object of bench.py's JSON line (identical on every rank after the reductions)."""
     tol = 1e-5 if precision == "fp32" else 2e-2
     vs1 = sharded_vs_single(w, precision, dev, rank, world, sgd=sgd)
     vso = sharded_vs_oracle(w, precision, dev, rank, world)
+    vsd = unsharded_in_group_vs_oracle(w, precision, dev, rank, world)
     # N ranks vs one GPU: same kernels, different tiling / summation order -> far inside the oracle tolerance
     lim = {"loss": 1e-5, "logits": 1e-6, "dweight": 2e-3 if precision != "fp32" else 1e-5, "dbias": 2e-3 if precision != "fp32" else 1e-5,
            "dfeat": 1e-2 if precision == "bf16" else 1e-5, "stats": 1e-5, "counts_abs": 4.0, "ema_x": 1e-5, "history_correctness": 1e-6,
            "history_confidence": 1e-6, "ogm_coeff": 1e-5, "heads_after_sgd": 1e-4}
     ok1 = vs1["ranks_bit_identical"] and all(v <= lim[k] for k, v in vs1.items() if k in lim)
     oko = all(v <= tol for v in vso.values())
-    flag = torch.tensor([1 if (ok1 and (oko or rank != 0)) else 0], device=dev)
+    okd = all(v <= tol for v in vsd.values())
+    flag = torch.tensor([1 if (ok1 and okd and (oko or rank != 0)) else 0], device=dev)
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     return {"ok": bool(int(flag.item())), "ranks": world, "batch_per_rank": w["B"], "steps": 2, "fused_sgd": bool(sgd),
             "vs_single_gpu_on_concatenated_batch": vs1, "vs_cpu_oracle_small": {k: float(v) for k, v in vso.items()},
-            "oracle_tolerance": tol}
+            "unsharded_engines_in_the_group_vs_cpu_oracle": {k: float(v) for k, v in vsd.items()}, "oracle_tolerance": tol}
 
 
 if __name__ == "__main__":
