@@ -83,8 +83,6 @@ def sharded_vs_single(w, precision, dev, rank, world, sgd=False, steps=2, seed=4
     for s in range(steps):
         f1, f2, y, idx = _global_batch(w, Bg, dev, seed, bf16, s)
         o1 = eng_1.step([f1, f2], W1, b1, y, idx=idx, need_dfeat=w["dfeat"], ogm_alpha=w["alpha"])
-        if os.environ.get("LF_PARITY_SYNC"):
-            torch.cuda.synchronize()
         os_ = eng_s.step([f1[sl], f2[sl]], Ws, bs, y[sl], idx=idx[sl] if idx is not None else None, need_dfeat=w["dfeat"],
                          ogm_alpha=w["alpha"])
         torch.cuda.synchronize()
