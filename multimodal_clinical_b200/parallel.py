@@ -35,9 +35,15 @@ def allreduce_sum_(t: torch.Tensor, pg=None) -> torch.Tensor:
     return t
 
 
-def gather_payload(payload: torch.Tensor, pg=None) -> torch.Tensor:
+def gather_payload(payload: torch.Tensor, pg=None, engine_world: Optional[int] = None) -> torch.Tensor:
     """Every rank's [stats | idx | conf] byte payload -> (world, nbytes), rank-major: the ONE exchange between
-    the forward and the backward pass.  lf_step_mid consumes the rank-major layout directly."""
+    the forward and the backward pass.  lf_step_mid consumes the rank-major layout directly.
+
+    ``engine_world`` is the world size the CALLING ENGINE works with.  An engine that treats its batch as the whole
+    batch (``LateFusionStep(sharded=False)``: the DDP layout) passes 1 and gets its own payload back without any
+    collective, whatever torch.distributed says -- row 0 of a gathered buffer would be rank 0's statistics."""
+    if engine_world is not None and engine_world == 1:
+        return payload
     rank, ws = world(pg)
     if ws == 1:
         return payload

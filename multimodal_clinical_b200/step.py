@@ -441,7 +441,7 @@ class LateFusionStep:
                 p_idx.copy_(idx)                                  # fell back to NCCL after all (no peer mapping)
             # (world, payload bytes).  An engine that treats its batch as the whole batch (one GPU, or sharded=False under a
             # DDP wrapper) consumes its own payload: it must not look at the process group, whose rank 0 holds other data
-            gathered = parallel.gather_payload(pay, self.pg) if self.world > 1 else pay
+            gathered = parallel.gather_payload(pay, self.pg, engine_world=self.world)
         mid.mode, mid.classes, mid.batch_global, mid.n_ranks = self.mode, Cn, Bg, self.world
         mid.batch_local, mid.rank, mid.n_data, mid.update_ema = B, self.rank, self.n_data or 0, int(update_ema)
         base = gathered.data_ptr()

@@ -143,3 +143,41 @@ def test_single_process_helpers_are_identity():
     a, b = parallel.gather_batch(idx, conf)
     assert a is idx and b is conf
     assert parallel.shard_range(3, 128) == (384, 128)
+
+
+def _ddp_layout_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from multimodal_clinical_b200 import parallel
+        pay = torch.full((64,), rank + 1, dtype=torch.uint8)
+        ok = True
+        if rank == 1:
+            # only ONE rank calls: a collective would block until the timeout.  The engine's own world size decides.
+            got = parallel.gather_payload(pay, None, engine_world=1)
+            ok = got is pay
+        dist.barrier()
+        # a sharded engine (engine_world == group size, or not given) still gathers rank-major
+        g = parallel.gather_payload(pay, None, engine_world=world).view(world, -1)
+        ok = ok and bool((g[0] == 1).all()) and bool((g[1] == 2).all())
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_unsharded_engine_inside_a_process_group_keeps_its_own_payload():
+    """The DDP layout (LateFusionStep(sharded=False) while torch.distributed is initialised): lf_step_mid must consume THIS
+    rank's statistics.  parallel.gather_payload used to key on the process group alone and handed back rank 0's row."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_layout_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
