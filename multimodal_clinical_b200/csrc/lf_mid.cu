@@ -589,8 +589,19 @@ __global__ void __launch_bounds__(256, 1) mid_light_kernel(MidParams p) {
   const int nrow = a.stats_rows ? (int)a.n_stats_rows : a.n_ranks;
   auto col_sum = [&](int c) -> double {                // statistic c summed over the rows / ranks in order
     double s = 0.0;
+    int r = 0;
+    if (a.stats_rows) {
+      // per-CTA rows of a fused forward (up to 296 of them): eight loads in flight, added in row order
+      for (; r + 8 <= nrow; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = a.stats_rows[(size_t)(r + u) * len + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+      }
+    }
 #pragma unroll 1
-    for (int r = 0; r < nrow; ++r) {
+    for (; r < nrow; ++r) {
       double v;
       if (a.stats_rows) v = (double)a.stats_rows[(size_t)r * len + c];
       else if (!rec_base) v = a.stats_parts[(size_t)r * a.stats_stride + c];

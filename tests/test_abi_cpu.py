@@ -95,6 +95,33 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
     assert lib.lf_ogm_modulate(C.byref(tl), None, 2, 0, 0, None, 0, None) == 0
 
 
+def test_capability_queries_are_pure_host_functions(lib):
+    """lf_heads_backward_splits_rows / lf_heads_backward_fuses_allreduce decide the step's launch plan on the host (no CUDA
+    call): narrow heads and the fused QMF backward form dL/dz inside one kernel (no bwd_phase 3 / 4), wide mean-fusion heads
+    take the row kernel as a separate phase, and the dW tail (with the fused all-reduce) exists where the tiles fit one wave."""
+    from multimodal_clinical_b200 import _lib
+    a = _lib.LfHeadsArgs()
+    assert lib.lf_heads_backward_splits_rows(None) == 0 and lib.lf_heads_backward_splits_rows(C.byref(a)) == 0
+    a.batch, a.batch_global, a.dim, a.classes, a.need_dfeat = 256, 256, 512, 6, 1
+    a.mode, a.precision = _lib.LF_MODE_JLOGITS, _lib.LF_PREC_FP32
+    assert lib.lf_heads_backward_splits_rows(C.byref(a)) == 0          # K2 / K3: one fused FMA pass
+    assert lib.lf_heads_backward_fuses_allreduce(C.byref(a)) == 0
+    a.classes, a.dim, a.mode, a.precision = 101, 768, _lib.LF_MODE_QMF, _lib.LF_PREC_BF16
+    a.batch = a.batch_global = 32768
+    a.ld_logits, a.ld_dlogits = 104, 104
+    assert lib.lf_heads_backward_splits_rows(C.byref(a)) == 0          # K4: tc_backward_qmf forms dL/dz itself
+    assert lib.lf_heads_backward_fuses_allreduce(C.byref(a)) == 1
+    a.mode = _lib.LF_MODE_JLOGITS                                      # Food101 mean fusion: stand-alone row kernels
+    assert lib.lf_heads_backward_splits_rows(C.byref(a)) == 1
+    a.classes, a.dim, a.ld_logits, a.ld_dlogits = 309, 512, 312, 312   # K5
+    a.batch = a.batch_global = 131072
+    assert lib.lf_heads_backward_splits_rows(C.byref(a)) == 1
+    assert lib.lf_heads_backward_fuses_allreduce(C.byref(a)) == 1
+    a.bwd_phase = 5                                                    # phases are 0 .. 4
+    a.precision = _lib.LF_PREC_TF32
+    assert lib.lf_heads_backward(C.byref(a), None) != 0
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from multimodal_clinical_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
