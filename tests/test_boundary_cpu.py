@@ -171,3 +171,24 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert "workload" in line["config"] and line["config"]["workload"].startswith("k2")
+
+
+def test_bench_algorithmic_bytes_follow_survey_8d():
+    """roofline.achieved / step_roofline rest on these figures: SURVEY.md 8(d) per-sample bytes (fp32), the two-pass QMF step
+    adding one more read of the features, bf16 halving the feature / dfeat terms."""
+    import bench
+    W = bench.WORKLOADS
+    assert bench.step_alg_bytes_per_sample(W["k3"]) == 8272                       # 4096 + 4096 + 72 + 8
+    assert bench.step_alg_bytes_per_sample(W["k5"]) == 11908                      # 4096 + 4096 + 3708 + 8
+    one_pass_k4 = 6144 + 6144 + 1616 + 16
+    assert one_pass_k4 == 13920
+    assert bench.step_alg_bytes_per_sample(W["k4"]) == one_pass_k4 + 2 * 768 * 4  # two-pass: + M D 4 = 20 064
+    assert bench.step_alg_bytes_per_sample(W["k4"], fe=2) == 10848                # the figure of the default (bf16) bench line
+    assert bench.step_alg_bytes_per_sample(W["k2"]) == 8304 + 2 * 512 * 4
+    # per-launch bytes of the K4 bf16 kernels: every input read once, every output written once
+    B, D, C = W["k4"]["B"], W["k4"]["D"], W["k4"]["C"]
+    fwd = bench.kernel_alg_bytes("tc_forward_qmf", W["k4"], B, fe=2)
+    assert fwd == (2 * B * D + 2 * C * D) * 2 + (4 * B * C + 6 * B) * 4 + 8 * B == 154975232
+    dw = bench.kernel_alg_bytes("tc_dweight", W["k4"], B, fe=2)
+    assert dw == (2 * B * 104 + 2 * B * D) * 2 + 2 * C * D * 4 == 114915328
+    assert bench.kernel_alg_bytes("no_such_kernel", W["k4"], B) is None
