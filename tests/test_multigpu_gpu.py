@@ -1,6 +1,7 @@
 """Sharded (multi-GPU) parity, run by pytest when the box has at least two GPUs: N ranks under torchrun must reproduce one
 GPU running the concatenated batch (replicated EMA / History / heads bit-identical across ranks, gradients to rounding)
-and the CPU oracle on a small problem.  The checker is tools/parity_multigpu.py -- the same code bench.py runs before it
+and the CPU oracle on a small problem; and the DDP layout -- unsharded engines inside the process group, a different batch on
+every rank -- must behave like lone GPUs (each against the oracle on its own data).  The checker is tools/parity_multigpu.py -- the same code bench.py runs before it
 times anything (``parity_check`` in its JSON line), so the driver's scaling runs carry the same evidence."""
 import json
 import os
@@ -29,6 +30,8 @@ def test_two_ranks_match_one_gpu_and_the_oracle(workload, batch):
     rc, res = _torchrun(2, "--workload", workload, "--batch", str(batch))
     assert rc == 0 and res["ok"], res
     assert res["vs_single_gpu_on_concatenated_batch"]["ranks_bit_identical"]
+    tol = res["oracle_tolerance"]
+    assert all(v <= tol for v in res["unsharded_engines_in_the_group_vs_cpu_oracle"].values()), res
 
 
 def test_parity_checker_on_one_gpu():
